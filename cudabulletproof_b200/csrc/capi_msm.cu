@@ -1,0 +1,186 @@
+// capi_msm.cu — C ABI for the MSM path: device-resident bpk_msm_device and the host-pointer
+// drop-ins cuda_point_vector_multi_scalar_mul{,_shared} (reference cuda_bulletproof_kernels.cu:62-207).
+#include <stdio.h>
+#include "../../include/cuda_bulletproof.h"
+#include "common.h"
+#include "ge25519.cuh"
+#include "msm.h"
+
+namespace cbp {
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_last_error{0};
+std::atomic<int> g_last_cuda_error{0};
+
+// sum of `count` extended points by one warp (lane-strided partial sums, shuffle tree)
+__global__ void point_sum_kernel(const uint8_t* __restrict__ pts, size_t count, int normalize,
+                                 uint8_t* __restrict__ out) {
+    int lane = threadIdx.x;
+    ge_p3 acc;
+    ge_p3_0(acc);
+    for (size_t i = lane; i < count; i += 32) {
+        ge_p3 q;
+        ge_load(q, pts + i * 128);
+        ge_add(acc, acc, q);
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        ge_p3 other;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            other.X.v[j] = __shfl_down_sync(0xffffffffu, acc.X.v[j], o);
+            other.Y.v[j] = __shfl_down_sync(0xffffffffu, acc.Y.v[j], o);
+            other.Z.v[j] = __shfl_down_sync(0xffffffffu, acc.Z.v[j], o);
+            other.T.v[j] = __shfl_down_sync(0xffffffffu, acc.T.v[j], o);
+        }
+        ge_add(acc, acc, other);
+    }
+    if (lane == 0) {
+        if (normalize) ge_normalize(acc);
+        ge_store(out, acc);
+    }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ ge_p3 basepoint() {
+    ge_p3 B;
+    B.X = fe{{0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u}};
+    B.Y = fe{{0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u}};
+    fe_set1(B.Z);
+    fe_mul(B.T, B.X, B.Y);
+    return B;
+}
+__global__ void __launch_bounds__(128) synth_points_kernel(uint8_t* __restrict__ pts, uint64_t* __restrict__ ks,
+                                                           size_t n, uint64_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = splitmix64(seed ^ splitmix64(i)) | 1ull;
+    uint32_t kw[2] = {(uint32_t)k, (uint32_t)(k >> 32)};
+    ge_p3 B = basepoint(), r;
+    ge_scalarmult_bits(r, kw, 64, B);
+    ge_normalize(r);
+    ge_store(pts + i * 128, r);
+    if (ks) ks[i] = k;
+}
+__global__ void synth_scalars_kernel(uint64_t* __restrict__ out, size_t n, uint64_t seed, int bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = splitmix64(seed ^ (0xA5A5A5A5ull + i * 4));
+    for (int j = 0; j < 4; j++) {
+        s = splitmix64(s + j);
+        int lo = j * 64;
+        uint64_t v = s;
+        if (bits <= lo) v = 0;
+        else if (bits < lo + 64) v &= (~0ull) >> (lo + 64 - bits);
+        out[i * 4 + j] = v;
+    }
+}
+}  // namespace cbp
+
+using namespace cbp;
+
+extern "C" {
+
+const char* bpk_version(void) { return "cudabulletproof_b200 0.1 (sm_100a)"; }
+int bpk_last_error(void) { return g_last_error.load(); }
+int bpk_last_cuda_error(void) { return g_last_cuda_error.load(); }
+uint64_t bpk_kernel_launches(void) { return g_launches.load(); }
+
+int bpk_msm_window_bits(size_t n) { return msm_pick_window(n); }
+int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes) {
+    if (!bytes || window_bits < 0 || window_bits > 16 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
+        return fail(BPK_ERR_ARG);
+    MsmPlan p;
+    msm_make_plan(&p, n, window_bits);
+    *bytes = p.workspace_bytes;
+    return BPK_OK;
+}
+int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* d_result, void* d_workspace,
+                   size_t workspace_bytes, int window_bits, int normalize, void* stream) {
+    if (!d_result || (n && (!d_scalars || !d_points || !d_workspace))) return fail(BPK_ERR_ARG);
+    if (window_bits < 0 || window_bits > 16 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
+        return fail(BPK_ERR_ARG);
+    MsmPlan p;
+    msm_make_plan(&p, n, window_bits);
+    if (n && workspace_bytes < p.workspace_bytes) return fail(BPK_ERR_WORKSPACE);
+    int launches = 0;
+    int rc = msm_run(p, d_scalars, d_points, d_result, d_workspace, normalize, (cudaStream_t)stream, &launches);
+    count_launches(launches);
+    return fail_cuda(rc);
+}
+int bpk_point_sum_device(const void* d_points, size_t count, void* d_result, int normalize, void* stream) {
+    if (!d_result || (count && !d_points)) return fail(BPK_ERR_ARG);
+    point_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const uint8_t*)d_points, count, normalize, (uint8_t*)d_result);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+int bpk_synth_points_device(void* d_points, uint64_t* d_k, size_t n, uint64_t seed, void* stream) {
+    if (n && !d_points) return fail(BPK_ERR_ARG);
+    if (!n) return BPK_OK;
+    synth_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint8_t*)d_points, d_k, n, seed);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+int bpk_synth_scalars_device(void* d_scalars, size_t n, uint64_t seed, int bits, void* stream) {
+    if ((n && !d_scalars) || bits < 1 || bits > 256) return fail(BPK_ERR_ARG);
+    if (!n) return BPK_OK;
+    synth_scalars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint64_t*)d_scalars, n, seed, bits);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+// ---- host-pointer drop-ins --------------------------------------------------------------------
+static int msm_host(ge25519* result, const FieldVector* scalars, const PointVector* points) {
+    size_t n = scalars->length;
+    MsmPlan p;
+    msm_make_plan(&p, n, 0);
+    uint8_t *d_s = nullptr, *d_p = nullptr, *d_ws = nullptr, *d_r = nullptr;
+    cudaStream_t st = 0;
+    int rc = BPK_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_r, 128)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+    if (n) {
+        if ((e = cudaMalloc(&d_s, n * 32)) != cudaSuccess || (e = cudaMalloc(&d_p, n * 128)) != cudaSuccess ||
+            (e = cudaMalloc(&d_ws, p.workspace_bytes)) != cudaSuccess) {
+            rc = fail(BPK_ERR_CUDA, e);
+            goto done;
+        }
+        if ((e = cudaMemcpyAsync(d_s, scalars->elements, n * 32, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_p, points->elements, n * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+            rc = fail(BPK_ERR_CUDA, e);
+            goto done;
+        }
+    }
+    rc = bpk_msm_device(d_s, d_p, n, d_r, d_ws, p.workspace_bytes, p.c, 1, st);
+    if (rc == BPK_OK) {
+        ge25519 tmp;
+        e = cudaMemcpyAsync(&tmp, d_r, 128, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(BPK_ERR_CUDA, e);
+        else *result = tmp;
+    }
+done:
+    cudaFree(d_s);
+    cudaFree(d_p);
+    cudaFree(d_ws);
+    cudaFree(d_r);
+    return rc;
+}
+
+void cuda_point_vector_multi_scalar_mul(ge25519* result, const FieldVector* scalars, const PointVector* points) {
+    if (scalars->length != points->length) {  // cuda_bulletproof_kernels.cu:65-68: message, result untouched
+        fprintf(stderr, "Error: Vector lengths must match for multi-scalar multiplication\n");
+        fail(BPK_ERR_ARG);
+        return;
+    }
+    msm_host(result, scalars, points);
+}
+void cuda_point_vector_multi_scalar_mul_shared(ge25519* result, const FieldVector* scalars, const PointVector* points) {
+    cuda_point_vector_multi_scalar_mul(result, scalars, points);
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// microbench.cu — standalone integer-pipe microbenchmarks for B200 (not part of the library).
+// Measures the roofline denominators DESIGN.md uses for the IMAD-bound kernels:
+//   imad_wide_indep : independent IMAD.WIDE.U32 chains            -> peak IMAD.WIDE issue rate
+//   imad_lo_indep   : independent 32-bit IMAD chains              -> peak IMAD issue rate
+//   imad_wide_carry : mad.lo.cc/madc.hi.cc carry chains (fe_mul's inner pattern)
+//   fe_mul / fe_sq / ge_madd / ge_dbl : sustained field / group operation rates
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o microbench microbench.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "ge25519.cuh"
+using namespace cbp;
+
+#define ITERS 4096
+
+__global__ void __launch_bounds__(256) k_imad_wide_indep(uint64_t* out, uint32_t a, uint32_t b) {
+    uint64_t acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
+    uint32_t x = a + threadIdx.x, y = b;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = (uint64_t)x * y + acc[i];
+        x = (uint32_t)acc[0];  // keep operands live / varying
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_imad_lo_indep(uint32_t* out, uint32_t a, uint32_t b) {
+    uint32_t acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
+    uint32_t x = a + threadIdx.x, y = b;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = x * y + acc[i];
+        x = acc[0];
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_imad_wide_carry(uint32_t* out, uint32_t a, uint32_t b) {
+    uint32_t c[9], d[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { c[i] = threadIdx.x + i; d[i] = threadIdx.x * 3 + i; }
+    uint32_t x0 = a + threadIdx.x, x1 = a ^ 0x55, x2 = a + 7, x3 = a * 3, y = b;
+    for (int it = 0; it < ITERS; it++) {
+        mad_row4(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], x0, x1, x2, x3, y);
+        mad_row4(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], x1, x2, x3, x0, y);
+        y = c[0] ^ d[1];
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) s ^= c[i] ^ d[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_fe_mul(uint32_t* out, uint32_t seed) {
+    fe a, b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.v[i] = seed * (i + 1) + threadIdx.x; b.v[i] = seed ^ (i * 77 + blockIdx.x); }
+    for (int it = 0; it < ITERS / 4; it++) {
+        fe_mul(a, a, b);
+        fe_mul(b, b, a);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a.v[0] ^ b.v[3];
+}
+__global__ void __launch_bounds__(256) k_fe_sq(uint32_t* out, uint32_t seed) {
+    fe a, b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.v[i] = seed * (i + 1) + threadIdx.x; b.v[i] = seed ^ (i * 77 + blockIdx.x); }
+    for (int it = 0; it < ITERS / 4; it++) {
+        fe_sq(a, a);
+        fe_sq(b, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a.v[0] ^ b.v[3];
+}
+__global__ void __launch_bounds__(128, 4) k_ge_madd(uint32_t* out, uint32_t seed) {
+    ge_p3 p;
+    ge_niels q;
+    ge_p3_0(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        p.X.v[i] = seed + i + threadIdx.x;
+        q.yplusx.v[i] = seed * 3 + i;
+        q.yminusx.v[i] = seed * 5 + i + blockIdx.x;
+        q.xy2d.v[i] = seed * 7 + i;
+    }
+    for (int it = 0; it < ITERS / 16; it++) ge_madd(p, p, q, (it & 1) != 0);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = p.X.v[0] ^ p.T.v[1] ^ p.Y.v[2] ^ p.Z.v[3];
+}
+__global__ void __launch_bounds__(128, 4) k_ge_dbl(uint32_t* out, uint32_t seed) {
+    ge_p3 p;
+    ge_p3_0(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { p.X.v[i] = seed + i + threadIdx.x; p.Y.v[i] = seed * 9 + blockIdx.x; }
+    for (int it = 0; it < ITERS / 16; it++) ge_dbl(p, p);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = p.X.v[0] ^ p.T.v[1] ^ p.Y.v[2] ^ p.Z.v[3];
+}
+
+template <typename F>
+static double time_ms(F launch, int reps) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch();
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; i++) launch();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms / reps;
+}
+
+int main() {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    int sms = prop.multiProcessorCount;
+    void* buf;
+    cudaMalloc(&buf, (size_t)sms * 64 * 256 * 8);
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, sms, prop.clockRate);
+    for (int bps = 1; bps <= 8; bps *= 2) {
+        int grid = sms * bps;
+        double threads = (double)grid * 256;
+        double ms;
+        ms = time_ms([&] { k_imad_wide_indep<<<grid, 256>>>((uint64_t*)buf, 12345, 6789); }, 5);
+        printf("{\"bench\": \"imad_wide_indep\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Tops\": %.3f}\n", bps, ms,
+               threads * ITERS * 8 / ms / 1e9);
+        ms = time_ms([&] { k_imad_lo_indep<<<grid, 256>>>((uint32_t*)buf, 12345, 6789); }, 5);
+        printf("{\"bench\": \"imad_lo_indep\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Tops\": %.3f}\n", bps, ms,
+               threads * ITERS * 8 / ms / 1e9);
+        ms = time_ms([&] { k_imad_wide_carry<<<grid, 256>>>((uint32_t*)buf, 12345, 6789); }, 5);
+        printf("{\"bench\": \"imad_wide_carry\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Tops\": %.3f}\n", bps, ms,
+               threads * ITERS * 8 / ms / 1e9);  // 2 rows x 4 wide multiply-adds
+        ms = time_ms([&] { k_fe_mul<<<grid, 256>>>((uint32_t*)buf, 99); }, 5);
+        printf("{\"bench\": \"fe_mul\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Gops\": %.2f, \"imad_Tops\": %.3f}\n", bps, ms,
+               threads * (ITERS / 2) / ms / 1e6, threads * (ITERS / 2) * 72 / ms / 1e9);
+        ms = time_ms([&] { k_fe_sq<<<grid, 256>>>((uint32_t*)buf, 99); }, 5);
+        printf("{\"bench\": \"fe_sq\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Gops\": %.2f}\n", bps, ms,
+               threads * (ITERS / 2) / ms / 1e6);
+    }
+    for (int bps = 1; bps <= 4; bps *= 2) {
+        int grid = sms * bps;
+        double threads = (double)grid * 128;
+        double ms = time_ms([&] { k_ge_madd<<<grid, 128>>>((uint32_t*)buf, 99); }, 5);
+        printf("{\"bench\": \"ge_madd\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Gops\": %.3f, \"imad_Tops\": %.3f}\n", bps, ms,
+               threads * (ITERS / 16) / ms / 1e6, threads * (ITERS / 16) * 504 / ms / 1e9);
+        ms = time_ms([&] { k_ge_dbl<<<grid, 128>>>((uint32_t*)buf, 99); }, 5);
+        printf("{\"bench\": \"ge_dbl\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Gops\": %.3f}\n", bps, ms,
+               threads * (ITERS / 16) / ms / 1e6);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
+    return 0;
+}

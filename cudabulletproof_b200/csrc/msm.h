@@ -1,0 +1,25 @@
+// msm.h — host-side plan/launcher for the Pippenger MSM (msm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace cbp {
+
+struct MsmPlan {
+    size_t n;           // number of (scalar, point) pairs
+    int c;              // window width in bits (signed digits)
+    int W;              // number of windows = ceil(256 / c)
+    uint32_t B;         // buckets per window = 2^(c-1)
+    uint32_t nbuckets;  // W * B
+    size_t off_table, off_counts, off_offsets, off_cursors, off_tiles, off_entries, off_buckets;
+    size_t off_redX[2], off_redY[2];
+    size_t workspace_bytes;
+};
+
+int msm_pick_window(size_t n);
+void msm_make_plan(MsmPlan* p, size_t n, int c /* 0 = auto */);
+int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
+            int normalize, cudaStream_t stream, int* launches);
+
+}  // namespace cbp

@@ -1,0 +1,161 @@
+"""Host-side mirror of the reference operator interface over the C ABI.
+
+Two layers, same names as the reference where one exists:
+  * numpy-in / numpy-out wrappers of the host-pointer drop-ins (cuda_bulletproof.h), used by the
+    parity tests so they read like the reference's own call sites;
+  * torch-tensor wrappers of the device-resident API (bpk.h): torch is only the allocator and the
+    stream provider here — every computation is a kernel of libcudabulletproof_b200.so.
+fe25519 arrays are (n, 4) uint64; ge25519 arrays are (n, 16) uint64 (X,Y,Z,T)."""
+import ctypes as C
+
+import numpy as np
+
+
+def _lib():
+    from . import load
+    return load()
+
+
+def _check(rc, what):
+    from . import check
+    check(rc, what)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fv(a):
+    from . import FieldVector
+    return FieldVector(a.ctypes.data, a.shape[0])
+
+
+def _pv(a):
+    from . import PointVector
+    return PointVector(a.ctypes.data, a.shape[0])
+
+
+def _c(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.ndim == 2 and a.shape[1] == cols, a.shape
+    return a
+
+
+# ---------------- host-pointer drop-ins (reference cuda_bulletproof.h) ----------------
+def cuda_point_vector_multi_scalar_mul(scalars, points, shared=False, result=None):
+    """result = sum scalars[i]*points[i]; returns the (16,) uint64 ge25519 (normalised)."""
+    s, p = _c(scalars, 4), _c(points, 16)
+    out = np.zeros(16, dtype=np.uint64) if result is None else result
+    fv, pv = _fv(s), _pv(p)
+    fn = _lib().cuda_point_vector_multi_scalar_mul_shared if shared else _lib().cuda_point_vector_multi_scalar_mul
+    fn(_ptr(out), C.byref(fv), C.byref(pv))
+    return out
+
+
+def cuda_field_vector_inner_product(a, b, shared=False, result=None):
+    a, b = _c(a, 4), _c(b, 4)
+    out = np.zeros(4, dtype=np.uint64) if result is None else result
+    fa, fb = _fv(a), _fv(b)
+    fn = _lib().cuda_field_vector_inner_product_shared if shared else _lib().cuda_field_vector_inner_product
+    fn(_ptr(out), C.byref(fa), C.byref(fb))
+    return out
+
+
+def _batch2(name, a, b):
+    a, b = _c(a, 4), _c(b, 4)
+    out = np.zeros_like(a)
+    getattr(_lib(), name)(_ptr(out), _ptr(a), _ptr(b), a.shape[0])
+    return out
+
+
+def cuda_batch_field_add(a, b):
+    return _batch2("cuda_batch_field_add", a, b)
+
+
+def cuda_batch_field_sub(a, b):
+    return _batch2("cuda_batch_field_sub", a, b)
+
+
+def cuda_batch_field_mul(a, b):
+    return _batch2("cuda_batch_field_mul", a, b)
+
+
+def cuda_soa_field_add(a, b):
+    return _batch2("cuda_soa_field_add", a, b)
+
+
+def cuda_batch_field_square(a):
+    a = _c(a, 4)
+    out = np.zeros_like(a)
+    _lib().cuda_batch_field_square(_ptr(out), _ptr(a), a.shape[0])
+    return out
+
+
+def cuda_batch_field_invert(a):
+    a = _c(a, 4)
+    out = np.zeros_like(a)
+    _lib().cuda_batch_field_invert(_ptr(out), _ptr(a), a.shape[0])
+    return out
+
+
+# ---------------- device-resident API (bpk.h) on torch tensors ----------------
+def _stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _dev_u8(nbytes, device):
+    import torch
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+class Msm:
+    """Pippenger MSM with a reusable workspace: result = sum_i scalars[i] * points[i].
+
+    scalars: cuda uint8 tensor (n, 32); points: cuda uint8 tensor (n, 128) (reference AoS ge25519)."""
+
+    def __init__(self, n, device="cuda", window_bits=0):
+        import torch
+        self.n, self.device = int(n), torch.device(device)
+        lib = _lib()
+        self.window_bits = window_bits or lib.bpk_msm_window_bits(self.n)
+        nbytes = C.c_size_t(0)
+        _check(lib.bpk_msm_workspace_bytes(self.n, self.window_bits, C.byref(nbytes)), "bpk_msm_workspace_bytes")
+        self.workspace = _dev_u8(nbytes.value, self.device)
+        self.result = torch.zeros(128, dtype=torch.uint8, device=self.device)
+
+    def __call__(self, scalars, points, normalize=True, out=None, stream=None):
+        out = self.result if out is None else out
+        assert scalars.is_cuda and points.is_cuda and scalars.numel() == self.n * 32 and points.numel() == self.n * 128
+        _check(_lib().bpk_msm_device(scalars.data_ptr(), points.data_ptr(), self.n, out.data_ptr(),
+                                     self.workspace.data_ptr(), self.workspace.numel(), self.window_bits,
+                                     1 if normalize else 0, _stream_ptr(stream)), "bpk_msm_device")
+        return out
+
+
+def point_sum(points, normalize=True, stream=None):
+    """Sum of extended points (count, 128) uint8 on device -> (128,) uint8."""
+    import torch
+    out = torch.zeros(128, dtype=torch.uint8, device=points.device)
+    _check(_lib().bpk_point_sum_device(points.data_ptr(), points.numel() // 128, out.data_ptr(),
+                                       1 if normalize else 0, _stream_ptr(stream)), "bpk_point_sum_device")
+    return out
+
+
+def synth_points(n, seed, device="cuda", stream=None):
+    """P_i = k_i * B (normalised) and the 64-bit k_i: (n,128) uint8, (n,) int64 tensors."""
+    import torch
+    pts = torch.empty((n, 128), dtype=torch.uint8, device=device)
+    ks = torch.empty(n, dtype=torch.int64, device=device)
+    _check(_lib().bpk_synth_points_device(pts.data_ptr(), ks.data_ptr(), n, seed, _stream_ptr(stream)),
+           "bpk_synth_points_device")
+    return pts, ks
+
+
+def synth_scalars(n, seed, bits=252, device="cuda", stream=None):
+    import torch
+    sc = torch.empty((n, 32), dtype=torch.uint8, device=device)
+    _check(_lib().bpk_synth_scalars_device(sc.data_ptr(), n, seed, bits, _stream_ptr(stream)),
+           "bpk_synth_scalars_device")
+    return sc

@@ -1,0 +1,95 @@
+/*
+ * bpk.h — device-resident C ABI of libcudabulletproof_b200.so ("bpk" = bulletproof kernels).
+ *
+ * The reference's entry points (cuda_bulletproof.h) take host arrays and malloc/copy/sync per call
+ * (cuda_bulletproof_kernels.cu:77-115), which is PCIe-bound at 2^20 points.  These functions are
+ * the same operations on buffers already resident in HBM: plain device pointers and sizes, an
+ * explicit cudaStream_t (passed as void*), caller-provided workspace, int status, no allocation,
+ * no synchronisation, no printing.  The host-pointer drop-ins are thin wrappers over these.
+ *
+ * Layouts: fe25519 / scalars = 32 B little-endian; ge25519 = 128 B (X,Y,Z,T), arrays are AoS
+ * exactly as the reference's FieldVector / PointVector elements.
+ */
+#ifndef CBP_BPK_H
+#define CBP_BPK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPK_OK 0
+#define BPK_ERR_ARG 1
+#define BPK_ERR_CUDA 2
+#define BPK_ERR_WORKSPACE 3
+
+const char* bpk_version(void);
+/* last error recorded by any entry point of this library in this process (0 = none) */
+int bpk_last_error(void);
+int bpk_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t bpk_kernel_launches(void);
+
+/* ---- multi-scalar multiplication: replaces cuda_point_vector_multi_scalar_mul (cuda_bulletproof.h:13) ---- */
+/* window_bits = 0 picks c(n).  *bytes = workspace needed by bpk_msm_device for that (n, window_bits). */
+int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes);
+int bpk_msm_window_bits(size_t n);
+/* d_result: one ge25519 (128 B); normalize != 0 returns (x, y, 1, xy) canonical like the CPU MSM */
+int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* d_result, void* d_workspace,
+                   size_t workspace_bytes, int window_bits, int normalize, void* stream);
+/* sum of `count` extended points (multi-GPU partial results), normalised: d_result = sum d_points[i] */
+int bpk_point_sum_device(const void* d_points, size_t count, void* d_result, int normalize, void* stream);
+
+/* ---- batched fe25519: replaces cuda_batch_field_{add,sub,mul,square,invert} (cuda_bulletproof.h:31-50) ---- */
+#define BPK_FE_ADD 0
+#define BPK_FE_SUB 1
+#define BPK_FE_MUL 2
+#define BPK_FE_SQR 3
+int bpk_fe_batch_device(int op, void* d_out, const void* d_a, const void* d_b, size_t count, void* stream);
+int bpk_fe_batch_invert_workspace_bytes(size_t count, size_t* bytes);
+int bpk_fe_batch_invert_device(void* d_out, const void* d_in, size_t count, void* d_workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* ---- scalars mod l: replaces cuda_field_vector_inner_product (cuda_bulletproof.h:22) ---- */
+int bpk_sc_inner_product_workspace_bytes(size_t n, size_t* bytes);
+int bpk_sc_inner_product_device(void* d_out, const void* d_a, const void* d_b, size_t n, void* d_workspace,
+                                size_t workspace_bytes, void* stream);
+/* num_vectors independent inner products of length n each (contiguous): cuda_inner_product.cu:302 */
+int bpk_sc_inner_product_batch_device(void* d_out, const void* d_a, const void* d_b, size_t n, size_t num_vectors,
+                                      void* stream);
+
+/* ---- IPA folding (bulletproof_vectors.cu:488-500 and :641-663) ---- */
+/* a' = u a_L + u^-1 a_R ; b' = u^-1 b_L + u b_R  (mod l);  in/out may alias (in place on the low half) */
+int bpk_ipa_fold_scalars_device(void* d_a_out, void* d_b_out, const void* d_a, const void* d_b, size_t n_half,
+                                const void* d_u, const void* d_u_inv, void* stream);
+/* G'_j = u^-1 G_j + u G_{j+n'} ; H'_j = u H_j + u^-1 H_{j+n'} ; outputs normalised */
+int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, const void* d_H, size_t n_half,
+                               const void* d_u, const void* d_u_inv, void* stream);
+
+/* ---- range proofs: replaces cuda_range_proof_verify (cuda_bulletproof.h:61) on batches ---- */
+/* Flat proof record, uint64 words (n-bit proof, k = log2 n):
+ *   V,A,S,T1,T2 (5 x 128 B) | taux,mu,t (3 x 32 B) | a,b,c,x (4 x 32 B) | L[0..k) (k x 128 B) | R[0..k) (k x 128 B) */
+size_t bpk_proof_record_bytes(size_t n);
+/* generator set shared by every proof: G[n], H[n], g, h (ge25519, AoS).  Builds device tables. */
+int bpk_gens_workspace_bytes(size_t n, size_t* bytes);
+int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
+                         const void* d_h, size_t n, void* stream);
+/* d_accept[i] = 1 iff proof i verifies (exact checks).  One CTA per proof. */
+int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, size_t n, size_t num_proofs,
+                                  uint8_t* d_accept, void* stream);
+/* deterministic batch prover used to synthesise benchmark inputs: values[i] < 2^n, seeds[i] */
+int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const uint64_t* d_seeds, size_t n,
+                                 size_t num_proofs, void* d_proofs, void* stream);
+
+/* ---- synthetic inputs (bench / tests): P_i = k_i * B for a hash-derived 64-bit k_i, returned
+ * normalised, plus k_i itself so that callers can check MSMs against a scalar identity ---- */
+int bpk_synth_points_device(void* d_points, uint64_t* d_k, size_t n, uint64_t seed, void* stream);
+/* uniform `bits`-bit integers (bits <= 256; 252 gives reduced scalars < l), 32 B little-endian each */
+int bpk_synth_scalars_device(void* d_scalars, size_t n, uint64_t seed, int bits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

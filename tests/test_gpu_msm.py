@@ -1,0 +1,138 @@
+"""GPU parity: Pippenger MSM vs the CPU oracle's naive MSM (bulletproof_vectors.cu:189-224 restated),
+through the host-pointer drop-in cuda_point_vector_multi_scalar_mul, plus size-independent checks
+at BASELINE.json's full size (2^20) through the device-resident API."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from oracle import pyref
+
+pytestmark = pytest.mark.gpu
+
+P, L = pyref.P, pyref.L
+
+
+def oracle_msm(oracle, sc, pts):
+    out = np.zeros(16, dtype=np.uint64)
+    fv, pv = ob.field_vector(sc), ob.point_vector(pts)
+    oracle.point_vector_multi_scalar_mul(ob.ptr(out), C.byref(fv), C.byref(pv))
+    return out
+
+
+def curve_points(rng, n):
+    base = pyref.pt_mul(rng.getrandbits(64) | 1, pyref.B)
+    step = pyref.pt_mul(rng.getrandbits(64) | 1, pyref.B)
+    pts, cur = [], base
+    for _ in range(n):
+        pts.append(cur)
+        cur = pyref.pt_add(cur, step)
+    return pts
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 64, 147, 300])
+def test_msm_matches_oracle_random(oracle, n):
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(1000 + n)
+    sc = ob.ints_to_fe([rng.getrandbits(256) for _ in range(n)])
+    pts = np.stack([ob.affine_to_ge(*p) for p in curve_points(rng, n)])
+    for shared in (False, True):
+        got = cbp.cuda_point_vector_multi_scalar_mul(sc, pts, shared=shared)
+        assert np.array_equal(got, oracle_msm(oracle, sc, pts))
+
+
+def test_msm_edge_scalars_and_points(oracle):
+    """SURVEY.md §8d C3 edge suite: special scalars, all-equal scalars/points, (P,-P), identity, torsion."""
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(7)
+    special = [0, 1, L - 1, L, 2**252, 2**255 - 20, 2**255 - 19, 2**256 - 1, 2**255, 2**16, 2**16 - 1, 2**15, 2**15 + 1]
+    pts = curve_points(rng, len(special))
+    sc = ob.ints_to_fe(special)
+    pv = np.stack([ob.affine_to_ge(*p) for p in pts])
+    assert np.array_equal(cbp.cuda_point_vector_multi_scalar_mul(sc, pv), oracle_msm(oracle, sc, pv))
+    # all-equal scalars, all-equal points (one bucket per window gets everything)
+    k = rng.getrandbits(255)
+    sc = ob.ints_to_fe([k] * 40)
+    pv = np.stack([ob.affine_to_ge(*pts[0])] * 40)
+    assert np.array_equal(cbp.cuda_point_vector_multi_scalar_mul(sc, pv), oracle_msm(oracle, sc, pv))
+    # (P, -P) pairs cancel to the identity; identity inputs
+    pv = np.stack([ob.affine_to_ge(*pts[1]), ob.affine_to_ge(*pyref.pt_neg(pts[1])), ob.affine_to_ge(0, 1)])
+    sc = ob.ints_to_fe([k, k, 12345])
+    got = cbp.cuda_point_vector_multi_scalar_mul(sc, pv)
+    assert np.array_equal(got, oracle_msm(oracle, sc, pv))
+    assert ob.ge_to_affine(got) == (0, 1)
+    # non-normalised (Z != 1) inputs
+    z = 0x1234567890ABCDEF1234567890ABCDEF
+    proj = []
+    for (x, y) in pts[:5]:
+        proj.append(np.concatenate([ob.int_to_fe(x * z % P), ob.int_to_fe(y * z % P), ob.int_to_fe(z),
+                                    ob.int_to_fe(x * y % P * z % P)]))
+    pv = np.stack(proj)
+    sc = ob.ints_to_fe([rng.getrandbits(256) for _ in range(5)])
+    assert np.array_equal(cbp.cuda_point_vector_multi_scalar_mul(sc, pv), oracle_msm(oracle, sc, pv))
+    # a point with an 8-torsion component: k is NOT reduced mod l, so this must still match
+    y = 3
+    while pyref.recover_x(y, 0) is None:
+        y += 1
+    Q = (pyref.recover_x(y, 0), y)
+    pv = np.stack([ob.affine_to_ge(*Q), ob.affine_to_ge(*pyref.pt_mul(L, Q))])
+    sc = ob.ints_to_fe([L + 5, 7])
+    got = cbp.cuda_point_vector_multi_scalar_mul(sc, pv)
+    assert np.array_equal(got, oracle_msm(oracle, sc, pv))
+    assert ob.ge_to_affine(got) == pyref.pt_add(pyref.pt_mul(L + 5, Q), pyref.pt_mul(7, pyref.pt_mul(L, Q)))
+
+
+def test_msm_empty_and_mismatch(capfd):
+    import cudabulletproof_b200 as cbp
+    e_s, e_p = np.zeros((0, 4), np.uint64), np.zeros((0, 16), np.uint64)
+    got = cbp.cuda_point_vector_multi_scalar_mul(e_s, e_p)
+    assert ob.ge_to_affine(got) == (0, 1)
+    res = np.full(16, 0xDEADBEEF, dtype=np.uint64)
+    cbp.cuda_point_vector_multi_scalar_mul(ob.ints_to_fe([1, 2]), np.zeros((3, 16), np.uint64), result=res)
+    assert (res == 0xDEADBEEF).all()  # cuda_bulletproof_kernels.cu:65-68
+    assert "Vector lengths must match" in capfd.readouterr().err
+
+
+@pytest.mark.parametrize("window_bits", [4, 7, 11, 13, 16])
+def test_msm_all_window_sizes_agree(oracle, window_bits):
+    import torch
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(50 + window_bits)
+    n = 200
+    sc = ob.ints_to_fe([rng.getrandbits(256) for _ in range(n)])
+    pts = np.stack([ob.affine_to_ge(*p) for p in curve_points(rng, n)])
+    want = oracle_msm(oracle, sc, pts)
+    d_s = torch.from_numpy(sc.view(np.uint8).reshape(n, 32)).cuda()
+    d_p = torch.from_numpy(pts.view(np.uint8).reshape(n, 128)).cuda()
+    msm = cbp.Msm(n, window_bits=window_bits)
+    got = msm(d_s, d_p).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("log_n", [12, 16, 20])
+def test_msm_full_size_scalar_identity(oracle, log_n):
+    """Size-independent check at full size: points P_i = k_i*B, so MSM(s, P) = (sum s_i k_i mod l) * B,
+    one CPU scalar multiplication."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    n = 1 << log_n
+    pts, ks = cbp.synth_points(n, seed=0xC3 + log_n)
+    sc = cbp.synth_scalars(n, seed=0x5CA1A000 + log_n, bits=252)
+    msm = cbp.Msm(n)
+    got = msm(sc, pts).cpu().numpy().view(np.uint64).copy()
+    torch.cuda.synchronize()
+    ks_h = ks.cpu().numpy().astype(np.uint64)
+    sc_h = sc.cpu().numpy().view(np.uint64).reshape(n, 4)
+    acc = 0
+    for i in range(n):
+        acc += (int(sc_h[i, 0]) | int(sc_h[i, 1]) << 64 | int(sc_h[i, 2]) << 128 | int(sc_h[i, 3]) << 192) * int(ks_h[i])
+    acc %= L
+    want = np.zeros(16, dtype=np.uint64)
+    oracle.ge25519_scalarmult_base(ob.ptr(want), acc.to_bytes(32, "little"))
+    oracle.ge25519_normalize(ob.ptr(want))
+    assert np.array_equal(got, want)
+    # atomics reorder bucket contents between runs; the group element must not change
+    again = msm(sc, pts).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, again)
