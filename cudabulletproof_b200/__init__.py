@@ -69,8 +69,10 @@ SIGNATURES = {
     "bpk_proof_record_bytes": (_sz, [_sz]),
     "bpk_gens_workspace_bytes": (_i, [_sz, C.POINTER(_sz)]),
     "bpk_gens_init_device": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "bpk_range_verify_batch_device": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
-    "bpk_range_prove_batch_device": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "bpk_range_verify_workspace_bytes": (_i, [_sz, _sz, C.POINTER(_sz)]),
+    "bpk_range_verify_batch_device": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
+    "bpk_range_prove_workspace_bytes": (_i, [_sz, _sz, C.POINTER(_sz)]),
+    "bpk_range_prove_batch_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
     "bpk_synth_points_device": (_i, [_vp, _vp, _sz, _u64, _vp]),
     "bpk_synth_scalars_device": (_i, [_vp, _sz, _u64, _i, _vp]),
     # include/cuda_bulletproof.h

@@ -1,0 +1,414 @@
+// ipa.cu — inner-product-argument folding kernels, stand-alone IPA verification and the host-pointer
+// drop-ins cuda_range_proof_verify / cuda_inner_product_verify (cuda_bulletproof.h:61,72).
+//
+//   fold scalars  bulletproof_vectors.cu:488-500  a' = u a_L + u^-1 a_R ; b' = u^-1 b_L + u b_R  (mod l, D11/D21)
+//   fold points   bulletproof_vectors.cu:641-663  G'_j = u^-1 G_j + u G_{j+n'} ; H'_j = u H_j + u^-1 H_{j+n'}
+//   verify        bulletproof_vectors.cu:541-762  P + sum(u_j^2 L_j + u_j^-2 R_j) == a G' + b H' + a b Q, evaluated
+//                 as ONE Pippenger MSM over 2n + 2k + 2 points that must be the identity (no folding).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include "../../include/cuda_bulletproof.h"
+#include "common.h"
+#include "msm.h"
+#include "rangeproof.cuh"
+#include "sha256.cuh"
+
+namespace cbp {
+
+// ---- folding --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ipa_fold_scalars_kernel(uint8_t* a_out, uint8_t* b_out, const uint8_t* a,
+                                                               const uint8_t* b, size_t n_half,
+                                                               const uint8_t* __restrict__ u_p,
+                                                               const uint8_t* __restrict__ ui_p) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_half) return;
+    sc u, ui, al, ar, bl, br, t0, t1, na, nb;
+    sc_load(t0, u_p);
+    sc_reduce(u, t0);
+    sc_load(t0, ui_p);
+    sc_reduce(ui, t0);
+    sc_load(t0, a + j * 32);
+    sc_reduce(al, t0);
+    sc_load(t0, a + (j + n_half) * 32);
+    sc_reduce(ar, t0);
+    sc_load(t0, b + j * 32);
+    sc_reduce(bl, t0);
+    sc_load(t0, b + (j + n_half) * 32);
+    sc_reduce(br, t0);
+    sc_mul(t0, u, al);
+    sc_mul(t1, ui, ar);
+    sc_add(na, t0, t1);
+    sc_mul(t0, ui, bl);
+    sc_mul(t1, u, br);
+    sc_add(nb, t0, t1);
+    sc_store(a_out + j * 32, na);  // j < n_half: safe in place (each thread reads j and j+n_half first)
+    sc_store(b_out + j * 32, nb);
+}
+// r = k1 A + k2 B with shared doublings (Shamir), scalars < l
+__device__ __forceinline__ void double_scalarmult(ge_p3& r, const sc& k1, const ge_p3& A, const sc& k2, const ge_p3& B) {
+    ge_p3 AB;
+    ge_add(AB, A, B);
+    ge_cached cA, cB, cAB;
+    ge_to_cached(cA, A);
+    ge_to_cached(cB, B);
+    ge_to_cached(cAB, AB);
+    ge_p3 acc;
+    ge_p3_0(acc);
+    for (int i = 252; i >= 0; i--) {
+        ge_dbl(acc, acc);
+        uint32_t b1 = (k1.v[i >> 5] >> (i & 31)) & 1, b2 = (k2.v[i >> 5] >> (i & 31)) & 1;
+        if (b1 & b2) ge_add_cached(acc, acc, cAB, false);
+        else if (b1) ge_add_cached(acc, acc, cA, false);
+        else if (b2) ge_add_cached(acc, acc, cB, false);
+    }
+    r = acc;
+}
+__global__ void __launch_bounds__(64) ipa_fold_points_kernel(uint8_t* G_out, uint8_t* H_out, const uint8_t* G,
+                                                             const uint8_t* H, size_t n_half,
+                                                             const uint8_t* __restrict__ u_p,
+                                                             const uint8_t* __restrict__ ui_p) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n_half) return;
+    bool is_h = id >= n_half;
+    size_t j = is_h ? id - n_half : id;
+    sc u, ui, t0;
+    sc_load(t0, u_p);
+    sc_reduce(u, t0);
+    sc_load(t0, ui_p);
+    sc_reduce(ui, t0);
+    const uint8_t* src = is_h ? H : G;
+    ge_p3 lo, hi, r;
+    ge_load(lo, src + j * 128);
+    ge_load(hi, src + (j + n_half) * 128);
+    // G: u^-1 lo + u hi ; H: u lo + u^-1 hi.  Scalars >= l cannot occur (reduced), points may carry torsion:
+    // k < l is used as an integer exactly like the CPU double-and-add.
+    double_scalarmult(r, is_h ? u : ui, lo, is_h ? ui : u, hi);
+    ge_normalize(r);
+    ge_store((is_h ? H_out : G_out) + j * 128, r);
+}
+
+// ---- stand-alone IPA verification -------------------------------------------------------------------
+struct IpaChal {
+    uint32_t valid;
+    uint32_t pad[7];
+    sc a, b, ab;
+    sc u[32], uinv[32], usq[32], uinvsq[32];
+};
+// one thread: transcript, inversions (k <= 32)
+__global__ void ipa_verify_challenges_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ R, int k,
+                                             const uint8_t* __restrict__ a_p, const uint8_t* __restrict__ b_p,
+                                             const uint8_t* __restrict__ x_p, const uint8_t* __restrict__ tr0,
+                                             IpaChal* __restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    bool valid = true;
+    uint32_t tr[8];
+    for (int i = 0; i < 8; i++)
+        tr[i] = (uint32_t)tr0[4 * i] | ((uint32_t)tr0[4 * i + 1] << 8) | ((uint32_t)tr0[4 * i + 2] << 16) |
+                ((uint32_t)tr0[4 * i + 3] << 24);
+    Sha256 sh;
+    sc run;
+    sc_set1(run);
+    for (int j = 0; j < k; j++) {
+        ge_p3 Lp, Rp;
+        ge_load(Lp, L + (size_t)j * 128);
+        ge_load(Rp, R + (size_t)j * 128);
+        valid = valid && ge_is_on_curve(Lp) && ge_is_on_curve(Rp);
+        ge_normalize(Lp);
+        ge_normalize(Rp);
+        sh.init();
+        sh.update_str("InnerProductChal", 16);
+        sh.update_words(tr);
+        sh.update_words(Lp.X.v);
+        sh.update_words(Rp.X.v);
+        sh.final_challenge(tr);
+        if (j == 0) {
+            fe xs;
+            fe_load(xs, x_p);
+            fe_canon(xs);
+            for (int i = 0; i < 8; i++) valid = valid && (xs.v[i] == tr[i]);
+        }
+        sc t;
+        for (int i = 0; i < 8; i++) t.v[i] = tr[i];
+        sc_reduce(out->u[j], t);
+        out->uinv[j] = run;  // prefix product, fixed up below
+        sc_mul(run, run, out->u[j]);
+    }
+    sc inv;
+    sc_invert(inv, run);
+    for (int j = k - 1; j >= 0; j--) {
+        sc pre = out->uinv[j], ui;
+        sc_mul(ui, inv, pre);
+        sc_mul(inv, inv, out->u[j]);
+        out->uinv[j] = ui;
+        sc_mul(out->usq[j], out->u[j], out->u[j]);
+        sc_mul(out->uinvsq[j], ui, ui);
+    }
+    sc t;
+    sc_load(t, a_p);
+    sc_reduce(out->a, t);
+    sc_load(t, b_p);
+    sc_reduce(out->b, t);
+    sc_mul(out->ab, out->a, out->b);
+    out->valid = valid ? 1u : 0u;
+}
+// builds the MSM instance: [a s_i] G_i, [b s_i^-1] H_i, [ab] Q, [u_j^2] (-L_j), [u_j^-2] (-R_j), [1] (-P)
+__global__ void __launch_bounds__(128) ipa_verify_assemble_kernel(const IpaChal* __restrict__ ch, size_t n, int k,
+                                                                  const uint8_t* __restrict__ G,
+                                                                  const uint8_t* __restrict__ H,
+                                                                  const uint8_t* __restrict__ Q,
+                                                                  const uint8_t* __restrict__ L,
+                                                                  const uint8_t* __restrict__ R,
+                                                                  const uint8_t* __restrict__ P,
+                                                                  uint8_t* __restrict__ scalars,
+                                                                  uint8_t* __restrict__ points) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = 2 * n + 2 * (size_t)k + 2;
+    if (id >= total) return;
+    sc s;
+    ge_p3 pt;
+    if (id < 2 * n) {
+        bool is_h = id >= n;
+        size_t i = is_h ? id - n : id;
+        sc_set1(s);
+        for (int j = 0; j < k; j++) {
+            bool bit = (i >> (k - 1 - j)) & 1;
+            sc_mul(s, s, (bit != is_h) ? ch->u[j] : ch->uinv[j]);  // H uses the inverse exponents
+        }
+        sc_mul(s, s, is_h ? ch->b : ch->a);
+        ge_load(pt, (is_h ? H : G) + i * 128);
+    } else if (id == 2 * n) {
+        s = ch->ab;
+        ge_load(pt, Q);
+    } else if (id < 2 * n + 1 + 2 * (size_t)k) {
+        size_t j = id - 2 * n - 1;
+        bool is_r = j >= (size_t)k;
+        if (is_r) j -= k;
+        s = is_r ? ch->uinvsq[j] : ch->usq[j];
+        ge_p3 t;
+        ge_load(t, (is_r ? R : L) + j * 128);
+        ge_neg(pt, t);
+    } else {
+        sc_set1(s);
+        ge_p3 t;
+        ge_load(t, P);
+        ge_neg(pt, t);
+    }
+    sc_store(scalars + id * 32, s);
+    ge_store(points + id * 128, pt);
+}
+__global__ void ipa_verify_decide_kernel(const IpaChal* __restrict__ ch, const uint8_t* __restrict__ result,
+                                         uint8_t* __restrict__ accept) {
+    if (threadIdx.x || blockIdx.x) return;
+    ge_p3 r;
+    ge_load(r, result);
+    accept[0] = (ch->valid && ge_is_identity(r)) ? 1 : 0;
+}
+
+}  // namespace cbp
+
+using namespace cbp;
+
+extern "C" {
+
+int bpk_ipa_fold_scalars_device(void* d_a_out, void* d_b_out, const void* d_a, const void* d_b, size_t n_half,
+                                const void* d_u, const void* d_u_inv, void* stream) {
+    if (!n_half) return BPK_OK;
+    if (!d_a_out || !d_b_out || !d_a || !d_b || !d_u || !d_u_inv) return fail(BPK_ERR_ARG);
+    ipa_fold_scalars_kernel<<<(unsigned)((n_half + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (uint8_t*)d_a_out, (uint8_t*)d_b_out, (const uint8_t*)d_a, (const uint8_t*)d_b, n_half, (const uint8_t*)d_u,
+        (const uint8_t*)d_u_inv);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, const void* d_H, size_t n_half,
+                               const void* d_u, const void* d_u_inv, void* stream) {
+    if (!n_half) return BPK_OK;
+    if (!d_G_out || !d_H_out || !d_G || !d_H || !d_u || !d_u_inv) return fail(BPK_ERR_ARG);
+    if (d_G_out == d_G || d_H_out == d_H) return fail(BPK_ERR_ARG);  // outputs must not alias inputs
+    ipa_fold_points_kernel<<<(unsigned)((2 * n_half + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+        (uint8_t*)d_G_out, (uint8_t*)d_H_out, (const uint8_t*)d_G, (const uint8_t*)d_H, n_half, (const uint8_t*)d_u,
+        (const uint8_t*)d_u_inv);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+// ---- host-pointer drop-ins ----------------------------------------------------------------------------
+static bool ipa_verify_host(const InnerProductProof* proof, const ge25519* P, const PointVector* G,
+                            const PointVector* H, const ge25519* Q, const uint8_t tr0[32]) {
+    size_t n = proof->n;
+    if (G->length != n || H->length != n) return false;  // bulletproof_vectors.cu:550-556
+    if (n == 0 || (n & (n - 1))) return false;
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    if (proof->L_len != (size_t)k || proof->L.length != (size_t)k || proof->R.length != (size_t)k) return false;
+    if (proof->a.length < 1 || proof->b.length < 1 || k > 30) return false;
+    size_t total = 2 * n + 2 * (size_t)k + 2;
+    MsmPlan plan;
+    msm_make_plan(&plan, total, 0);
+    size_t off_G = 0, off_H = off_G + n * 128, off_Q = off_H + n * 128, off_P = off_Q + 128, off_L = off_P + 128,
+           off_R = off_L + (size_t)k * 128 + 128, off_s = off_R + (size_t)k * 128 + 128, off_ch = off_s + 128,
+           off_sc = off_ch + ((sizeof(IpaChal) + 255) / 256) * 256, off_pt = off_sc + total * 32,
+           off_res = off_pt + total * 128, off_ws = off_res + 256, bytes = off_ws + plan.workspace_bytes;
+    uint8_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) {
+        fail(BPK_ERR_CUDA, e);
+        return false;
+    }
+    bool ok = false;
+    uint8_t small[128];
+    cudaStream_t st = 0;
+    do {
+        if ((e = cudaMemcpyAsync(d + off_G, G->elements, n * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d + off_H, H->elements, n * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d + off_Q, Q, 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d + off_P, P, 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if (k) {
+            if ((e = cudaMemcpyAsync(d + off_L, proof->L.elements, (size_t)k * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d + off_R, proof->R.elements, (size_t)k * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        }
+        memcpy(small, proof->a.elements, 32);
+        memcpy(small + 32, proof->b.elements, 32);
+        memcpy(small + 64, &proof->x, 32);
+        memcpy(small + 96, tr0, 32);
+        if ((e = cudaMemcpyAsync(d + off_s, small, 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        IpaChal* ch = (IpaChal*)(d + off_ch);
+        ipa_verify_challenges_kernel<<<1, 32, 0, st>>>(d + off_L, d + off_R, k, d + off_s, d + off_s + 32, d + off_s + 64,
+                                                       d + off_s + 96, ch);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        ipa_verify_assemble_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ch, n, k, d + off_G, d + off_H,
+                                                                                   d + off_Q, d + off_L, d + off_R,
+                                                                                   d + off_P, d + off_sc, d + off_pt);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        count_launches(2);
+        int launches = 0;
+        int rc = msm_run(plan, d + off_sc, d + off_pt, d + off_res, d + off_ws, 0, st, &launches);
+        count_launches(launches);
+        if (rc) {
+            e = (cudaError_t)rc;
+            break;
+        }
+        ipa_verify_decide_kernel<<<1, 32, 0, st>>>(ch, d + off_res, d + off_res + 128);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        count_launches(1);
+        uint8_t acc = 0;
+        if ((e = cudaMemcpyAsync(&acc, d + off_res + 128, 1, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        ok = acc != 0;
+    } while (0);
+    if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
+    cudaFree(d);
+    return ok;
+}
+
+bool cuda_inner_product_verify(const InnerProductProof* proof, const ge25519* P, const PointVector* G,
+                               const PointVector* H, const ge25519* Q) {
+    uint8_t zero[32] = {0};  // bulletproof_vectors.cu:589
+    return ipa_verify_host(proof, P, G, H, Q, zero);
+}
+
+// generator tables are cached across calls: the reference signature passes G, H, g, h every time
+static std::mutex g_gens_mu;
+static uint8_t* g_gens_dev = nullptr;
+static uint8_t* g_gens_key = nullptr;
+static size_t g_gens_key_bytes = 0, g_gens_n = 0;
+
+static const uint8_t* gens_for(size_t n, const PointVector* G, const PointVector* H, const ge25519* g, const ge25519* h) {
+    size_t key_bytes = (2 * n + 2) * 128;
+    uint8_t* key = (uint8_t*)malloc(key_bytes);
+    memcpy(key, G->elements, n * 128);
+    memcpy(key + n * 128, H->elements, n * 128);
+    memcpy(key + 2 * n * 128, g, 128);
+    memcpy(key + 2 * n * 128 + 128, h, 128);
+    if (g_gens_dev && g_gens_n == n && g_gens_key_bytes == key_bytes && memcmp(key, g_gens_key, key_bytes) == 0) {
+        free(key);
+        return g_gens_dev;
+    }
+    if (g_gens_dev) cudaFree(g_gens_dev);
+    free(g_gens_key);
+    g_gens_dev = nullptr;
+    g_gens_key = nullptr;
+    size_t ws = 0;
+    if (bpk_gens_workspace_bytes(n, &ws) != BPK_OK) {
+        free(key);
+        return nullptr;
+    }
+    uint8_t* d_in = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&g_gens_dev, ws)) != cudaSuccess || (e = cudaMalloc(&d_in, key_bytes)) != cudaSuccess ||
+        (e = cudaMemcpy(d_in, key, key_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        fail(BPK_ERR_CUDA, e);
+        cudaFree(g_gens_dev);
+        cudaFree(d_in);
+        g_gens_dev = nullptr;
+        free(key);
+        return nullptr;
+    }
+    int rc = bpk_gens_init_device(g_gens_dev, ws, d_in, d_in + n * 128, d_in + 2 * n * 128, d_in + 2 * n * 128 + 128, n, 0);
+    e = cudaDeviceSynchronize();
+    cudaFree(d_in);
+    if (rc != BPK_OK || e != cudaSuccess) {
+        if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
+        cudaFree(g_gens_dev);
+        g_gens_dev = nullptr;
+        free(key);
+        return nullptr;
+    }
+    g_gens_key = key;
+    g_gens_key_bytes = key_bytes;
+    g_gens_n = n;
+    return g_gens_dev;
+}
+
+bool cuda_range_proof_verify(const RangeProof* proof, const ge25519* V, size_t n, const PointVector* G,
+                             const PointVector* H, const ge25519* g, const ge25519* h) {
+    // structural checks of the CPU verifier (nb:6669-6672; bulletproof_vectors.cu:550-556)
+    if (G->length != n || H->length != n || proof->ip_proof.n != n) return false;
+    if (n == 0 || n > (size_t)kMaxN || (n & (n - 1))) return false;
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    const InnerProductProof* ip = &proof->ip_proof;
+    if (ip->L_len != (size_t)k || ip->L.length != (size_t)k || ip->R.length != (size_t)k) return false;
+    if (ip->a.length < 1 || ip->b.length < 1) return false;
+    std::lock_guard<std::mutex> lock(g_gens_mu);
+    const uint8_t* gens = gens_for(n, G, H, g, h);
+    if (!gens) return false;
+    size_t rec = proof_record_bytes(k), ws = 0;
+    bpk_range_verify_workspace_bytes(n, 1, &ws);
+    uint8_t* hrec = (uint8_t*)calloc(1, rec);
+    memcpy(hrec + kRecV, &proof->V, 5 * 128 + 3 * 32);
+    memcpy(hrec + kRecIpA, ip->a.elements, 32);
+    memcpy(hrec + kRecIpB, ip->b.elements, 32);
+    memcpy(hrec + kRecIpC, &ip->c, 32);
+    memcpy(hrec + kRecIpX, &ip->x, 32);
+    if (k) {
+        memcpy(hrec + kRecL, ip->L.elements, (size_t)k * 128);
+        memcpy(hrec + kRecL + (size_t)k * 128, ip->R.elements, (size_t)k * 128);
+    }
+    uint8_t* d = nullptr;
+    bool ok = false;
+    cudaError_t e = cudaMalloc(&d, rec + 128 + 256 + ws);
+    if (e == cudaSuccess) {
+        uint8_t* d_V = d + ((rec + 255) / 256) * 256;
+        uint8_t* d_acc = d_V + 128;
+        uint8_t* d_ws = d_acc + 128;
+        e = cudaMalloc(&d_ws, ws);  // separate allocation keeps alignment simple
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, hrec, rec, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_V, V, 128, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) {
+            int rc = bpk_range_verify_batch_device(gens, d, d_V, n, 1, d_acc, d_ws, ws, 0);
+            uint8_t acc = 0;
+            if (rc == BPK_OK) e = cudaMemcpy(&acc, d_acc, 1, cudaMemcpyDeviceToHost);
+            ok = rc == BPK_OK && e == cudaSuccess && acc != 0;
+        }
+        cudaFree(d_ws);
+    }
+    if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
+    cudaFree(d);
+    free(hrec);
+    return ok;
+}
+
+}  // extern "C"

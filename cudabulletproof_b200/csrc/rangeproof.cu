@@ -1,0 +1,572 @@
+// rangeproof.cu — batched range-proof verification for sm_100a and the generator tables it uses.
+//
+// Replaces cuda_range_proof_verify / cuda_inner_product_verify (reference notebook cell
+// cuda_range_proof_verify.cu, nb:6529-6900, pure host code with heuristic comparisons) and the CPU
+// verifier range_proof_verify (bulletproof_range_proof.cu:1717-1812) + inner_product_verify
+// (bulletproof_vectors.cu:541-762).  Decisions are bit-exact with oracle/ref_corrected.c.
+//
+// Instead of folding G/H round by round (the reference's 4(n-1) scalar multiplications,
+// bulletproof_vectors.cu:641-663) the verifier evaluates the two identities
+//   (t - delta) g + taux h                       ==  z^2 V + x T1 + x^2 T2
+//   sum (a s_i + z) G_i + sum ((b s_i^-1 - z^2 2^i) y^-i - z) H_i + (mu + ab - t) h
+//                                                ==  A + x S + sum u_j^2 L_j + sum u_j^-2 R_j
+// as multi-scalar sums: the 2n+2 shared generators through precomputed 8-bit fixed-base tables
+// (no doublings), the 2 log n + 5 per-proof points with 4-bit windows.
+//
+// Kernels per batch:
+//   verify_transcript  1 thread / proof : on-curve checks, SHA-256 challenges, scalar inversions
+//   verify_msm         1 CTA    / proof : coefficients, fixed-base sums, per-window variable sums
+//   verify_finish      1 thread / (proof, identity): Horner over the 64 windows, equality test
+//   verify_combine     accept bits
+#include <stdio.h>
+#include <string.h>
+#include "../../include/cuda_bulletproof.h"
+#include "common.h"
+#include "rangeproof.cuh"
+#include "sha256.cuh"
+
+namespace cbp {
+
+// ---- generator tables -----------------------------------------------------------------------------
+__global__ void gens_pow_kernel(const uint8_t* __restrict__ G, const uint8_t* __restrict__ H,
+                                const uint8_t* __restrict__ g, const uint8_t* __restrict__ h, uint32_t n,
+                                uint8_t* __restrict__ pow_out, uint8_t* __restrict__ bases_out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nb = 2 * n + 2;
+    if (b >= nb) return;
+    const uint8_t* src = b < n ? G + (size_t)b * 128 : b < 2 * n ? H + (size_t)(b - n) * 128 : b == 2 * n ? g : h;
+    ge_p3 P;
+    ge_load(P, src);
+    ge_p3 Pn = P;
+    ge_normalize(Pn);
+    ge_store(bases_out + (size_t)b * 128, Pn);
+    for (int j = 0; j < kFixWin; j++) {
+        ge_store(pow_out + ((size_t)b * kFixWin + j) * 128, P);
+        for (int s = 0; s < 8; s++) ge_dbl(P, P);
+    }
+}
+// one thread per (base, window): multiples 1..128 of 2^(8 win) Base, normalised with one inversion
+__global__ void __launch_bounds__(64) gens_table_kernel(const uint8_t* __restrict__ pow_in, uint32_t nbases,
+                                                        uint8_t* __restrict__ table, uint8_t* __restrict__ prefix) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nbases * kFixWin) return;
+    ge_p3 M, acc;
+    ge_load(M, pow_in + (size_t)id * 128);
+    acc = M;
+    uint8_t* slot = table + (size_t)id * kFixEntries * 96;
+    uint8_t* pre = prefix + (size_t)id * kFixEntries * 32;
+    fe run;
+    fe_set1(run);
+    for (int d = 0; d < kFixEntries; d++) {
+        fe_store(slot + d * 96, acc.X);
+        fe_store(slot + d * 96 + 32, acc.Y);
+        fe_store(slot + d * 96 + 64, acc.Z);
+        fe_store(pre + d * 32, run);
+        fe_mul(run, run, acc.Z);
+        ge_add(acc, acc, M);
+    }
+    fe inv;
+    fe_invert(inv, run);
+    for (int d = kFixEntries - 1; d >= 0; d--) {
+        fe X, Y, Z, p, zi;
+        fe_load(X, slot + d * 96);
+        fe_load(Y, slot + d * 96 + 32);
+        fe_load(Z, slot + d * 96 + 64);
+        fe_load(p, pre + d * 32);
+        fe_mul(zi, inv, p);
+        fe_mul(inv, inv, Z);
+        fe_mul(X, X, zi);
+        fe_mul(Y, Y, zi);
+        ge_niels q;
+        ge_to_niels_affine(q, X, Y);
+        ge_niels_store(slot + d * 96, q);
+    }
+}
+
+// ---- per-proof scalars produced by verify_transcript ------------------------------------------------
+struct VScal {
+    uint32_t valid;
+    uint32_t pad[7];
+    sc z, z2, x, x2, a, b;
+    sc g1;   // identity 1, g coefficient: t - delta
+    sc h1;   // identity 1, h coefficient: taux
+    sc h2;   // identity 2, h coefficient: mu + a b - t   (Q = h)
+    sc s0;   // prod u_j^-1
+    sc ypow[kMaxK + 1];  // y^-(2^m)
+    sc usq[kMaxK], uinvsq[kMaxK];
+};
+
+__device__ __forceinline__ void words_of(uint32_t (&w)[8], const fe& a) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = a.v[i];
+}
+// affine coordinates of a projective point for hashing (fast path when Z == 1)
+__device__ __forceinline__ void affine_xy(fe& x, fe& y, const ge_p3& p) {
+    fe one;
+    fe_set1(one);
+    if (fe_equal(p.Z, one)) {
+        x = p.X;
+        y = p.Y;
+    } else {
+        fe zi;
+        fe_invert(zi, p.Z);
+        fe_mul(x, p.X, zi);
+        fe_mul(y, p.Y, zi);
+    }
+    fe_canon(x);
+    fe_canon(y);
+}
+__device__ __forceinline__ void sc_from_words(sc& r, const uint32_t (&w)[8]) {
+    sc t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.v[i] = w[i];
+    sc_reduce(r, t);
+}
+__device__ __forceinline__ void sc_load_reduce(sc& r, const void* p) {
+    sc t;
+    sc_load(t, p);
+    sc_reduce(r, t);
+}
+
+__global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes,
+                                                               const uint8_t* __restrict__ Vext, uint32_t n, int k,
+                                                               uint32_t num, VScal* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num) return;
+    const uint8_t* rec = proofs + (size_t)p * rec_bytes;
+    VScal& vs = out[p];
+    bool valid = true;
+    fe px[5], py[5];
+    ge_p3 V;
+    for (int q = 0; q < 5; q++) {
+        ge_p3 P;
+        ge_load(P, rec + q * 128);
+        valid = valid && ge_is_on_curve(P);
+        affine_xy(px[q], py[q], P);
+        if (q == 0) V = P;
+    }
+    if (Vext) {  // bulletproof_range_proof.cu:1729-1740: the caller's V must be the proof's V
+        ge_p3 E;
+        ge_load(E, Vext + (size_t)p * 128);
+        fe a, b, c, d;
+        fe_mul(a, E.X, V.Z);
+        fe_mul(b, V.X, E.Z);
+        fe_mul(c, E.Y, V.Z);
+        fe_mul(d, V.Y, E.Z);
+        valid = valid && ge_is_on_curve(E) && fe_equal(a, b) && fe_equal(c, d);
+    }
+    uint32_t w[8], yb[8], zb[8], xb[8];
+    Sha256 sh;
+    // y: bulletproof_challenge.cu:24-44
+    sh.init();
+    sh.update_str("BulletproofYChal", 16);
+    for (int q = 0; q < 3; q++) {
+        words_of(w, px[q]);
+        sh.update_words(w);
+        words_of(w, py[q]);
+        sh.update_words(w);
+    }
+    sh.update_str("y_ch", 4);
+    sh.final_challenge(yb);
+    // z: :47-58
+    sh.init();
+    sh.update_str("BulletproofZChal", 16);
+    sh.update_words(yb);
+    sh.update_str("z_ch", 4);
+    sh.final_challenge(zb);
+    // x: :61-77 (only 4 bytes of "xchal" are hashed)
+    sh.init();
+    sh.update_str("BulletproofXChal", 16);
+    for (int q = 3; q < 5; q++) {
+        words_of(w, px[q]);
+        sh.update_words(w);
+        words_of(w, py[q]);
+        sh.update_words(w);
+    }
+    sh.update_str("xcha", 4);
+    sh.final_challenge(xb);
+
+    sc y, z, x, t, taux, mu, a, b, c;
+    sc_from_words(y, yb);
+    sc_from_words(z, zb);
+    sc_from_words(x, xb);
+    sc_load_reduce(t, rec + kRecT);
+    sc_load_reduce(taux, rec + kRecTaux);
+    sc_load_reduce(mu, rec + kRecMu);
+    sc_load_reduce(a, rec + kRecIpA);
+    sc_load_reduce(b, rec + kRecIpB);
+    sc_load_reduce(c, rec + kRecIpC);
+    bool c_ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c_ok = c_ok && (c.v[i] == t.v[i]);
+    valid = valid && c_ok;
+
+    // IPA transcript: bulletproof_range_proof.cu:1668-1676, bulletproof_vectors.cu:448-465
+    uint32_t tr[8];
+    sh.init();
+    sh.update_str("BulletproofIP", 13);
+    sh.update_words(t.v);
+    sh.update_words(taux.v);
+    sh.update_words(mu.v);
+    sh.final_challenge(tr);
+    sc u[kMaxK];
+    for (int j = 0; j < k; j++) {
+        ge_p3 Lp, Rp;
+        ge_load(Lp, rec + kRecL + (size_t)j * 128);
+        ge_load(Rp, rec + kRecL + (size_t)(k + j) * 128);
+        valid = valid && ge_is_on_curve(Lp) && ge_is_on_curve(Rp);
+        fe lx, ly, rx, ry;
+        affine_xy(lx, ly, Lp);
+        affine_xy(rx, ry, Rp);
+        sh.init();
+        sh.update_str("InnerProductChal", 16);
+        sh.update_words(tr);
+        words_of(w, lx);
+        sh.update_words(w);
+        words_of(w, rx);
+        sh.update_words(w);
+        sh.final_challenge(tr);
+        if (j == 0) {  // stored first-round challenge must be the recomputed one (D15)
+            fe xs;
+            fe_load(xs, rec + kRecIpX);
+            fe_canon(xs);
+            bool same = true;
+#pragma unroll
+            for (int i = 0; i < 8; i++) same = same && (xs.v[i] == tr[i]);
+            valid = valid && same;
+        }
+        sc_from_words(u[j], tr);
+    }
+    // batch inversion of y, u_0 .. u_{k-1}
+    sc pre[kMaxK + 1], run, inv;
+    sc_set1(run);
+    pre[0] = run;
+    sc_mul(run, run, y);
+    for (int j = 0; j < k; j++) {
+        pre[j + 1] = run;
+        sc_mul(run, run, u[j]);
+    }
+    sc_invert(inv, run);
+    sc uinv[kMaxK], yinv;
+    for (int j = k - 1; j >= 0; j--) {
+        sc_mul(uinv[j], inv, pre[j + 1]);
+        sc_mul(inv, inv, u[j]);
+    }
+    yinv = inv;  // pre[0] = 1
+
+    vs.z = z;
+    sc_mul(vs.z2, z, z);
+    vs.x = x;
+    sc_mul(vs.x2, x, x);
+    vs.a = a;
+    vs.b = b;
+    // delta = (z - z^2) sum y^i - z^3 (2^n - 1): bulletproof_range_proof.cu:315-374
+    sc sum_y, cur, zmz2, z3, two_n, delta, tmp;
+    sc_set1(sum_y);
+    sc_set1(cur);
+    for (uint32_t i = 1; i < n; i++) {
+        sc_mul(cur, cur, y);
+        sc_add(sum_y, sum_y, cur);
+    }
+    sc_sub(zmz2, z, vs.z2);
+    sc_mul(z3, vs.z2, z);
+    sc_set0(two_n);
+    two_n.v[n >> 5] = 1u << (n & 31);  // n <= 64 < 252
+    sc one;
+    sc_set1(one);
+    sc_sub(two_n, two_n, one);
+    sc_mul(delta, zmz2, sum_y);
+    sc_mul(tmp, z3, two_n);
+    sc_sub(delta, delta, tmp);
+    sc_sub(vs.g1, t, delta);
+    vs.h1 = taux;
+    sc_mul(tmp, a, b);
+    sc_sub(tmp, tmp, t);
+    sc_add(vs.h2, tmp, mu);
+    sc s0;
+    sc_set1(s0);
+    for (int j = 0; j < k; j++) {
+        sc_mul(s0, s0, uinv[j]);
+        sc_mul(vs.usq[j], u[j], u[j]);
+        sc_mul(vs.uinvsq[j], uinv[j], uinv[j]);
+    }
+    vs.s0 = s0;
+    vs.ypow[0] = yinv;
+    for (int m = 1; m <= k; m++) sc_mul(vs.ypow[m], vs.ypow[m - 1], vs.ypow[m - 1]);
+    vs.valid = valid ? 1u : 0u;
+#ifdef CBP_DEBUG_VSCAL
+    if (k <= 4) {
+        vs.ypow[5] = sum_y; vs.ypow[6] = delta; vs.usq[4] = zmz2; vs.usq[5] = z3; vs.uinvsq[4] = two_n;
+        sc dbg; sc_mul(dbg, uinv[0], uinv[1]); vs.uinvsq[5] = dbg;
+    }
+#endif
+}
+
+// ---- the per-proof multi-scalar sums ----------------------------------------------------------------
+static constexpr int kVThreads = 128;
+static constexpr int kVarMax = 2 + 2 * kMaxK + 3;  // A, S, L_j, R_j | V, T1, T2
+
+__global__ void __launch_bounds__(kVThreads) verify_msm_kernel(const uint8_t* __restrict__ gens,
+                                                               const uint8_t* __restrict__ proofs, size_t rec_bytes,
+                                                               uint32_t n, int k, const VScal* __restrict__ vscal,
+                                                               uint8_t* __restrict__ fsum,
+                                                               uint8_t* __restrict__ winsum) {
+    __shared__ VScal vs;
+    __shared__ sc s_pow[kMaxN];
+    __shared__ int8_t digits[2 * kMaxN + 3][kFixWin];
+    __shared__ int8_t vdigits[kVarMax][64];
+    __shared__ ge_cached vtab[kVarMax][8];
+    __shared__ ge_p3 red[kVThreads];
+
+    const uint32_t p = blockIdx.x;
+    const int t = threadIdx.x;
+    const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
+    const uint8_t* table = gens + gh->table_off;
+    const uint8_t* rec = proofs + (size_t)p * rec_bytes;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&vscal[p]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&vs);
+        for (int i = t; i < (int)(sizeof(VScal) / 4); i += kVThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (!vs.valid) return;  // uniform across the CTA
+
+    // s_i = prod_j u_j^(+-1): doubling recurrence, one level per challenge
+    if (t == 0) s_pow[0] = vs.s0;
+    __syncthreads();
+    for (int m = 0; m < k; m++) {
+        int half = 1 << m;
+        if (t >= half && t < 2 * half) {
+            sc v;
+            sc_mul(v, s_pow[t - half], vs.usq[k - 1 - m]);
+            s_pow[t] = v;
+        }
+        __syncthreads();
+    }
+    const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
+    if (t < (int)n) {
+        // y^-i from the y^-(2^m) ladder
+        sc yp;
+        sc_set1(yp);
+        for (int m = 0; m < k; m++)
+            if ((t >> m) & 1) sc_mul(yp, yp, vs.ypow[m]);
+        sc cg, ch, tmp, two_i;
+        sc_mul(cg, vs.a, s_pow[t]);
+        sc_add(cg, cg, vs.z);
+        sc_set0(two_i);
+        two_i.v[t >> 5] = 1u << (t & 31);
+        sc_mul(tmp, vs.z2, two_i);
+        sc_mul(ch, vs.b, s_pow[n - 1 - t]);
+        sc_sub(ch, ch, tmp);
+        sc_mul(ch, ch, yp);
+        sc_sub(ch, ch, vs.z);
+        sc_recode_signed<8>(digits[t], cg, kFixWin);
+        sc_recode_signed<8>(digits[n + t], ch, kFixWin);
+    } else if (t == (int)n) {
+        sc_recode_signed<8>(digits[2 * n], vs.h2, kFixWin);
+        sc_recode_signed<8>(digits[2 * n + 1], vs.g1, kFixWin);
+        sc_recode_signed<8>(digits[2 * n + 2], vs.h1, kFixWin);
+    } else if (t - (int)n - 1 < nvar) {
+        // 4-bit digits of the per-proof scalars (all taken positive; the sums are compared, not added)
+        int q = t - (int)n - 1;
+        sc sv;
+        if (q == 0) sc_set1(sv);
+        else if (q == 1) sv = vs.x;
+        else if (q < 2 + k) sv = vs.usq[q - 2];
+        else if (q < nvar2) sv = vs.uinvsq[q - 2 - k];
+        else if (q == nvar2) sv = vs.z2;
+        else if (q == nvar2 + 1) sv = vs.x;
+        else sv = vs.x2;
+        sc_recode_signed<4>(vdigits[q], sv, 64);
+    }
+    // multiples 1..8 of the per-proof points
+    for (int item = t; item < nvar * 8; item += kVThreads) {
+        int q = item >> 3, mlt = (item & 7) + 1;
+        int off = q == 0 ? kRecA : q == 1 ? kRecS : q < 2 + k ? kRecL + (q - 2) * 128 :
+                  q < nvar2 ? kRecL + (k + q - 2 - k) * 128 : q == nvar2 ? kRecV : q == nvar2 + 1 ? kRecT1 : kRecT2;
+        ge_p3 P, acc;
+        ge_load(P, rec + off);
+        ge_p3_0(acc);
+        for (int bit = 3; bit >= 0; bit--) {
+            ge_dbl(acc, acc);
+            if ((mlt >> bit) & 1) ge_add(acc, acc, P);
+        }
+        ge_to_cached(vtab[q][mlt - 1], acc);
+    }
+    __syncthreads();
+
+    // fixed-base part: identity 2 on threads [0, 124), identity 1 on threads [124, 128)
+    ge_p3 acc;
+    ge_p3_0(acc);
+    const int nrows2 = 2 * (int)n + 1;
+    if (t < kVThreads - 4) {
+        for (int item = t; item < nrows2 * kFixWin; item += kVThreads - 4) {
+            int row = item / kFixWin, win = item % kFixWin;
+            uint32_t base = row < 2 * (int)n ? (uint32_t)row : 2 * n + 1;
+            fixed_base_madd(acc, table, base, win, digits[row][win]);
+        }
+    } else {
+        for (int item = t - (kVThreads - 4); item < 2 * kFixWin; item += 4) {
+            int row = item / kFixWin, win = item % kFixWin;  // row 0: g (t - delta), row 1: h (taux)
+            fixed_base_madd(acc, table, 2 * n + row, win, digits[nrows2 + row][win]);
+        }
+    }
+    ge_p3 f1 = acc;
+    if (t >= kVThreads - 4) ge_p3_0(acc);
+    cta_point_sum(acc, red);  // identity-2 generator sum in thread 0
+    if (t >= kVThreads - 4) red[t] = f1;
+    __syncthreads();
+    if (t == 0) {
+        ge_store(fsum + ((size_t)p * 2 + 1) * 128, acc);
+        ge_p3 s = red[kVThreads - 4];
+        for (int i = 1; i < 4; i++) ge_add(s, s, red[kVThreads - 4 + i]);
+        ge_store(fsum + ((size_t)p * 2 + 0) * 128, s);
+    }
+    // variable part: one 4-bit window per thread; threads [0,64) identity 2, [64,128) identity 1
+    {
+        int w = t & 63, which = t >> 6;  // which = 0 -> identity 2 points [0, nvar2), 1 -> identity 1 [nvar2, nvar)
+        int q0 = which ? nvar2 : 0, q1 = which ? nvar : nvar2;
+        ge_p3 ws;
+        ge_p3_0(ws);
+        for (int q = q0; q < q1; q++) {
+            int d = vdigits[q][w];
+            if (d != 0) {
+                int mag = d < 0 ? -d : d;
+                ge_add_cached(ws, ws, vtab[q][mag - 1], d < 0);
+            }
+        }
+        ge_store(winsum + (((size_t)p * 2 + (which ? 0 : 1)) * 64 + w) * 128, ws);
+    }
+}
+
+// Horner over the 64 window sums, then F == Var as projective points.  index 0: identity 1, 1: identity 2.
+__global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restrict__ vscal,
+                                                           const uint8_t* __restrict__ fsum,
+                                                           const uint8_t* __restrict__ winsum, uint32_t num,
+                                                           uint8_t* __restrict__ flags) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= num * 2) return;
+    if (!vscal[id >> 1].valid) {
+        flags[id] = 0;
+        return;
+    }
+    ge_p3 acc;
+    ge_p3_0(acc);
+    const uint8_t* ws = winsum + (size_t)id * 64 * 128;
+    for (int w = 63; w >= 0; w--) {
+        ge_dbl(acc, acc);
+        ge_dbl(acc, acc);
+        ge_dbl(acc, acc);
+        ge_dbl(acc, acc);
+        ge_p3 x;
+        ge_load(x, ws + (size_t)w * 128);
+        ge_add(acc, acc, x);
+    }
+    ge_p3 F;
+    ge_load(F, fsum + (size_t)id * 128);
+    fe a, b, c, d;
+    fe_mul(a, F.X, acc.Z);
+    fe_mul(b, acc.X, F.Z);
+    fe_mul(c, F.Y, acc.Z);
+    fe_mul(d, acc.Y, F.Z);
+    flags[id] = (fe_equal(a, b) && fe_equal(c, d)) ? 1 : 0;
+}
+__global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_t num, uint8_t* __restrict__ accept) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < num) accept[p] = flags[2 * p] & flags[2 * p + 1];
+}
+
+static constexpr size_t kVerifyChunk = 4096;  // proofs per pass: bounds the window-sum scratch (16 KiB / proof)
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace cbp
+
+using namespace cbp;
+
+extern "C" {
+
+size_t bpk_proof_record_bytes(size_t n) {
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    return proof_record_bytes(k);
+}
+int bpk_gens_workspace_bytes(size_t n, size_t* bytes) {
+    if (!bytes || n == 0 || n > kMaxN || (n & (n - 1))) return fail(BPK_ERR_ARG);
+    size_t nb = 2 * n + 2;
+    size_t table = nb * kFixWin * kFixEntries * 96;
+    size_t scratch = nb * kFixWin * kFixEntries * 32 + nb * kFixWin * 128;
+    *bytes = 256 + align256(table) + align256(scratch) + align256(nb * 128);
+    return BPK_OK;
+}
+int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
+                         const void* d_h, size_t n, void* stream) {
+    size_t need = 0;
+    if (bpk_gens_workspace_bytes(n, &need) != BPK_OK) return BPK_ERR_ARG;
+    if (!d_gens_ws || !d_G || !d_H || !d_g || !d_h) return fail(BPK_ERR_ARG);
+    if (ws_bytes < need) return fail(BPK_ERR_WORKSPACE);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t nb = (uint32_t)(2 * n + 2);
+    GensHeader hd;
+    memset(&hd, 0, sizeof hd);
+    hd.magic = kGensMagic;
+    hd.n = (uint32_t)n;
+    hd.nbases = nb;
+    hd.table_off = 256;
+    hd.scratch_off = hd.table_off + align256((size_t)nb * kFixWin * kFixEntries * 96);
+    hd.bases_off = hd.scratch_off + align256((size_t)nb * kFixWin * kFixEntries * 32 + (size_t)nb * kFixWin * 128);
+    uint8_t* ws = (uint8_t*)d_gens_ws;
+    CBP_CUDA(cudaMemcpyAsync(ws, &hd, sizeof hd, cudaMemcpyHostToDevice, st));
+    uint8_t* prefix = ws + hd.scratch_off;
+    uint8_t* pow = prefix + (size_t)nb * kFixWin * kFixEntries * 32;
+    gens_pow_kernel<<<(nb + 63) / 64, 64, 0, st>>>((const uint8_t*)d_G, (const uint8_t*)d_H, (const uint8_t*)d_g,
+                                                  (const uint8_t*)d_h, (uint32_t)n, pow, ws + hd.bases_off);
+    CBP_CHECK_LAUNCH();
+    gens_table_kernel<<<(nb * kFixWin + 63) / 64, 64, 0, st>>>(pow, nb, ws + hd.table_off, prefix);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+int bpk_range_verify_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes) {
+    if (!bytes || n == 0 || n > kMaxN || (n & (n - 1))) return fail(BPK_ERR_ARG);
+    size_t chunk = num_proofs < kVerifyChunk ? num_proofs : kVerifyChunk;
+    if (chunk == 0) chunk = 1;
+    *bytes = align256(chunk * sizeof(VScal)) + align256(chunk * 2 * 128) + align256(chunk * 2 * 64 * 128) +
+             align256(chunk * 2);
+    return BPK_OK;
+}
+int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, const void* d_V, size_t n,
+                                  size_t num_proofs, uint8_t* d_accept, void* d_workspace, size_t workspace_bytes,
+                                  void* stream) {
+    size_t need = 0;
+    if (bpk_range_verify_workspace_bytes(n, num_proofs, &need) != BPK_OK) return BPK_ERR_ARG;
+    if (!num_proofs) return BPK_OK;
+    if (!d_gens_ws || !d_proofs || !d_accept || !d_workspace) return fail(BPK_ERR_ARG);
+    if (workspace_bytes < need) return fail(BPK_ERR_WORKSPACE);
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    size_t rec = proof_record_bytes(k);
+    size_t chunk = num_proofs < kVerifyChunk ? num_proofs : kVerifyChunk;
+    uint8_t* ws = (uint8_t*)d_workspace;
+    VScal* vscal = (VScal*)ws;
+    uint8_t* fsum = ws + align256(chunk * sizeof(VScal));
+    uint8_t* winsum = fsum + align256(chunk * 2 * 128);
+    uint8_t* flags = winsum + align256(chunk * 2 * 64 * 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (size_t done = 0; done < num_proofs; done += chunk) {
+        uint32_t cnt = (uint32_t)((num_proofs - done) < chunk ? (num_proofs - done) : chunk);
+        const uint8_t* pr = (const uint8_t*)d_proofs + done * rec;
+        const uint8_t* ve = d_V ? (const uint8_t*)d_V + done * 128 : nullptr;
+        verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
+        CBP_CHECK_LAUNCH();
+        verify_msm_kernel<<<cnt, kVThreads, 0, st>>>((const uint8_t*)d_gens_ws, pr, rec, (uint32_t)n, k, vscal, fsum,
+                                                     winsum);
+        CBP_CHECK_LAUNCH();
+        verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
+        CBP_CHECK_LAUNCH();
+        verify_combine_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(flags, cnt, d_accept + done);
+        CBP_CHECK_LAUNCH();
+    }
+    return BPK_OK;
+}
+
+}  // extern "C"

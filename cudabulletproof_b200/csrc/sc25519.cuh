@@ -65,7 +65,7 @@ __device__ __forceinline__ void sc_sub_l9(uint32_t (&r)[9]) {
 
 // r = x mod l for a 512-bit x (16 words).  Barrett: q3 = floor(floor(x / b^7) * mu / b^9),
 // r = (x - q3 l) mod b^9, then at most two subtractions of l.
-__device__ __noinline__ static void sc_reduce512(sc& out, const uint32_t (&x)[16]) {
+__device__ __forceinline__ void sc_reduce512(sc& out, const uint32_t (&x)[16]) {
     // q2 = q1 * mu, only words >= 9 are needed (q3); compute full columns from 7 up for exact carries
     uint32_t q3[9];
     {

@@ -159,3 +159,115 @@ def synth_scalars(n, seed, bits=252, device="cuda", stream=None):
     _check(_lib().bpk_synth_scalars_device(sc.data_ptr(), n, seed, bits, _stream_ptr(stream)),
            "bpk_synth_scalars_device")
     return sc
+
+
+# ---------------- range proofs ----------------
+def proof_record_bytes(n):
+    return int(_lib().bpk_proof_record_bytes(n))
+
+
+class Generators:
+    """Device-resident generator set (G[n], H[n], g, h) with its fixed-base tables.
+    G, H: (n, 16) uint64 numpy arrays or (n,128) uint8 cuda tensors; g, h: (16,) / (128,)."""
+
+    def __init__(self, G, H, g, h, device="cuda", stream=None):
+        import torch
+        self.device = torch.device(device)
+
+        def dev(a):
+            if isinstance(a, np.ndarray):
+                a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.uint8).reshape(-1))
+            return a.to(self.device).contiguous().view(torch.uint8).reshape(-1)
+
+        dG, dH, dg, dh = dev(G), dev(H), dev(g), dev(h)
+        self.n = dG.numel() // 128
+        assert dH.numel() == self.n * 128 and dg.numel() == 128 and dh.numel() == 128
+        nbytes = C.c_size_t(0)
+        _check(_lib().bpk_gens_workspace_bytes(self.n, C.byref(nbytes)), "bpk_gens_workspace_bytes")
+        self.workspace = _dev_u8(nbytes.value, self.device)
+        _check(_lib().bpk_gens_init_device(self.workspace.data_ptr(), self.workspace.numel(), dG.data_ptr(),
+                                           dH.data_ptr(), dg.data_ptr(), dh.data_ptr(), self.n, _stream_ptr(stream)),
+               "bpk_gens_init_device")
+        torch.cuda.current_stream().synchronize()  # inputs may be temporaries
+        self.record_bytes = proof_record_bytes(self.n)
+
+
+def range_prove_batch(gens, values, gammas, seeds, stream=None):
+    """values: (m,) int/uint64, gammas: (m,4) uint64 scalars, seeds: (m,) -> (m, record_bytes) uint8 cuda tensor."""
+    import torch
+    m = len(values)
+    d_v = torch.from_numpy(np.asarray(values, dtype=np.uint64).view(np.int64)).to(gens.device)
+    d_s = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(gens.device)
+    d_g = torch.from_numpy(np.ascontiguousarray(gammas, dtype=np.uint64).view(np.uint8).reshape(-1)).to(gens.device)
+    out = torch.zeros((m, gens.record_bytes), dtype=torch.uint8, device=gens.device)
+    _check(_lib().bpk_range_prove_batch_device(gens.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(),
+                                               d_s.data_ptr(), gens.n, m, out.data_ptr(), None, 0,
+                                               _stream_ptr(stream)), "bpk_range_prove_batch_device")
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
+class RangeVerifier:
+    """Batched verification with a reusable workspace: accept[i] in {0,1} per proof record."""
+
+    def __init__(self, gens, max_proofs):
+        import torch
+        self.gens, self.max_proofs = gens, int(max_proofs)
+        nbytes = C.c_size_t(0)
+        _check(_lib().bpk_range_verify_workspace_bytes(gens.n, self.max_proofs, C.byref(nbytes)),
+               "bpk_range_verify_workspace_bytes")
+        self.workspace = _dev_u8(nbytes.value, gens.device)
+        self.accept = torch.zeros(self.max_proofs, dtype=torch.uint8, device=gens.device)
+
+    def __call__(self, proofs, V=None, stream=None, out=None):
+        m = proofs.numel() // self.gens.record_bytes
+        assert m <= self.max_proofs and proofs.is_cuda
+        out = self.accept if out is None else out
+        _check(_lib().bpk_range_verify_batch_device(self.gens.workspace.data_ptr(), proofs.data_ptr(),
+                                                    V.data_ptr() if V is not None else None, self.gens.n, m,
+                                                    out.data_ptr(), self.workspace.data_ptr(),
+                                                    self.workspace.numel(), _stream_ptr(stream)),
+               "bpk_range_verify_batch_device")
+        return out[:m]
+
+
+def cuda_range_proof_verify(proof, V, n, G, H, g, h):
+    """Drop-in (cuda_bulletproof.h:61): proof is a ctypes RangeProof (any struct with the reference layout),
+    V/g/h (16,) uint64, G/H (n,16) uint64."""
+    G, H = _c(G, 16), _c(H, 16)
+    gv, hv = _pv(G), _pv(H)
+    V = np.ascontiguousarray(V, dtype=np.uint64)
+    g = np.ascontiguousarray(g, dtype=np.uint64)
+    h = np.ascontiguousarray(h, dtype=np.uint64)
+    return bool(_lib().cuda_range_proof_verify(C.byref(proof), _ptr(V), n, C.byref(gv), C.byref(hv), _ptr(g), _ptr(h)))
+
+
+def cuda_inner_product_verify(proof, P, G, H, Q):
+    G, H = _c(G, 16), _c(H, 16)
+    gv, hv = _pv(G), _pv(H)
+    P = np.ascontiguousarray(P, dtype=np.uint64)
+    Q = np.ascontiguousarray(Q, dtype=np.uint64)
+    return bool(_lib().cuda_inner_product_verify(C.byref(proof), _ptr(P), C.byref(gv), C.byref(hv), _ptr(Q)))
+
+
+def ipa_fold_scalars(a, b, u, u_inv, stream=None):
+    """a, b: cuda uint8 (2n', 32); u, u_inv: cuda uint8 (32,) -> folded (n', 32) tensors."""
+    import torch
+    nh = a.numel() // 64
+    ao = torch.empty((nh, 32), dtype=torch.uint8, device=a.device)
+    bo = torch.empty((nh, 32), dtype=torch.uint8, device=a.device)
+    _check(_lib().bpk_ipa_fold_scalars_device(ao.data_ptr(), bo.data_ptr(), a.data_ptr(), b.data_ptr(), nh,
+                                              u.data_ptr(), u_inv.data_ptr(), _stream_ptr(stream)),
+           "bpk_ipa_fold_scalars_device")
+    return ao, bo
+
+
+def ipa_fold_points(G, H, u, u_inv, stream=None):
+    import torch
+    nh = G.numel() // 256
+    Go = torch.empty((nh, 128), dtype=torch.uint8, device=G.device)
+    Ho = torch.empty((nh, 128), dtype=torch.uint8, device=G.device)
+    _check(_lib().bpk_ipa_fold_points_device(Go.data_ptr(), Ho.data_ptr(), G.data_ptr(), H.data_ptr(), nh,
+                                             u.data_ptr(), u_inv.data_ptr(), _stream_ptr(stream)),
+           "bpk_ipa_fold_points_device")
+    return Go, Ho

@@ -76,12 +76,20 @@ size_t bpk_proof_record_bytes(size_t n);
 int bpk_gens_workspace_bytes(size_t n, size_t* bytes);
 int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
                          const void* d_h, size_t n, void* stream);
-/* d_accept[i] = 1 iff proof i verifies (exact checks).  One CTA per proof. */
-int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, size_t n, size_t num_proofs,
-                                  uint8_t* d_accept, void* stream);
-/* deterministic batch prover used to synthesise benchmark inputs: values[i] < 2^n, seeds[i] */
-int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const uint64_t* d_seeds, size_t n,
-                                 size_t num_proofs, void* d_proofs, void* stream);
+/* d_accept[i] = 1 iff proof i verifies (exact checks, bit-exact with the CPU oracle's range_proof_verify).
+ * d_V (optional, num_proofs ge25519): the caller's commitments, each must equal its proof's V
+ * (bulletproof_range_proof.cu:1729-1740); NULL skips that check. */
+int bpk_range_verify_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes);
+int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, const void* d_V, size_t n,
+                                  size_t num_proofs, uint8_t* d_accept, void* d_workspace, size_t workspace_bytes,
+                                  void* stream);
+/* deterministic batch prover (generate_range_proof, bulletproof_range_proof.cu:1159-1714, restated):
+ * proof i commits d_values[i] (< 2^n) with blinding and nonces drawn from the SplitMix64 stream
+ * seeded by d_seeds[i] — the same stream oracle/ref_corrected.c draws, so proofs are bit-identical. */
+int bpk_range_prove_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes);
+int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas /* 32 B each */,
+                                 const uint64_t* d_seeds, size_t n, size_t num_proofs, void* d_proofs,
+                                 void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- synthetic inputs (bench / tests): P_i = k_i * B for a hash-derived 64-bit k_i, returned
  * normalised, plus k_i itself so that callers can check MSMs against a scalar identity ---- */

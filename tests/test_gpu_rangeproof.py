@@ -1,0 +1,232 @@
+"""GPU parity for the range-proof path (BASELINE.json configs 1, 2, 5): batched prover and verifier
+vs the CPU oracle (oracle/ref_corrected.c) — proofs byte-identical, accept/reject identical, every
+tampered field rejected — plus the host-pointer drop-ins cuda_range_proof_verify /
+cuda_inner_product_verify and the IPA folding kernels."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from oracle import pyref
+from tests.helpers import Gens, flatten_proof, oracle_prove, oracle_verify
+
+pytestmark = pytest.mark.gpu
+
+L = pyref.L
+
+
+@pytest.fixture(scope="module")
+def gens16(oracle):
+    return Gens(oracle, 16)
+
+
+@pytest.fixture(scope="module")
+def gens64(oracle):
+    return Gens(oracle, 64)
+
+
+def dev_gens(g):
+    import cudabulletproof_b200 as cbp
+    return cbp.Generators(g.G, g.H, g.g, g.h)
+
+
+def gamma_for(seed):
+    return (0x1234567 + seed * 7919) % (2**252)
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_gpu_prover_is_byte_identical_to_oracle(oracle, gens16, gens64, n):
+    import cudabulletproof_b200 as cbp
+    g = gens16 if n == 16 else gens64
+    dg = dev_gens(g)
+    cases = [(42, 1), (0, 2), (2**n - 1, 3), (0xBEEF & (2**n - 1), 4)]
+    vals = [v for v, _ in cases]
+    seeds = [s for _, s in cases]
+    gam = ob.ints_to_fe([gamma_for(s) for s in seeds])
+    got = cbp.range_prove_batch(dg, vals, gam, seeds).cpu().numpy()
+    for i, (v, s) in enumerate(cases):
+        proof, V = oracle_prove(oracle, g, v, s)
+        want = flatten_proof(proof, n).view(np.uint8)
+        assert np.array_equal(got[i], want), (n, v, s, np.nonzero(got[i] != want)[0][:8])
+        oracle.range_proof_free(C.byref(proof))
+
+
+def test_gpu_prover_out_of_range_value(oracle, gens16):
+    """config 1: value 65536 with n = 16 must not yield a valid proof (D20: initialised, invalid)."""
+    import cudabulletproof_b200 as cbp
+    dg = dev_gens(gens16)
+    gam = ob.ints_to_fe([gamma_for(2)])
+    got = cbp.range_prove_batch(dg, [65536], gam, [2])
+    proof, V = oracle_prove(oracle, gens16, 65536, 2)
+    assert np.array_equal(got[0].cpu().numpy(), flatten_proof(proof, 16).view(np.uint8))
+    ver = cbp.RangeVerifier(dg, 1)
+    assert int(ver(got)[0]) == 0
+    assert not oracle_verify(oracle, gens16, proof, V)
+    oracle.range_proof_free(C.byref(proof))
+
+
+def tamper_cases(rec_bytes, k, rng):
+    """byte offsets covering every field of the record"""
+    offs = [0, 32 + 5, 64, 96 + 31, 128 + 3, 256 + 40, 384 + 70, 512 + 100, 640, 672 + 8, 704 + 16, 736, 768 + 9, 800, 832 + 1]
+    for j in range(2 * k):
+        offs.append(864 + 128 * j + rng.randrange(0, 64))
+    return offs
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_batch_verify_matches_oracle_honest_and_tampered(oracle, gens16, gens64, n):
+    import torch
+    import cudabulletproof_b200 as cbp
+    g = gens16 if n == 16 else gens64
+    dg = dev_gens(g)
+    k = n.bit_length() - 1
+    rng = random.Random(n)
+    recs, expect, structs = [], [], []
+    for s, v in [(11, 42), (12, 2**n - 1)]:
+        proof, V = oracle_prove(oracle, g, v, s)
+        base = flatten_proof(proof, n).view(np.uint8).copy()
+        recs.append(base)
+        expect.append(oracle_verify(oracle, g, proof, V))
+        oracle.range_proof_free(C.byref(proof))
+    assert expect == [True, True]
+    base = recs[0]
+    for off in tamper_cases(len(base), k, rng):
+        bad = base.copy()
+        bad[off] ^= 1 << rng.randrange(8)
+        recs.append(bad)
+        expect.append(False)
+    d = torch.from_numpy(np.stack(recs)).cuda()
+    ver = cbp.RangeVerifier(dg, len(recs))
+    got = ver(d).cpu().numpy().astype(bool).tolist()
+    assert got == expect
+    # spot-check a few tampered records against the oracle itself through the drop-in struct path
+    from tests.test_gpu_rangeproof import record_to_struct  # noqa
+    for idx in [2, 5, 9, 12, len(recs) - 1]:
+        proof, V, keep = record_to_struct(recs[idx], n)
+        assert oracle_verify(oracle, g, proof, V) == got[idx]
+
+
+def record_to_struct(rec, n):
+    """flat record -> ctypes RangeProof (oracle layout) + V, keeping the backing arrays alive"""
+    k = n.bit_length() - 1
+    w = np.ascontiguousarray(rec).view(np.uint64)
+    proof = ob.RangeProof()
+    C.memmove(C.byref(proof), w[0:92].tobytes(), 92 * 8)
+    a, b = w[92:96].copy().reshape(1, 4), w[96:100].copy().reshape(1, 4)
+    Ls = w[108:108 + 16 * k].copy().reshape(k, 16)
+    Rs = w[108 + 16 * k:108 + 32 * k].copy().reshape(k, 16)
+    ip = proof.ip_proof
+    ip.n = n
+    ip.a, ip.b = ob.field_vector(a), ob.field_vector(b)
+    C.memmove(C.byref(ip.c), w[100:104].tobytes(), 32)
+    C.memmove(C.byref(ip.x), w[104:108].tobytes(), 32)
+    ip.L, ip.R = ob.point_vector(Ls), ob.point_vector(Rs)
+    ip.L_len = k
+    V = w[0:16].copy()
+    return proof, V, (a, b, Ls, Rs)
+
+
+def test_dropin_cuda_range_proof_verify_config1(oracle, gens16):
+    """complete_bulletproof_test.cu:153,247: 16-bit proof of 42 accepts; the 65536 attempt rejects;
+    a wrong external V rejects; wrong generator vector length rejects (nb:6669-6672)."""
+    import cudabulletproof_b200 as cbp
+    g = gens16
+    proof, V = oracle_prove(oracle, g, 42, seed=1)
+    assert cbp.cuda_range_proof_verify(proof, V, 16, g.G, g.H, g.g, g.h) is True
+    assert cbp.cuda_range_proof_verify(proof, V, 16, g.G, g.H, g.g, g.h) is True  # cached generator tables
+    V2 = V.copy()
+    V2[1] ^= 2
+    assert cbp.cuda_range_proof_verify(proof, V2, 16, g.G, g.H, g.g, g.h) is False
+    assert cbp.cuda_range_proof_verify(proof, V, 16, g.G[:8], g.H, g.g, g.h) is False
+    proof.mu.limbs[0] ^= 1
+    assert cbp.cuda_range_proof_verify(proof, V, 16, g.G, g.H, g.g, g.h) is False
+    oracle.range_proof_free(C.byref(proof))
+    bad, Vb = oracle_prove(oracle, g, 65536, seed=2)
+    assert cbp.cuda_range_proof_verify(bad, Vb, 16, g.G, g.H, g.g, g.h) is False
+    oracle.range_proof_free(C.byref(bad))
+
+
+@pytest.mark.parametrize("n", [2, 8, 64])
+def test_dropin_cuda_inner_product_verify(oracle, gens64, n):
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(90 + n)
+    a = ob.ints_to_fe([rng.getrandbits(252) for _ in range(n)])
+    b = ob.ints_to_fe([rng.getrandbits(252) for _ in range(n)])
+    G, H, Q = gens64.G[:n].copy(), gens64.H[:n].copy(), gens64.h
+    av, bv, Gv, Hv = ob.field_vector(a), ob.field_vector(b), ob.point_vector(G), ob.point_vector(H)
+    c = np.zeros(4, dtype=np.uint64)
+    oracle.field_vector_inner_product(ob.ptr(c), C.byref(av), C.byref(bv))
+    P1, P2, P3, P = (np.zeros(16, dtype=np.uint64) for _ in range(4))
+    oracle.point_vector_multi_scalar_mul(ob.ptr(P1), C.byref(av), C.byref(Gv))
+    oracle.point_vector_multi_scalar_mul(ob.ptr(P2), C.byref(bv), C.byref(Hv))
+    oracle.ge25519_scalarmult(ob.ptr(P3), ob.fe_to_int(c).to_bytes(32, "little"), ob.ptr(Q))
+    oracle.ge25519_add(ob.ptr(P), ob.ptr(P1), ob.ptr(P2))
+    oracle.ge25519_add(ob.ptr(P), ob.ptr(P), ob.ptr(P3))
+    proof = ob.InnerProductProof()
+    oracle.inner_product_prove(C.byref(proof), C.byref(av), C.byref(bv), C.byref(Gv), C.byref(Hv), ob.ptr(Q), ob.ptr(c),
+                               bytes(32))
+    assert oracle.inner_product_verify(C.byref(proof), ob.ptr(P), C.byref(Gv), C.byref(Hv), ob.ptr(Q))
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is True
+    proof.b.elements[0].limbs[2] ^= 4
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
+    proof.b.elements[0].limbs[2] ^= 4
+    proof.L.elements[0].Y.limbs[0] ^= 1  # off-curve L
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
+    proof.L.elements[0].Y.limbs[0] ^= 1
+    P[5] ^= 1
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
+    oracle.inner_product_proof_free(C.byref(proof))
+
+
+@pytest.mark.parametrize("n_half", [1, 8, 32])
+def test_ipa_fold_kernels_match_oracle(oracle, gens64, n_half):
+    import torch
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(400 + n_half)
+    n = 2 * n_half
+    a = ob.ints_to_fe([rng.getrandbits(256) for _ in range(n)])  # unreduced inputs allowed
+    b = ob.ints_to_fe([rng.getrandbits(252) for _ in range(n)])
+    u_int = rng.getrandbits(252) % L
+    u, ui = ob.int_to_fe(u_int), ob.int_to_fe(pow(u_int, L - 2, L))
+    G, H = gens64.G[:n].copy(), gens64.H[:n].copy()
+    wa, wb = np.zeros((n_half, 4), np.uint64), np.zeros((n_half, 4), np.uint64)
+    wG, wH = np.zeros((n_half, 16), np.uint64), np.zeros((n_half, 16), np.uint64)
+    oracle.ipa_fold_scalars(ob.ptr(wa), ob.ptr(wb), ob.ptr(a), ob.ptr(b), n_half, ob.ptr(u), ob.ptr(ui))
+    oracle.ipa_fold_points(ob.ptr(wG), ob.ptr(wH), ob.ptr(G), ob.ptr(H), n_half, ob.ptr(u), ob.ptr(ui))
+
+    def dev(x):
+        return torch.from_numpy(x.view(np.uint8).reshape(-1)).cuda()
+
+    ga, gb = cbp.ipa_fold_scalars(dev(a), dev(b), dev(u), dev(ui))
+    gG, gH = cbp.ipa_fold_points(dev(G), dev(H), dev(u), dev(ui))
+    assert np.array_equal(ga.cpu().numpy().view(np.uint64).reshape(n_half, 4), wa)
+    assert np.array_equal(gb.cpu().numpy().view(np.uint64).reshape(n_half, 4), wb)
+    assert np.array_equal(gG.cpu().numpy().view(np.uint64).reshape(n_half, 16), wG)
+    assert np.array_equal(gH.cpu().numpy().view(np.uint64).reshape(n_half, 16), wH)
+
+
+def test_batch_verify_larger_batch_with_one_percent_tampered(oracle, gens64):
+    """config 5 in miniature: 256 GPU-proved 64-bit proofs, a few tampered; decisions must equal the
+    oracle's on a sample and all honest proofs must accept."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    dg = dev_gens(gens64)
+    m = 256
+    rng = random.Random(5)
+    vals = [rng.getrandbits(64) for _ in range(m)]
+    seeds = list(range(1000, 1000 + m))
+    gam = ob.ints_to_fe([gamma_for(s) for s in seeds])
+    proofs = cbp.range_prove_batch(dg, vals, gam, seeds)
+    bad_idx = sorted(rng.sample(range(m), 5))
+    h = proofs.cpu().numpy()
+    for i in bad_idx:
+        h[i, rng.randrange(h.shape[1])] ^= 1 << rng.randrange(8)
+    d = torch.from_numpy(h).cuda()
+    ver = cbp.RangeVerifier(dg, m)
+    got = ver(d).cpu().numpy().astype(bool)
+    assert [i for i in range(m) if not got[i]] == bad_idx
+    for i in bad_idx[:2] + [0, 7]:
+        proof, V, keep = record_to_struct(h[i], 64)
+        assert oracle_verify(oracle, gens64, proof, V) == bool(got[i])
