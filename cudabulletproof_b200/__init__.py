@@ -54,6 +54,9 @@ SIGNATURES = {
     "bpk_last_error": (_i, []),
     "bpk_last_cuda_error": (_i, []),
     "bpk_kernel_launches": (_u64, []),
+    "bpk_profile_enable": (_i, [_i]),
+    "bpk_profile_reset": (_i, []),
+    "bpk_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),
     "bpk_msm_workspace_bytes": (_i, [_sz, _i, C.POINTER(_sz)]),
     "bpk_msm_window_bits": (_i, [_sz]),
     "bpk_msm_device": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp]),

@@ -17,6 +17,9 @@ inline int fail(int code, cudaError_t ce = cudaSuccess) {
 }
 inline int fail_cuda(int ce) { return ce == 0 ? BPK_OK : fail(BPK_ERR_CUDA, (cudaError_t)ce); }
 inline void count_launches(int n) { g_launches.fetch_add((uint64_t)n); }
+// optional per-kernel timing: no-ops unless bpk_profile_enable(1)
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
 }  // namespace cbp
 
 #define CBP_CHECK_LAUNCH()                                                  \

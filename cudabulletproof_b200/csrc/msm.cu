@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include "ge25519.cuh"
 #include "msm.h"
+#include "common.h"
 
 namespace cbp {
 
@@ -355,11 +356,14 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
+    prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
     if (e != cudaSuccess) return (int)e;
     {
         size_t threads = (n + kPreChunk - 1) / kPreChunk;
+        prof_begin(BPK_PROF_MSM_PRECOMPUTE, st);
         msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)d_points, n, table);
+        prof_end(BPK_PROF_MSM_PRECOMPUTE, st);
         CBP_LAUNCH_CHECK(); nl++;
     }
     unsigned dgrid = (unsigned)((n + 255) / 256);
@@ -374,7 +378,9 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     CBP_LAUNCH_CHECK(); nl++;
     msm_digits_kernel<true><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, cursors, entries);
     CBP_LAUNCH_CHECK(); nl++;
+    prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
     msm_accumulate_kernel<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(table, entries, offsets, nullptr, p.nbuckets, buckets);
+    prof_end(BPK_PROF_MSM_ACCUMULATE, st);
     CBP_LAUNCH_CHECK(); nl++;
     // reduction levels
     const uint8_t* X = buckets;
@@ -396,6 +402,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     } while (n_in > 1);
     msm_finish_kernel<<<1, 32, 0, st>>>(X, Y, p.W, p.c, normalize, (uint8_t*)d_result);
     CBP_LAUNCH_CHECK(); nl++;
+    prof_end(BPK_PROF_MSM_TOTAL, st);
     if (launches) *launches = nl;
     return 0;
 }

@@ -552,20 +552,24 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     uint8_t* winsum = fsum + align256(chunk * 2 * 128);
     uint8_t* flags = winsum + align256(chunk * 2 * 64 * 128);
     cudaStream_t st = (cudaStream_t)stream;
+    prof_begin(BPK_PROF_VERIFY_TOTAL, st);
     for (size_t done = 0; done < num_proofs; done += chunk) {
         uint32_t cnt = (uint32_t)((num_proofs - done) < chunk ? (num_proofs - done) : chunk);
         const uint8_t* pr = (const uint8_t*)d_proofs + done * rec;
         const uint8_t* ve = d_V ? (const uint8_t*)d_V + done * 128 : nullptr;
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
+        prof_begin(BPK_PROF_VERIFY_MSM, st);
         verify_msm_kernel<<<cnt, kVThreads, 0, st>>>((const uint8_t*)d_gens_ws, pr, rec, (uint32_t)n, k, vscal, fsum,
                                                      winsum);
+        prof_end(BPK_PROF_VERIFY_MSM, st);
         CBP_CHECK_LAUNCH();
         verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
         CBP_CHECK_LAUNCH();
         verify_combine_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(flags, cnt, d_accept + done);
         CBP_CHECK_LAUNCH();
     }
+    prof_end(BPK_PROF_VERIFY_TOTAL, st);
     return BPK_OK;
 }
 

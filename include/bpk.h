@@ -32,6 +32,18 @@ int bpk_last_cuda_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t bpk_kernel_launches(void);
 
+/* ---- per-kernel device timing (bench.py's roofline): CUDA events recorded on the launching stream
+ * around the named kernel of every call while enabled; read returns the mean duration in ms ---- */
+#define BPK_PROF_MSM_ACCUMULATE 0 /* msm_accumulate_kernel  */
+#define BPK_PROF_MSM_TOTAL 1      /* whole bpk_msm_device   */
+#define BPK_PROF_VERIFY_MSM 2     /* verify_msm_kernel      */
+#define BPK_PROF_VERIFY_TOTAL 3   /* whole bpk_range_verify_batch_device */
+#define BPK_PROF_MSM_PRECOMPUTE 4 /* msm_precompute_kernel (HBM streaming) */
+#define BPK_PROF_KINDS 5
+int bpk_profile_enable(int enable);
+int bpk_profile_reset(void);
+int bpk_profile_read(int kind, float* mean_ms, int* samples); /* synchronises the recorded events */
+
 /* ---- multi-scalar multiplication: replaces cuda_point_vector_multi_scalar_mul (cuda_bulletproof.h:13) ---- */
 /* window_bits = 0 picks c(n).  *bytes = workspace needed by bpk_msm_device for that (n, window_bits). */
 int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes);
