@@ -159,6 +159,10 @@ __device__ __forceinline__ void mul_wide(uint32_t (&w)[16], const fe& a, const f
           "r"(O[12]), "r"(O[13]), "r"(O[14]));
 }
 
+// Note (measured, profiles/r01_microbench_int_pipe.jsonl): one level of subtractive Karatsuba (48 wide
+// multiplies + ~80 ALU instructions instead of 64) was tried and is SLOWER on B200 (100 vs 112 G fe_mul/s):
+// ptxas moves part of the extra carry/negate work onto the same FMA pipe (IMAD.MOV / IMAD.X), so the
+// schoolbook carry-chain form below stays.
 __device__ __forceinline__ void fe_mul(fe& r, const fe& a, const fe& b) {
     uint32_t w[16];
     mul_wide(w, a, b);

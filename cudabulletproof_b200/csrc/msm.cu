@@ -149,13 +149,19 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     block_total = smem[32 + (blockDim.x >> 5) - 1];
     return warp_off + x - v;
 }
+// SEG = true scans the per-bucket SEGMENT counts ceil(count / kSegLen) (>= 1) instead of the counts
+template <bool SEG>
+__device__ __forceinline__ uint32_t scan_input(uint32_t c, int seg_shift) {
+    return SEG ? (c ? (c + (1u << seg_shift) - 1u) >> seg_shift : 1u) : c;
+}
+template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint32_t total,
-                                                                      uint32_t* __restrict__ tile_sums) {
+                                                                      int seg_shift, uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t smem[64];
     uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPer, s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++)
-        if (base + j < total) s += in[base + j];
+        if (base + j < total) s += scan_input<SEG>(in[base + j], seg_shift);
     uint32_t bt;
     block_exclusive_scan(s, smem, bt);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = bt;
@@ -167,8 +173,9 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t* tile_sums, u
     uint32_t ex = block_exclusive_scan(v, smem, bt);
     if (threadIdx.x < ntiles) tile_sums[threadIdx.x] = ex;
 }
+template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t total,
-                                                                  const uint32_t* __restrict__ tile_sums,
+                                                                  int seg_shift, const uint32_t* __restrict__ tile_sums,
                                                                   uint32_t* __restrict__ offsets,
                                                                   uint32_t* __restrict__ cursors) {
     __shared__ uint32_t smem[64];
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
     uint32_t v[kScanPer], s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++) {
-        v[j] = base + j < total ? in[base + j] : 0;
+        v[j] = base + j < total ? scan_input<SEG>(in[base + j], seg_shift) : 0;
         s += v[j];
     }
     uint32_t bt;
@@ -184,22 +191,132 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 #pragma unroll
     for (int j = 0; j < kScanPer; j++) {
         if (base + j <= total) offsets[base + j] = ex;  // offsets[total] = grand total (sentinel)
-        if (base + j < total) cursors[base + j] = ex;
+        if (cursors && base + j < total) cursors[base + j] = ex;
         ex += v[j];
     }
 }
 
+// ---- warp-level point helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void ge_shfl_down(ge_p3& out, const ge_p3& in, int delta) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        out.X.v[j] = __shfl_down_sync(0xffffffffu, in.X.v[j], delta);
+        out.Y.v[j] = __shfl_down_sync(0xffffffffu, in.Y.v[j], delta);
+        out.Z.v[j] = __shfl_down_sync(0xffffffffu, in.Z.v[j], delta);
+        out.T.v[j] = __shfl_down_sync(0xffffffffu, in.T.v[j], delta);
+    }
+}
+__device__ __forceinline__ void ge_warp_sum(ge_p3& v) {  // result in lane 0
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        ge_p3 other;
+        ge_shfl_down(other, v, o);
+        ge_add(v, v, other);
+    }
+}
+
+// ---- 4b. segments: split long runs, order by length -----------------------------------------------------
+// A bucket's run of entries is cut into segments of at most kSegLen entries; one thread accumulates one
+// segment.  This bounds the serial work per thread (adversarial inputs: all scalars equal; ordinary
+// inputs: the top window of 252/253-bit scalars has few distinct digits, and the carry bucket of a
+// partially filled top window receives half of all points) and, because segments are then ordered by
+// length (counting sort, longest first, grouped by window group), the 32 segments of a warp run in
+// lockstep instead of waiting for the longest of 32 Poisson-distributed runs.
+static constexpr uint32_t kMinSegLen = 64;  // segment length = max(64, 2 * mean run length), a power of two
+static constexpr int kMaxGroups = 8;
+static constexpr int kSegBinsPerGroup = 65;  // length classes ceil(64 len / seglen), longest first
+static constexpr int kSegBins = 1024;  // >= kMaxGroups * kSegBinsPerGroup, = threads of the bin scan
+
+struct GroupMap {
+    int ngroups;
+    int w_hi[kMaxGroups], w_lo[kMaxGroups];  // processed top window first
+    uint8_t group_of_window[64];
+};
+
+__global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restrict__ counts,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ segoff, uint32_t nbuckets,
+                                                        uint32_t B, int seg_shift, GroupMap gm, uint2* __restrict__ desc,
+                                                        uint32_t* __restrict__ heavy, uint32_t* __restrict__ heavy_cnt) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nbuckets) return;
+    uint32_t c = counts[id], ns = scan_input<true>(c, seg_shift), so = segoff[id], start = offsets[id];
+    for (uint32_t q = 0; q < ns; q++) desc[so + q] = make_uint2(start + (q << seg_shift), id);
+    if (ns > 1) {
+        uint32_t w = id / B;
+        int g = gm.group_of_window[w];
+        uint32_t idx = atomicAdd(&heavy_cnt[g], 1u);
+        heavy[(uint32_t)gm.w_lo[g] * B + idx] = id;
+    }
+}
+__device__ __forceinline__ uint32_t seg_length(uint2 d, const uint32_t* __restrict__ offsets, int seg_shift) {
+    uint32_t rest = offsets[d.y + 1] - d.x, cap = 1u << seg_shift;
+    return rest < cap ? rest : cap;
+}
+__device__ __forceinline__ uint32_t seg_bin(uint2 d, const uint32_t* __restrict__ offsets, int seg_shift, uint32_t B,
+                                            const GroupMap& gm) {
+    uint32_t len = seg_length(d, offsets, seg_shift), w = d.y / B;
+    uint32_t cls = (len * 64u + (1u << seg_shift) - 1u) >> seg_shift;  // 0..64
+    return (uint32_t)gm.group_of_window[w] * kSegBinsPerGroup + (64u - cls);  // longest first within a group
+}
+__global__ void __launch_bounds__(256) seg_hist_kernel(const uint2* __restrict__ desc,
+                                                       const uint32_t* __restrict__ offsets,
+                                                       const uint32_t* __restrict__ nsegs_p, uint32_t B, int seg_shift,
+                                                       GroupMap gm, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[kSegBins];
+    for (int i = threadIdx.x; i < kSegBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint32_t nsegs = *nsegs_p;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsegs; i += gridDim.x * blockDim.x)
+        atomicAdd(&sh[seg_bin(desc[i], offsets, seg_shift, B, gm)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSegBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// exclusive scan of the bins in place; binstart (a copy) keeps the group boundaries for the accumulate launches
+__global__ void __launch_bounds__(kSegBins) seg_bin_scan_kernel(uint32_t* __restrict__ hist,
+                                                                uint32_t* __restrict__ binstart) {
+    __shared__ uint32_t smem[64];
+    uint32_t v = hist[threadIdx.x], bt;
+    uint32_t ex = block_exclusive_scan(v, smem, bt);
+    hist[threadIdx.x] = ex;
+    binstart[threadIdx.x] = ex;
+    if (threadIdx.x == 0) binstart[kSegBins] = bt;
+}
+__global__ void __launch_bounds__(256) seg_scatter_kernel(const uint2* __restrict__ desc,
+                                                          const uint32_t* __restrict__ offsets,
+                                                          const uint32_t* __restrict__ nsegs_p, uint32_t B,
+                                                          int seg_shift, GroupMap gm, uint32_t* __restrict__ cursors,
+                                                          uint32_t* __restrict__ order) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nsegs = *nsegs_p;
+    bool live = i < nsegs;
+    uint32_t bin = live ? seg_bin(desc[i], offsets, seg_shift, B, gm) : 0xffffffffu;
+    uint32_t active = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+    uint32_t peers = __match_any_sync(active, bin);  // warp-aggregated atomics
+    int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&cursors[bin], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
 // ---- 5. bucket accumulation ---------------------------------------------------------------------
-// One thread per (window, bucket).  order[] (optional) lists bucket ids longest-run first so that the
-// 32 buckets of a warp have near-equal run lengths.
+// One thread per segment of group g (order[] range from binstart).  7M mixed additions from the
+// 96-byte affine table, next operand prefetched while the current addition runs.
 __global__ void __launch_bounds__(128, 4)
     msm_accumulate_kernel(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
-                          const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order, uint32_t nbuckets,
-                          uint8_t* __restrict__ bucket_sums) {
+                          const uint2* __restrict__ desc, const uint32_t* __restrict__ offsets,
+                          const uint32_t* __restrict__ segoff, int seg_shift, const uint32_t* __restrict__ order,
+                          const uint32_t* __restrict__ binstart, int group,
+                          uint8_t* __restrict__ bucket_sums, uint8_t* __restrict__ seg_sums) {
+    uint32_t lo = binstart[group * kSegBinsPerGroup], hi = binstart[(group + 1) * kSegBinsPerGroup];
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nbuckets) return;
-    uint32_t id = order ? order[t] : t;
-    uint32_t e = offsets[id], end = offsets[id + 1];
+    if (t >= hi - lo) return;
+    uint32_t seg = order[lo + t];
+    uint2 d = desc[seg];
+    uint32_t e = d.x, end = d.x + seg_length(d, offsets, seg_shift), id = d.y;
     ge_p3 acc;
     ge_p3_0(acc);
     if (e < end) {
@@ -210,7 +327,7 @@ __global__ void __launch_bounds__(128, 4)
             uint32_t neg = ent & 1u;
             ge_niels cur = q;
             ++e;
-            if (e < end) {  // prefetch the next operand while this addition runs
+            if (e < end) {
                 ent = __ldg(entries + e);
                 ge_niels_load(q, table + (size_t)(ent >> 1) * 96);
             }
@@ -218,7 +335,31 @@ __global__ void __launch_bounds__(128, 4)
             if (e >= end) break;
         }
     }
-    ge_store(bucket_sums + (size_t)id * 128, acc);
+    bool single = segoff[id + 1] - segoff[id] == 1;
+    ge_store(single ? bucket_sums + (size_t)id * 128 : seg_sums + (size_t)seg * 128, acc);
+}
+// buckets cut into several segments: one warp adds the segment sums
+__global__ void __launch_bounds__(128) msm_heavy_fix_kernel(const uint32_t* __restrict__ heavy,
+                                                            const uint32_t* __restrict__ heavy_cnt, int group,
+                                                            uint32_t heavy_base, const uint32_t* __restrict__ segoff,
+                                                            const uint8_t* __restrict__ seg_sums,
+                                                            uint8_t* __restrict__ bucket_sums) {
+    uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    uint32_t cnt = heavy_cnt[group];
+    for (; gw < cnt; gw += (gridDim.x * blockDim.x) >> 5) {
+        uint32_t id = heavy[heavy_base + gw];
+        uint32_t s0 = segoff[id], s1 = segoff[id + 1];
+        ge_p3 acc;
+        ge_p3_0(acc);
+        for (uint32_t q = s0 + lane; q < s1; q += 32) {
+            ge_p3 x;
+            ge_load(x, seg_sums + (size_t)q * 128);
+            ge_add(acc, acc, x);
+        }
+        ge_warp_sum(acc);
+        if (lane == 0) ge_store(bucket_sums + (size_t)id * 128, acc);
+    }
 }
 
 // ---- 6. running-sum reduction -------------------------------------------------------------------
@@ -265,23 +406,96 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint8_t* __
     ge_store(Yout + ((size_t)w * n_out + t) * 128, tot);
 }
 
+// ---- 6b. warp-cooperative reduction level -------------------------------------------------------------
+// Same invariant as msm_reduce_level_kernel, but one WARP consumes 32*m pairs: each lane runs the
+// sequential running sum over its m pairs, then the 32 lane results are combined with shuffles:
+//   R = sum_l run_l (inclusive suffix scan S_l, R = S_0),  sum_l l*run_l = sum_{l>=1} S_l,
+//   T = sum_l tot_l + m * sum_l l*run_l,  U = sum_l u_l.
+// Depth ~ 3m + 20 point operations for a 32m-fold reduction: used for the upper (latency-bound) levels.
+__global__ void __launch_bounds__(128) msm_reduce_warp_kernel(const uint8_t* __restrict__ Xin,
+                                                              const uint8_t* __restrict__ Yin, uint32_t n_in,
+                                                              uint32_t n_out, int nwin, int has_y, int m,
+                                                              uint8_t* __restrict__ Xout, uint8_t* __restrict__ Yout) {
+    uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (gw >= n_out * (uint32_t)nwin) return;  // whole warp
+    uint32_t w = gw / n_out, t = gw % n_out;
+    const uint8_t* xb = Xin + (size_t)w * n_in * 128;
+    const uint8_t* yb = Yin + (size_t)w * n_in * 128;
+    ge_p3 run, tot, u;
+    ge_p3_0(run);
+    ge_p3_0(tot);
+    ge_p3_0(u);
+    uint32_t j0 = (t * 32 + lane) * (uint32_t)m;
+    for (int i = m - 1; i >= 0; i--) {
+        uint32_t j = j0 + i;
+        if (j < n_in) {
+            ge_p3 x;
+            ge_load(x, xb + (size_t)j * 128);
+            ge_add(run, run, x);
+            if (has_y) {
+                ge_p3 y;
+                ge_load(y, yb + (size_t)j * 128);
+                ge_add(u, u, y);
+            }
+        }
+        if (m > 1) ge_add(tot, tot, run);
+    }
+    if (m == 1) tot = run;
+    // inclusive suffix scan of run over the lanes
+    ge_p3 S = run;
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        ge_p3 other;
+        ge_shfl_down(other, S, o);
+        if (lane + o < 32) ge_add(S, S, other);
+    }
+    ge_p3 V = S;
+    if (lane == 0) ge_p3_0(V);
+    ge_warp_sum(V);  // sum_{l>=1} S_l = sum_l l * run_l
+    ge_p3 Csum;
+    ge_add(Csum, tot, u);
+    ge_warp_sum(Csum);  // sum_l (tot_l + u_l)
+    if (lane == 0) {
+        for (int q = 1; q < m; q <<= 1) ge_dbl(V, V);  // m * sum l run_l
+        ge_add(Csum, Csum, V);                         // T + U
+        ge_p3 MR = S;                                  // S_0 = R
+        for (int q = 1; q < 32 * m; q <<= 1) ge_dbl(MR, MR);
+        ge_p3 nMR;
+        ge_neg(nMR, MR);
+        ge_add(Csum, Csum, nMR);
+        ge_store(Xout + ((size_t)w * n_out + t) * 128, MR);
+        ge_store(Yout + ((size_t)w * n_out + t) * 128, Csum);
+    }
+}
+
 // ---- 7. window combine + normalise --------------------------------------------------------------
-// window sum S_w = X_w + Y_w (the single remaining pair, weight 1); result = sum_w 2^(cw) S_w.
-__global__ void msm_finish_kernel(const uint8_t* __restrict__ X, const uint8_t* __restrict__ Y, int W, int c,
-                                  int normalize, uint8_t* __restrict__ result) {
+// Horner chain over the windows, top down, kept in `state` between calls so that the chain for the
+// upper windows runs (on a second stream) while the lower windows are still being accumulated:
+//   for w = w_hi .. w_lo:  R += X_w + Y_w;  if (w > 0) R = 2^c R
+// The doublings after the last window of a call do not depend on the next group's sums.
+__global__ void msm_horner_kernel(const uint8_t* __restrict__ X, const uint8_t* __restrict__ Y, int w_hi, int w_lo,
+                                  int c, int first, int normalize, uint8_t* __restrict__ state,
+                                  uint8_t* __restrict__ result) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ge_p3 acc;
-    ge_p3_0(acc);
-    for (int w = W - 1; w >= 0; w--) {
-        for (int s = 0; s < c; s++) ge_dbl(acc, acc);
+    if (first) ge_p3_0(acc);
+    else ge_load(acc, state);
+    for (int w = w_hi; w >= w_lo; w--) {
         ge_p3 x, y;
         ge_load(x, X + (size_t)w * 128);
         ge_load(y, Y + (size_t)w * 128);
+        ge_add(x, x, y);
         ge_add(acc, acc, x);
-        ge_add(acc, acc, y);
+        if (w > 0)
+            for (int s = 0; s < c; s++) ge_dbl(acc, acc);
     }
-    if (normalize) ge_normalize(acc);
-    ge_store(result, acc);
+    if (w_lo == 0) {
+        if (normalize) ge_normalize(acc);
+        ge_store(result, acc);
+    } else {
+        ge_store(state, acc);
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -302,12 +516,18 @@ int msm_pick_window(size_t n) {
     return best_c;
 }
 
+static_assert(kMaxGroups * kSegBinsPerGroup <= kSegBins, "bin table too small");
+
 void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->n = n;
     p->c = c > 0 ? c : msm_pick_window(n);
     p->W = (256 + p->c - 1) / p->c;
     p->B = 1u << (p->c - 1);
     p->nbuckets = (uint32_t)p->W * p->B;
+    // segment length: a power of two, at least 64 and at least twice the mean run length n / B
+    p->seg_shift = 6;
+    while (((size_t)1 << p->seg_shift) < 2 * (n / p->B + 1) && p->seg_shift < 20) p->seg_shift++;
+    p->max_segs = (size_t)p->nbuckets + ((n * (size_t)p->W) >> p->seg_shift) + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -319,15 +539,23 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->off_offsets = take(((size_t)p->nbuckets + 1) * 4);
     p->off_cursors = take((size_t)p->nbuckets * 4);
     p->off_tiles = take(1024 * 4);
+    p->off_segoff = take(((size_t)p->nbuckets + 1) * 4);
+    p->off_desc = take(p->max_segs * 8);
+    p->off_order = take(p->max_segs * 4);
+    p->off_bins = take((2 * kSegBins + 1 + kMaxGroups) * 4);  // hist/cursors | binstart (+1) | heavy counters
+    p->off_heavy = take((size_t)p->nbuckets * 4);
     p->off_entries = take(n * (size_t)p->W * 4 + 4);
     p->off_buckets = take((size_t)p->nbuckets * 128);
-    // reduction ping-pong buffers: level 1 output has ceil(B/m) pairs per window
+    p->off_segsums = take(p->max_segs * 128);
     uint32_t n1 = (p->B + kReduceM - 1) / kReduceM;
     p->off_redX[0] = take((size_t)p->W * n1 * 128);
     p->off_redY[0] = take((size_t)p->W * n1 * 128);
-    uint32_t n2 = (n1 + kReduceM - 1) / kReduceM;
+    uint32_t n2 = (n1 + 31) / 32 + 1;
     p->off_redX[1] = take((size_t)p->W * n2 * 128);
     p->off_redY[1] = take((size_t)p->W * n2 * 128);
+    p->off_winX = take((size_t)p->W * 128);
+    p->off_winY = take((size_t)p->W * 128);
+    p->off_state = take(128);
     p->workspace_bytes = off;
 }
 
@@ -336,6 +564,61 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
         cudaError_t e_ = cudaGetLastError();      \
         if (e_ != cudaSuccess) return (int)e_;    \
     } while (0)
+
+// second stream + events for the window-group pipeline (one kit per device, created on first use)
+namespace {
+struct StreamKit {
+    cudaStream_t red[kMaxGroups] = {};  // one reduction stream per window group: group tails overlap each other
+    cudaStream_t aux = nullptr;         // the Horner chain, in group order
+    cudaEvent_t ev_group[kMaxGroups] = {}, ev_red[kMaxGroups] = {};
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    bool ok = false;
+};
+StreamKit g_kits[16];
+StreamKit* stream_kit() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    StreamKit& k = g_kits[dev];
+    if (!k.ok) {
+        if (cudaStreamCreateWithFlags(&k.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < kMaxGroups; i++) {
+            if (cudaStreamCreateWithFlags(&k.red[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&k.ev_group[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&k.ev_red[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&k.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&k.ev_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        k.ok = true;
+    }
+    return &k;
+}
+}  // namespace
+
+// windows are processed top-down in groups of halving size (.., 4, 2, 1, 1): while the lower groups are
+// still being accumulated, the upper groups are reduced and folded into the Horner chain on a second
+// stream, so only the last (single-window) group's reduction latency is exposed.
+static void make_groups(GroupMap* gm, int W, bool pipeline) {
+    gm->ngroups = 0;
+    int hi = W - 1;
+    if (!pipeline) {
+        gm->w_hi[0] = hi;
+        gm->w_lo[0] = 0;
+        gm->ngroups = 1;
+    } else {
+        int remaining = W;
+        while (remaining > 0) {
+            int take = remaining > 1 ? remaining / 2 : 1;
+            if (gm->ngroups == kMaxGroups - 1) take = remaining;
+            gm->w_hi[gm->ngroups] = hi;
+            gm->w_lo[gm->ngroups] = hi - take + 1;
+            gm->ngroups++;
+            hi -= take;
+            remaining -= take;
+        }
+    }
+    for (int g = 0; g < gm->ngroups; g++)
+        for (int w = gm->w_lo[g]; w <= gm->w_hi[g]; w++) gm->group_of_window[w] = (uint8_t)g;
+}
 
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
@@ -346,8 +629,19 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     uint32_t* offsets = (uint32_t*)(ws + p.off_offsets);
     uint32_t* cursors = (uint32_t*)(ws + p.off_cursors);
     uint32_t* tiles = (uint32_t*)(ws + p.off_tiles);
+    uint32_t* segoff = (uint32_t*)(ws + p.off_segoff);
+    uint2* desc = (uint2*)(ws + p.off_desc);
+    uint32_t* order = (uint32_t*)(ws + p.off_order);
+    uint32_t* bins = (uint32_t*)(ws + p.off_bins);
+    uint32_t* binstart = bins + kSegBins;
+    uint32_t* heavy_cnt = binstart + kSegBins + 1;
+    uint32_t* heavy = (uint32_t*)(ws + p.off_heavy);
     uint32_t* entries = (uint32_t*)(ws + p.off_entries);
     uint8_t* buckets = ws + p.off_buckets;
+    uint8_t* segsums = ws + p.off_segsums;
+    uint8_t* winX = ws + p.off_winX;
+    uint8_t* winY = ws + p.off_winY;
+    uint8_t* state = ws + p.off_state;
     int nl = 0;
     size_t n = p.n;
     if (n == 0) {  // empty sum = identity (the reference would cudaMalloc(0) and copy garbage)
@@ -356,8 +650,14 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
+    StreamKit* kit = n >= (1u << 15) ? stream_kit() : nullptr;
+    GroupMap gm;
+    make_groups(&gm, p.W, kit != nullptr);
+
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 1 + kMaxGroups) * 4, st);
     if (e != cudaSuccess) return (int)e;
     {
         size_t threads = (n + kPreChunk - 1) / kPreChunk;
@@ -370,38 +670,98 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     msm_digits_kernel<false><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, counts, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
     uint32_t ntiles = (p.nbuckets + 1 + kScanTile - 1) / kScanTile;  // +1: the sentinel slot
-    scan_tile_sums_kernel<<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, tiles);
+    scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, 0, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, tiles, offsets, cursors);
+    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, 0, tiles, offsets, cursors);
     CBP_LAUNCH_CHECK(); nl++;
     msm_digits_kernel<true><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, cursors, entries);
     CBP_LAUNCH_CHECK(); nl++;
-    prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
-    msm_accumulate_kernel<<<(p.nbuckets + 127) / 128, 128, 0, st>>>(table, entries, offsets, nullptr, p.nbuckets, buckets);
-    prof_end(BPK_PROF_MSM_ACCUMULATE, st);
+    // segments
+    scan_tile_sums_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, p.seg_shift, tiles);
     CBP_LAUNCH_CHECK(); nl++;
-    // reduction levels
-    const uint8_t* X = buckets;
-    const uint8_t* Y = buckets;
-    uint32_t n_in = p.B;
-    int has_y = 0, pp = 0;
-    do {
-        uint32_t n_out = (n_in + kReduceM - 1) / kReduceM;
-        uint8_t* Xo = ws + p.off_redX[pp];
-        uint8_t* Yo = ws + p.off_redY[pp];
-        uint32_t threads = n_out * (uint32_t)p.W;
-        msm_reduce_level_kernel<<<(threads + 127) / 128, 128, 0, st>>>(X, Y, n_in, n_out, p.W, has_y, Xo, Yo);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
+    CBP_LAUNCH_CHECK(); nl++;
+    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, p.seg_shift, tiles, segoff, nullptr);
+    CBP_LAUNCH_CHECK(); nl++;
+    const uint32_t* nsegs_p = segoff + p.nbuckets;
+    unsigned bgrid = (p.nbuckets + 255) / 256, sgrid = (unsigned)((p.max_segs + 255) / 256);
+    seg_build_kernel<<<bgrid, 256, 0, st>>>(counts, offsets, segoff, p.nbuckets, p.B, p.seg_shift, gm, desc, heavy, heavy_cnt);
+    CBP_LAUNCH_CHECK(); nl++;
+    seg_hist_kernel<<<sgrid < 1184 ? sgrid : 1184, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins);
+    CBP_LAUNCH_CHECK(); nl++;
+    seg_bin_scan_kernel<<<1, kSegBins, 0, st>>>(bins, binstart);
+    CBP_LAUNCH_CHECK(); nl++;
+    seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins, order);
+    CBP_LAUNCH_CHECK(); nl++;
+
+    for (int g = 0; g < gm.ngroups; g++) {
+        cudaStream_t tail = kit ? kit->red[g] : st;
+        int nwin = gm.w_hi[g] - gm.w_lo[g] + 1, w_lo = gm.w_lo[g];
+        // upper bound on this group's segments: its buckets + its share of the entries
+        size_t seg_bound = (size_t)nwin * p.B + ((n * (size_t)nwin) >> p.seg_shift) + 1;
+        if (g == 0) prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
+        msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, offsets, segoff,
+                                                                                  p.seg_shift, order, binstart, g, buckets,
+                                                                                  segsums);
+        if (g == gm.ngroups - 1) prof_end(BPK_PROF_MSM_ACCUMULATE, st);
         CBP_LAUNCH_CHECK(); nl++;
-        X = Xo;
-        Y = Yo;
-        n_in = n_out;
-        has_y = 1;
-        pp ^= 1;
-    } while (n_in > 1);
-    msm_finish_kernel<<<1, 32, 0, st>>>(X, Y, p.W, p.c, normalize, (uint8_t*)d_result);
-    CBP_LAUNCH_CHECK(); nl++;
+        if (kit) {
+            if ((e = cudaEventRecord(kit->ev_group[g], st)) != cudaSuccess) return (int)e;
+            if ((e = cudaStreamWaitEvent(tail, kit->ev_group[g], 0)) != cudaSuccess) return (int)e;
+        }
+        size_t heavy_bound = ((n * (size_t)nwin) >> p.seg_shift) + 1;
+        unsigned hgrid = (unsigned)((heavy_bound * 32 + 127) / 128);
+        msm_heavy_fix_kernel<<<hgrid < 2368 ? hgrid : 2368, 128, 0, tail>>>(heavy, heavy_cnt, g, (uint32_t)w_lo * p.B, segoff,
+                                                                            segsums, buckets);
+        CBP_LAUNCH_CHECK(); nl++;
+        // reduction levels for this group's windows
+        const uint8_t* X = buckets + (size_t)w_lo * p.B * 128;
+        const uint8_t* Y = X;
+        uint32_t n_in = p.B;
+        int has_y = 0, pp = 0, level = 0;
+        do {
+            bool seq = level == 0;  // level 0 is work-efficient (thread-sequential), upper levels warp-cooperative
+            int m = 1;
+            uint32_t n_out;
+            if (seq) {
+                n_out = (n_in + kReduceM - 1) / kReduceM;
+            } else {
+                while (m < 4 && (uint32_t)(32 * m) < n_in) m <<= 1;
+                n_out = (n_in + 32 * m - 1) / (32 * m);
+            }
+            uint8_t* Xo = n_out == 1 ? winX + (size_t)w_lo * 128 : ws + p.off_redX[pp] + (size_t)w_lo * n_out * 128;
+            uint8_t* Yo = n_out == 1 ? winY + (size_t)w_lo * 128 : ws + p.off_redY[pp] + (size_t)w_lo * n_out * 128;
+            if (seq) {
+                uint32_t threads = n_out * (uint32_t)nwin;
+                msm_reduce_level_kernel<<<(threads + 127) / 128, 128, 0, tail>>>(X, Y, n_in, n_out, nwin, has_y, Xo, Yo);
+            } else {
+                uint32_t threads = n_out * (uint32_t)nwin * 32;
+                msm_reduce_warp_kernel<<<(threads + 127) / 128, 128, 0, tail>>>(X, Y, n_in, n_out, nwin, has_y, m, Xo, Yo);
+            }
+            CBP_LAUNCH_CHECK(); nl++;
+            X = Xo;
+            Y = Yo;
+            n_in = n_out;
+            has_y = 1;
+            pp ^= 1;
+            level++;
+        } while (n_in > 1);
+        cudaStream_t hs = tail;
+        if (kit) {
+            hs = kit->aux;
+            if ((e = cudaEventRecord(kit->ev_red[g], tail)) != cudaSuccess) return (int)e;
+            if ((e = cudaStreamWaitEvent(hs, kit->ev_red[g], 0)) != cudaSuccess) return (int)e;
+        }
+        msm_horner_kernel<<<1, 32, 0, hs>>>(winX, winY, gm.w_hi[g], gm.w_lo[g], p.c, g == 0, normalize, state,
+                                            (uint8_t*)d_result);
+        CBP_LAUNCH_CHECK(); nl++;
+    }
+    if (kit) {
+        if ((e = cudaEventRecord(kit->ev_done, kit->aux)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(st, kit->ev_done, 0)) != cudaSuccess) return (int)e;
+    }
     prof_end(BPK_PROF_MSM_TOTAL, st);
     if (launches) *launches = nl;
     return 0;

@@ -12,8 +12,11 @@ struct MsmPlan {
     int W;              // number of windows = ceil(256 / c)
     uint32_t B;         // buckets per window = 2^(c-1)
     uint32_t nbuckets;  // W * B
-    size_t off_table, off_counts, off_offsets, off_cursors, off_tiles, off_entries, off_buckets;
-    size_t off_redX[2], off_redY[2];
+    int seg_shift;      // log2 of the accumulation segment length
+    size_t max_segs;    // upper bound on accumulation segments (buckets + entries / segment length)
+    size_t off_table, off_counts, off_offsets, off_cursors, off_tiles, off_segoff, off_desc, off_order, off_bins, off_heavy,
+        off_entries, off_buckets, off_segsums;
+    size_t off_redX[2], off_redY[2], off_winX, off_winY, off_state;
     size_t workspace_bytes;
 };
 
