@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -254,16 +254,12 @@ def run_cuda(args):
         n = 1 << args.log_n
         pts, _ = cbp.synth_points(n, seed=0xC3 + args.log_n + 1000 * rank, device=dev)
         sc = cbp.synth_scalars(n, seed=0x5CA1A000 + args.log_n + 1000 * rank, bits=252, device=dev)
-        msm = cbp.Msm(n, device=dev)
-        partial = torch.zeros(128, dtype=torch.uint8, device=dev)
-        gathered = torch.zeros((world, 128), dtype=torch.uint8, device=dev)
+        from cudabulletproof_b200.multi import ShardedMsm
+        smsm = ShardedMsm(n, world, dev)  # this rank's point range; NCCL all-gather of 128 B partials + point sum
+        msm = smsm.msm
 
         def step():
-            if world == 1:
-                return msm(sc, pts, normalize=True)
-            msm(sc, pts, normalize=False, out=partial)  # this rank's point range
-            dist.all_gather_into_tensor(gathered.view(-1), partial)  # NCCL has no EC-add: gather 128 B / rank
-            return cbp.point_sum(gathered, normalize=True)
+            return smsm(sc, pts)
 
         for _ in range(args.warmup):
             step()

@@ -1,6 +1,7 @@
 // capi_msm.cu — C ABI for the MSM path: device-resident bpk_msm_device and the host-pointer
 // drop-ins cuda_point_vector_multi_scalar_mul{,_shared} (reference cuda_bulletproof_kernels.cu:62-207).
 #include <stdio.h>
+#include <mutex>
 #include "../../include/cuda_bulletproof.h"
 #include "common.h"
 #include "ge25519.cuh"
@@ -108,7 +109,7 @@ int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* 
     msm_make_plan(&p, n, window_bits);
     if (n && workspace_bytes < p.workspace_bytes) return fail(BPK_ERR_WORKSPACE);
     int launches = 0;
-    int rc = msm_run(p, d_scalars, d_points, d_result, d_workspace, normalize, (cudaStream_t)stream, &launches);
+    int rc = msm_run(p, d_scalars, d_points, d_result, d_workspace, normalize, (cudaStream_t)stream, &launches, nullptr);
     count_launches(launches);
     return fail_cuda(rc);
 }
@@ -134,41 +135,65 @@ int bpk_synth_scalars_device(void* d_scalars, size_t n, uint64_t seed, int bits,
 }
 
 // ---- host-pointer drop-ins --------------------------------------------------------------------
+// The reference wrapper mallocs, copies, synchronises and frees on every call
+// (cuda_bulletproof_kernels.cu:77-115).  Here the device buffers are a grow-only cache (one per
+// process, guarded by a mutex), the scalars are uploaded first so that digit recoding / sorting
+// overlaps the (4x larger) point upload on a second stream, and there is one synchronisation.
+namespace {
+struct HostPath {
+    std::mutex mu;
+    uint8_t *d_s = nullptr, *d_p = nullptr, *d_ws = nullptr, *d_r = nullptr;
+    size_t cap_s = 0, cap_p = 0, cap_ws = 0;
+    cudaStream_t main = nullptr, copy = nullptr;
+    cudaEvent_t ev_points = nullptr;
+    bool ok = false;
+};
+HostPath g_hp;
+cudaError_t grow(uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+}  // namespace
+
 static int msm_host(ge25519* result, const FieldVector* scalars, const PointVector* points) {
     size_t n = scalars->length;
     MsmPlan p;
     msm_make_plan(&p, n, 0);
-    uint8_t *d_s = nullptr, *d_p = nullptr, *d_ws = nullptr, *d_r = nullptr;
-    cudaStream_t st = 0;
-    int rc = BPK_OK;
+    std::lock_guard<std::mutex> lock(g_hp.mu);
+    HostPath& hp = g_hp;
     cudaError_t e;
-    if ((e = cudaMalloc(&d_r, 128)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+    if (!hp.ok) {
+        if ((e = cudaStreamCreateWithFlags(&hp.main, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&hp.ev_points, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaMalloc(&hp.d_r, 256)) != cudaSuccess)
+            return fail(BPK_ERR_CUDA, e);
+        hp.ok = true;
+    }
     if (n) {
-        if ((e = cudaMalloc(&d_s, n * 32)) != cudaSuccess || (e = cudaMalloc(&d_p, n * 128)) != cudaSuccess ||
-            (e = cudaMalloc(&d_ws, p.workspace_bytes)) != cudaSuccess) {
-            rc = fail(BPK_ERR_CUDA, e);
-            goto done;
-        }
-        if ((e = cudaMemcpyAsync(d_s, scalars->elements, n * 32, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(d_p, points->elements, n * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
-            rc = fail(BPK_ERR_CUDA, e);
-            goto done;
-        }
+        if ((e = grow(&hp.d_s, &hp.cap_s, n * 32)) != cudaSuccess || (e = grow(&hp.d_p, &hp.cap_p, n * 128)) != cudaSuccess ||
+            (e = grow(&hp.d_ws, &hp.cap_ws, p.workspace_bytes)) != cudaSuccess)
+            return fail(BPK_ERR_CUDA, e);
+        if ((e = cudaMemcpyAsync(hp.d_s, scalars->elements, n * 32, cudaMemcpyHostToDevice, hp.main)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(hp.d_p, points->elements, n * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
+            (e = cudaEventRecord(hp.ev_points, hp.copy)) != cudaSuccess)
+            return fail(BPK_ERR_CUDA, e);
     }
-    rc = bpk_msm_device(d_s, d_p, n, d_r, d_ws, p.workspace_bytes, p.c, 1, st);
-    if (rc == BPK_OK) {
-        ge25519 tmp;
-        e = cudaMemcpyAsync(&tmp, d_r, 128, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = fail(BPK_ERR_CUDA, e);
-        else *result = tmp;
-    }
-done:
-    cudaFree(d_s);
-    cudaFree(d_p);
-    cudaFree(d_ws);
-    cudaFree(d_r);
-    return rc;
+    int launches = 0;
+    int rc = msm_run(p, hp.d_s, hp.d_p, hp.d_r, hp.d_ws, 1, hp.main, &launches, n ? hp.ev_points : nullptr);
+    count_launches(launches);
+    if (rc) return fail_cuda(rc);
+    ge25519 tmp;
+    e = cudaMemcpyAsync(&tmp, hp.d_r, 128, cudaMemcpyDeviceToHost, hp.main);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(hp.main);
+    if (e != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+    *result = tmp;
+    return BPK_OK;
 }
 
 void cuda_point_vector_multi_scalar_mul(ge25519* result, const FieldVector* scalars, const PointVector* points) {

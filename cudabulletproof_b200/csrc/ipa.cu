@@ -284,7 +284,7 @@ static bool ipa_verify_host(const InnerProductProof* proof, const ge25519* P, co
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         count_launches(2);
         int launches = 0;
-        int rc = msm_run(plan, d + off_sc, d + off_pt, d + off_res, d + off_ws, 0, st, &launches);
+        int rc = msm_run(plan, d + off_sc, d + off_pt, d + off_res, d + off_ws, 0, st, &launches, nullptr);
         count_launches(launches);
         if (rc) {
             e = (cudaError_t)rc;

@@ -622,7 +622,7 @@ static void make_groups(GroupMap* gm, int W, bool pipeline) {
 
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
-            int normalize, cudaStream_t st, int* launches) {
+            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready) {
     uint8_t* ws = (uint8_t*)d_ws;
     uint8_t* table = ws + p.off_table;
     uint32_t* counts = (uint32_t*)(ws + p.off_counts);
@@ -659,13 +659,6 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 1 + kMaxGroups) * 4, st);
     if (e != cudaSuccess) return (int)e;
-    {
-        size_t threads = (n + kPreChunk - 1) / kPreChunk;
-        prof_begin(BPK_PROF_MSM_PRECOMPUTE, st);
-        msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)d_points, n, table);
-        prof_end(BPK_PROF_MSM_PRECOMPUTE, st);
-        CBP_LAUNCH_CHECK(); nl++;
-    }
     unsigned dgrid = (unsigned)((n + 255) / 256);
     msm_digits_kernel<false><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, counts, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
@@ -696,6 +689,14 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins, order);
     CBP_LAUNCH_CHECK(); nl++;
 
+    if (points_ready && (e = cudaStreamWaitEvent(st, points_ready, 0)) != cudaSuccess) return (int)e;
+    {
+        size_t threads = (n + kPreChunk - 1) / kPreChunk;
+        prof_begin(BPK_PROF_MSM_PRECOMPUTE, st);
+        msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)d_points, n, table);
+        prof_end(BPK_PROF_MSM_PRECOMPUTE, st);
+        CBP_LAUNCH_CHECK(); nl++;
+    }
     for (int g = 0; g < gm.ngroups; g++) {
         cudaStream_t tail = kit ? kit->red[g] : st;
         int nwin = gm.w_hi[g] - gm.w_lo[g] + 1, w_lo = gm.w_lo[g];

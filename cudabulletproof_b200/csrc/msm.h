@@ -22,7 +22,9 @@ struct MsmPlan {
 
 int msm_pick_window(size_t n);
 void msm_make_plan(MsmPlan* p, size_t n, int c /* 0 = auto */);
+// points_ready (optional): event after which d_points may be read (lets the caller overlap the point
+// upload with the scalar-only front end: digit recoding, histogram, sort)
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
-            int normalize, cudaStream_t stream, int* launches);
+            int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready);
 
 }  // namespace cbp
