@@ -20,7 +20,10 @@ struct fe {
 };
 
 // ------------------------------------------------------------------------------------------
-// carry-chain building blocks (one asm block per chain: the CC flag is implicit state)
+// carry-chain building blocks (one asm block per chain: the CC flag is implicit state).
+// Write-only outputs are early-clobber ("=&r"): each block is several instructions and writes its
+// first outputs before it has read its last inputs, so an output must never share a register with
+// an input (without '&' the compiler may coalesce them, which silently corrupts the chain).
 // ------------------------------------------------------------------------------------------
 
 // acc[0..7] (+carry into acc[8]) += {x0,x1,x2,x3} * b, product k landing on words (2k, 2k+1)
@@ -66,7 +69,7 @@ __device__ __forceinline__ void mul_row4(uint32_t& c0, uint32_t& c1, uint32_t& c
         "mul.hi.u32 %5, %10, %12;\n\t"
         "mul.lo.u32 %6, %11, %12;\n\t"
         "mul.hi.u32 %7, %11, %12;"
-        : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3), "=r"(c4), "=r"(c5), "=r"(c6), "=r"(c7)
+        : "=&r"(c0), "=&r"(c1), "=&r"(c2), "=&r"(c3), "=&r"(c4), "=&r"(c5), "=&r"(c6), "=&r"(c7)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
 }
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ void fe_fold(fe& r, const uint32_t (&w)[16]) {
         "addc.cc.u32 %5, %5, %14;\n\t"
         "addc.cc.u32 %6, %6, %15;\n\t"
         "addc.u32    %7, %8, %16;"
-        : "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=r"(top)
+        : "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=&r"(top)
         : "r"(e8), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(o7), "r"(o8));
     // value = e[0..7] + top * 2^256 with top <= 38: fold again, then once more for the final carry
     uint32_t t = top * 38u, c;
@@ -99,7 +102,7 @@ __device__ __forceinline__ void fe_fold(fe& r, const uint32_t (&w)[16]) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32    %8, 0, 0;"
-        : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=r"(c)
+        : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=&r"(c)
         : "r"(t));
     e0 += c * 38u;  // after a wrap the low words are < 2^12, so this cannot carry
     r.v[0] = e0; r.v[1] = e1; r.v[2] = e2; r.v[3] = e3; r.v[4] = e4; r.v[5] = e5; r.v[6] = e6; r.v[7] = e7;
@@ -151,8 +154,8 @@ __device__ __forceinline__ void mul_wide(uint32_t (&w)[16], const fe& a, const f
         "addc.cc.u32 %12, %27, %42;\n\t"
         "addc.cc.u32 %13, %28, %43;\n\t"
         "addc.u32    %14, %29, %44;"
-        : "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
-          "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+        : "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(w[8]), "=&r"(w[9]),
+          "=&r"(w[10]), "=&r"(w[11]), "=&r"(w[12]), "=&r"(w[13]), "=&r"(w[14]), "=&r"(w[15])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
           "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]), "r"(O[2]),
           "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]),
@@ -182,8 +185,8 @@ __device__ __forceinline__ void fe_add(fe& r, const fe& a, const fe& b) {
         "addc.cc.u32 %6, %15, %23;\n\t"
         "addc.cc.u32 %7, %16, %24;\n\t"
         "addc.u32    %8, 0, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7]), "=r"(c)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
+          "=&r"(r.v[7]), "=&r"(c)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
     uint32_t t = c * 38u, c2;
@@ -197,7 +200,7 @@ __device__ __forceinline__ void fe_add(fe& r, const fe& a, const fe& b) {
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32    %8, 0, 0;"
         : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
-          "+r"(r.v[7]), "=r"(c2)
+          "+r"(r.v[7]), "=&r"(c2)
         : "r"(t));
     r.v[0] += c2 * 38u;
 }
@@ -214,8 +217,8 @@ __device__ __forceinline__ void fe_sub(fe& r, const fe& a, const fe& b) {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32    %8, 0, 0;"  // 0 or 0xFFFFFFFF
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7]), "=r"(bw)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
+          "=&r"(r.v[7]), "=&r"(bw)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
     // a borrow means the true value is r - 2^256 = r - 38 (mod p)
@@ -230,7 +233,7 @@ __device__ __forceinline__ void fe_sub(fe& r, const fe& a, const fe& b) {
         "subc.cc.u32 %7, %7, 0;\n\t"
         "subc.u32    %8, 0, 0;"
         : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
-          "+r"(r.v[7]), "=r"(b2)
+          "+r"(r.v[7]), "=&r"(b2)
         : "r"(t));
     r.v[0] -= b2 & 38u;  // after a second wrap the value is >= 2^256 - 38, so this cannot borrow
 }

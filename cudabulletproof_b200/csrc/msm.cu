@@ -659,6 +659,23 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 1 + kMaxGroups) * 4, st);
     if (e != cudaSuccess) return (int)e;
+    {
+        // the affine table depends only on the points: build it on a side stream while the scalar-only
+        // front end (recoding, histogram, sort) runs on the main stream
+        cudaStream_t ps = st;
+        if (kit) {
+            ps = kit->aux;
+            if ((e = cudaEventRecord(kit->ev_done, st)) != cudaSuccess) return (int)e;  // order after earlier work on st
+            if ((e = cudaStreamWaitEvent(ps, kit->ev_done, 0)) != cudaSuccess) return (int)e;
+        }
+        if (points_ready && (e = cudaStreamWaitEvent(ps, points_ready, 0)) != cudaSuccess) return (int)e;
+        size_t threads = (n + kPreChunk - 1) / kPreChunk;
+        prof_begin(BPK_PROF_MSM_PRECOMPUTE, ps);
+        msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ps>>>((const uint8_t*)d_points, n, table);
+        prof_end(BPK_PROF_MSM_PRECOMPUTE, ps);
+        CBP_LAUNCH_CHECK(); nl++;
+        if (kit && (e = cudaEventRecord(kit->ev_ready, ps)) != cudaSuccess) return (int)e;
+    }
     unsigned dgrid = (unsigned)((n + 255) / 256);
     msm_digits_kernel<false><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, counts, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
@@ -689,13 +706,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins, order);
     CBP_LAUNCH_CHECK(); nl++;
 
-    if (points_ready && (e = cudaStreamWaitEvent(st, points_ready, 0)) != cudaSuccess) return (int)e;
-    {
-        size_t threads = (n + kPreChunk - 1) / kPreChunk;
-        prof_begin(BPK_PROF_MSM_PRECOMPUTE, st);
-        msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)d_points, n, table);
-        prof_end(BPK_PROF_MSM_PRECOMPUTE, st);
-        CBP_LAUNCH_CHECK(); nl++;
+    if (kit) {  // join the table build (side stream) before the first accumulation
+        if ((e = cudaStreamWaitEvent(st, kit->ev_ready, 0)) != cudaSuccess) return (int)e;
     }
     for (int g = 0; g < gm.ngroups; g++) {
         cudaStream_t tail = kit ? kit->red[g] : st;

@@ -20,6 +20,7 @@
 //   verify_combine     accept bits
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/cuda_bulletproof.h"
 #include "common.h"
 #include "rangeproof.cuh"
@@ -303,72 +304,65 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
 }
 
 // ---- the per-proof multi-scalar sums ----------------------------------------------------------------
-static constexpr int kVThreads = 128;
+// Split by phase into small single-purpose kernels (a first monolithic one-CTA-per-proof kernel was
+// instruction-fetch and barrier bound: 243 KB of SASS, 16 % issue utilisation, profiles/r01_verify_msm_*):
+//   verify_coeff    thread / (proof, slot)        : coefficients -> signed digits (global memory)
+//   verify_fixed    WARP   / proof                 : 131 x 32 table additions, lane = window, shuffle tree
+//   verify_vtab     thread / (proof, point, m)     : multiples 1..8 of the 17 per-proof points
+//   verify_winsum   thread / (identity, proof, w)  : 4-bit window sums over the per-proof points
 static constexpr int kVarMax = 2 + 2 * kMaxK + 3;  // A, S, L_j, R_j | V, T1, T2
+static constexpr int kCoeffThreads = 96;           // n + 3 + kVarMax <= 96 for n <= 64
+static constexpr int kRowsMax = 2 * kMaxN + 3;     // G_i, H_i, h(identity 2), g, h(identity 1)
 
-__global__ void __launch_bounds__(kVThreads) verify_msm_kernel(const uint8_t* __restrict__ gens,
-                                                               const uint8_t* __restrict__ proofs, size_t rec_bytes,
-                                                               uint32_t n, int k, const VScal* __restrict__ vscal,
-                                                               uint8_t* __restrict__ fsum,
-                                                               uint8_t* __restrict__ winsum) {
-    __shared__ VScal vs;
-    __shared__ sc s_pow[kMaxN];
-    __shared__ int8_t digits[2 * kMaxN + 3][kFixWin];
-    __shared__ int8_t vdigits[kVarMax][64];
-    __shared__ ge_cached vtab[kVarMax][8];
-    __shared__ ge_p3 red[kVThreads];
+__device__ __forceinline__ int var_point_offset(int q, int k) {  // record offset of per-proof point q
+    int nvar2 = 2 + 2 * k;
+    return q == 0 ? kRecA : q == 1 ? kRecS : q < nvar2 ? kRecL + (q - 2) * 128 : q == nvar2 ? kRecV :
+           q == nvar2 + 1 ? kRecT1 : kRecT2;
+}
 
+__global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const VScal* __restrict__ vscal, uint32_t n, int k,
+                                                                     int8_t* __restrict__ digits,
+                                                                     int8_t* __restrict__ vdigits) {
     const uint32_t p = blockIdx.x;
     const int t = threadIdx.x;
-    const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
-    const uint8_t* table = gens + gh->table_off;
-    const uint8_t* rec = proofs + (size_t)p * rec_bytes;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&vscal[p]);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&vs);
-        for (int i = t; i < (int)(sizeof(VScal) / 4); i += kVThreads) dst[i] = src[i];
-    }
-    __syncthreads();
-    if (!vs.valid) return;  // uniform across the CTA
-
-    // s_i = prod_j u_j^(+-1): doubling recurrence, one level per challenge
-    if (t == 0) s_pow[0] = vs.s0;
-    __syncthreads();
-    for (int m = 0; m < k; m++) {
-        int half = 1 << m;
-        if (t >= half && t < 2 * half) {
-            sc v;
-            sc_mul(v, s_pow[t - half], vs.usq[k - 1 - m]);
-            s_pow[t] = v;
-        }
-        __syncthreads();
-    }
+    const VScal& vs = vscal[p];
+    if (!vs.valid) return;
+    int8_t* drow = digits + (size_t)p * kRowsMax * kFixWin;
+    int8_t* vrow = vdigits + (size_t)p * kVarMax * 64;
     const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
     if (t < (int)n) {
-        // y^-i from the y^-(2^m) ladder
-        sc yp;
+        // s_t = prod_j u_j^(+-1) built from s_0 = prod u_j^-1: multiply by u_j^2 for every set bit;
+        // s_(n-1-t) is the same with the bits complemented.  y^-t from the y^-(2^m) ladder.
+        sc s = vs.s0, sr = vs.s0, yp;
         sc_set1(yp);
-        for (int m = 0; m < k; m++)
-            if ((t >> m) & 1) sc_mul(yp, yp, vs.ypow[m]);
+#pragma unroll 1
+        for (int m = 0; m < k; m++) {
+            sc u2 = vs.usq[k - 1 - m];
+            if ((t >> m) & 1) {
+                sc_mul(s, s, u2);
+                sc_mul(yp, yp, vs.ypow[m]);
+            } else {
+                sc_mul(sr, sr, u2);
+            }
+        }
         sc cg, ch, tmp, two_i;
-        sc_mul(cg, vs.a, s_pow[t]);
+        sc_mul(cg, vs.a, s);
         sc_add(cg, cg, vs.z);
         sc_set0(two_i);
         two_i.v[t >> 5] = 1u << (t & 31);
         sc_mul(tmp, vs.z2, two_i);
-        sc_mul(ch, vs.b, s_pow[n - 1 - t]);
+        sc_mul(ch, vs.b, sr);
         sc_sub(ch, ch, tmp);
         sc_mul(ch, ch, yp);
         sc_sub(ch, ch, vs.z);
-        sc_recode_signed<8>(digits[t], cg, kFixWin);
-        sc_recode_signed<8>(digits[n + t], ch, kFixWin);
-    } else if (t == (int)n) {
-        sc_recode_signed<8>(digits[2 * n], vs.h2, kFixWin);
-        sc_recode_signed<8>(digits[2 * n + 1], vs.g1, kFixWin);
-        sc_recode_signed<8>(digits[2 * n + 2], vs.h1, kFixWin);
-    } else if (t - (int)n - 1 < nvar) {
-        // 4-bit digits of the per-proof scalars (all taken positive; the sums are compared, not added)
-        int q = t - (int)n - 1;
+        sc_recode_signed<8>(drow + (size_t)t * kFixWin, cg, kFixWin);
+        sc_recode_signed<8>(drow + (size_t)(n + t) * kFixWin, ch, kFixWin);
+    } else if (t < (int)n + 3) {
+        int r = t - (int)n;  // row 2n: h (mu + ab - t), 2n+1: g (t - delta), 2n+2: h (taux)
+        sc v = r == 0 ? vs.h2 : r == 1 ? vs.g1 : vs.h1;
+        sc_recode_signed<8>(drow + (size_t)(2 * n + r) * kFixWin, v, kFixWin);
+    } else if (t - (int)n - 3 < nvar) {
+        int q = t - (int)n - 3;  // positive scalars of the per-proof points (the two sides are compared)
         sc sv;
         if (q == 0) sc_set1(sv);
         else if (q == 1) sv = vs.x;
@@ -377,66 +371,132 @@ __global__ void __launch_bounds__(kVThreads) verify_msm_kernel(const uint8_t* __
         else if (q == nvar2) sv = vs.z2;
         else if (q == nvar2 + 1) sv = vs.x;
         else sv = vs.x2;
-        sc_recode_signed<4>(vdigits[q], sv, 64);
+        sc_recode_signed<4>(vrow + (size_t)q * 64, sv, 64);
     }
-    // multiples 1..8 of the per-proof points
-    for (int item = t; item < nvar * 8; item += kVThreads) {
-        int q = item >> 3, mlt = (item & 7) + 1;
-        int off = q == 0 ? kRecA : q == 1 ? kRecS : q < 2 + k ? kRecL + (q - 2) * 128 :
-                  q < nvar2 ? kRecL + (k + q - 2 - k) * 128 : q == nvar2 ? kRecV : q == nvar2 + 1 ? kRecT1 : kRecT2;
-        ge_p3 P, acc;
-        ge_load(P, rec + off);
-        ge_p3_0(acc);
-        for (int bit = 3; bit >= 0; bit--) {
-            ge_dbl(acc, acc);
-            if ((mlt >> bit) & 1) ge_add(acc, acc, P);
-        }
-        ge_to_cached(vtab[q][mlt - 1], acc);
-    }
-    __syncthreads();
+}
 
-    // fixed-base part: identity 2 on threads [0, 124), identity 1 on threads [124, 128)
+// One warp per proof, lane = 8-bit window: for every row the warp reads its 32 digits with one 32-byte
+// access and each lane adds digit * 2^(8 lane) * Base from the table (7M, next operand prefetched).
+// 131 perfectly balanced additions per lane, no shared memory, no CTA barrier; 5-level shuffle tree.
+__device__ __forceinline__ void ge_shfl_xor(ge_p3& out, const ge_p3& in, int mask) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        out.X.v[j] = __shfl_xor_sync(0xffffffffu, in.X.v[j], mask);
+        out.Y.v[j] = __shfl_xor_sync(0xffffffffu, in.Y.v[j], mask);
+        out.Z.v[j] = __shfl_xor_sync(0xffffffffu, in.Z.v[j], mask);
+        out.T.v[j] = __shfl_xor_sync(0xffffffffu, in.T.v[j], mask);
+    }
+}
+__global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __restrict__ gens,
+                                                              const VScal* __restrict__ vscal,
+                                                              const int8_t* __restrict__ digits, uint32_t n,
+                                                              uint32_t num, uint8_t* __restrict__ fsum) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= num || !vscal[p].valid) return;  // whole warp
+    const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
+    const uint8_t* table = gens + gh->table_off + (size_t)lane * kFixEntries * 96;  // this lane's window
+    const int8_t* drow = digits + (size_t)p * kRowsMax * kFixWin + lane;
+    const int nrows2 = 2 * (int)n + 1, nrows = nrows2 + 2;
+    // sequence: the two identity-1 rows (g, h) first, then the 2n+1 identity-2 rows — one accumulator live
+    auto row_of = [&](int sidx) { return sidx < 2 ? nrows2 + sidx : sidx - 2; };
+    auto base_of = [&](int row) {
+        return row < 2 * (int)n ? (uint32_t)row : row == 2 * (int)n ? 2 * n + 1 : 2 * n + (uint32_t)(row - nrows2);
+    };
     ge_p3 acc;
     ge_p3_0(acc);
-    const int nrows2 = 2 * (int)n + 1;
-    if (t < kVThreads - 4) {
-        for (int item = t; item < nrows2 * kFixWin; item += kVThreads - 4) {
-            int row = item / kFixWin, win = item % kFixWin;
-            uint32_t base = row < 2 * (int)n ? (uint32_t)row : 2 * n + 1;
-            fixed_base_madd(acc, table, base, win, digits[row][win]);
-        }
-    } else {
-        for (int item = t - (kVThreads - 4); item < 2 * kFixWin; item += 4) {
-            int row = item / kFixWin, win = item % kFixWin;  // row 0: g (t - delta), row 1: h (taux)
-            fixed_base_madd(acc, table, 2 * n + row, win, digits[nrows2 + row][win]);
-        }
-    }
-    ge_p3 f1 = acc;
-    if (t >= kVThreads - 4) ge_p3_0(acc);
-    cta_point_sum(acc, red);  // identity-2 generator sum in thread 0
-    if (t >= kVThreads - 4) red[t] = f1;
-    __syncthreads();
-    if (t == 0) {
-        ge_store(fsum + ((size_t)p * 2 + 1) * 128, acc);
-        ge_p3 s = red[kVThreads - 4];
-        for (int i = 1; i < 4; i++) ge_add(s, s, red[kVThreads - 4 + i]);
-        ge_store(fsum + ((size_t)p * 2 + 0) * 128, s);
-    }
-    // variable part: one 4-bit window per thread; threads [0,64) identity 2, [64,128) identity 1
+    uint32_t mag;
+    bool neg;
+    ge_niels q;
     {
-        int w = t & 63, which = t >> 6;  // which = 0 -> identity 2 points [0, nvar2), 1 -> identity 1 [nvar2, nvar)
-        int q0 = which ? nvar2 : 0, q1 = which ? nvar : nvar2;
-        ge_p3 ws;
-        ge_p3_0(ws);
-        for (int q = q0; q < q1; q++) {
-            int d = vdigits[q][w];
-            if (d != 0) {
-                int mag = d < 0 ? -d : d;
-                ge_add_cached(ws, ws, vtab[q][mag - 1], d < 0);
-            }
-        }
-        ge_store(winsum + (((size_t)p * 2 + (which ? 0 : 1)) * 64 + w) * 128, ws);
+        int r0 = row_of(0);
+        fixed_digit(drow[(size_t)r0 * kFixWin], mag, neg);
+        if (mag) ge_niels_load(q, table + ((size_t)base_of(r0) * kFixWin * kFixEntries + (mag - 1)) * 96);
     }
+#pragma unroll 1
+    for (int sidx = 0; sidx < nrows; sidx++) {
+        uint32_t cmag = mag;
+        bool cneg = neg;
+        ge_niels cur = q;
+        if (sidx + 1 < nrows) {  // prefetch the next operand while this addition runs
+            int nr = row_of(sidx + 1);
+            fixed_digit(drow[(size_t)nr * kFixWin], mag, neg);
+            if (mag) ge_niels_load(q, table + ((size_t)base_of(nr) * kFixWin * kFixEntries + (mag - 1)) * 96);
+        }
+        if (cmag) ge_madd(acc, acc, cur, cneg);
+        if (sidx == 1 || sidx == nrows - 1) {  // end of an identity: butterfly sum over the 32 windows
+#pragma unroll 1
+            for (int o = 16; o > 0; o >>= 1) {
+                ge_p3 other;
+                ge_shfl_xor(other, acc, o);
+                ge_add(acc, acc, other);
+            }
+            if (lane == 0) ge_store(fsum + ((size_t)p * 2 + (sidx == 1 ? 0 : 1)) * 128, acc);
+            ge_p3_0(acc);
+        }
+    }
+}
+
+// multiples m = 1..8 of per-proof point q, as cached points; threads are grouped by m so that the
+// double-and-add pattern is uniform within a warp
+__global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, int k,
+                                                          const VScal* __restrict__ vscal, uint32_t num,
+                                                          uint8_t* __restrict__ vtab) {
+    const int nvar = 2 + 2 * k + 3;
+    uint32_t per_m = num * (uint32_t)nvar;
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= per_m * 8) return;
+    int mlt = (int)(id / per_m) + 1;
+    uint32_t rem = id % per_m, p = rem / (uint32_t)nvar;
+    int q = (int)(rem % (uint32_t)nvar);
+    if (!vscal[p].valid) return;
+    ge_p3 P, acc;
+    ge_load(P, proofs + (size_t)p * rec_bytes + var_point_offset(q, k));
+    acc = P;
+    // m in [1,8]: binary method from the top bit
+    int top = 31 - __clz(mlt);
+    for (int bit = top - 1; bit >= 0; bit--) {
+        ge_dbl(acc, acc);
+        if ((mlt >> bit) & 1) ge_add(acc, acc, P);
+    }
+    ge_cached c;
+    ge_to_cached(c, acc);
+    uint8_t* dst = vtab + (((size_t)p * kVarMax + q) * 8 + (mlt - 1)) * 128;
+    fe_store(dst, c.YplusX);
+    fe_store(dst + 32, c.YminusX);
+    fe_store(dst + 64, c.Z2);
+    fe_store(dst + 96, c.T2d);
+}
+// window sums: threads [0, 64 num) identity 2 (A, S, L_j, R_j), [64 num, 128 num) identity 1 (V, T1, T2)
+__global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restrict__ vscal,
+                                                            const int8_t* __restrict__ vdigits,
+                                                            const uint8_t* __restrict__ vtab, int k, uint32_t num,
+                                                            uint8_t* __restrict__ winsum) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= num * 128) return;
+    int which = id >= num * 64;  // 1: identity 1
+    uint32_t rem = which ? id - num * 64 : id, p = rem >> 6;
+    int w = rem & 63;
+    if (!vscal[p].valid) return;
+    const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
+    int q0 = which ? nvar2 : 0, q1 = which ? nvar : nvar2;
+    ge_p3 ws;
+    ge_p3_0(ws);
+#pragma unroll 1
+    for (int q = q0; q < q1; q++) {
+        int d = vdigits[((size_t)p * kVarMax + q) * 64 + w];
+        if (d != 0) {
+            int mag = d < 0 ? -d : d;
+            const uint8_t* src = vtab + (((size_t)p * kVarMax + q) * 8 + (mag - 1)) * 128;
+            ge_cached c;
+            fe_load(c.YplusX, src);
+            fe_load(c.YminusX, src + 32);
+            fe_load(c.Z2, src + 64);
+            fe_load(c.T2d, src + 96);
+            ge_add_cached(ws, ws, c, d < 0);
+        }
+    }
+    ge_store(winsum + (((size_t)p * 2 + (which ? 0 : 1)) * 64 + w) * 128, ws);
 }
 
 // Horner over the 64 window sums, then F == Var as projective points.  index 0: identity 1, 1: identity 2.
@@ -526,12 +586,32 @@ int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, cons
     return BPK_OK;
 }
 
+struct VerifyLayout {
+    size_t vscal, fsum, winsum, flags, digits, vdigits, vtab, total;
+};
+static VerifyLayout verify_layout(size_t chunk) {
+    VerifyLayout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += align256(bytes);
+        return o;
+    };
+    L.vscal = take(chunk * sizeof(VScal));
+    L.fsum = take(chunk * 2 * 128);
+    L.winsum = take(chunk * 2 * 64 * 128);
+    L.flags = take(chunk * 2);
+    L.digits = take(chunk * kRowsMax * kFixWin);
+    L.vdigits = take(chunk * kVarMax * 64);
+    L.vtab = take(chunk * kVarMax * 8 * 128);
+    L.total = off;
+    return L;
+}
 int bpk_range_verify_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes) {
     if (!bytes || n == 0 || n > kMaxN || (n & (n - 1))) return fail(BPK_ERR_ARG);
     size_t chunk = num_proofs < kVerifyChunk ? num_proofs : kVerifyChunk;
     if (chunk == 0) chunk = 1;
-    *bytes = align256(chunk * sizeof(VScal)) + align256(chunk * 2 * 128) + align256(chunk * 2 * 64 * 128) +
-             align256(chunk * 2);
+    *bytes = verify_layout(chunk).total;
     return BPK_OK;
 }
 int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, const void* d_V, size_t n,
@@ -546,11 +626,12 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     while (((size_t)1 << k) < n) k++;
     size_t rec = proof_record_bytes(k);
     size_t chunk = num_proofs < kVerifyChunk ? num_proofs : kVerifyChunk;
+    VerifyLayout L = verify_layout(chunk);
     uint8_t* ws = (uint8_t*)d_workspace;
-    VScal* vscal = (VScal*)ws;
-    uint8_t* fsum = ws + align256(chunk * sizeof(VScal));
-    uint8_t* winsum = fsum + align256(chunk * 2 * 128);
-    uint8_t* flags = winsum + align256(chunk * 2 * 64 * 128);
+    VScal* vscal = (VScal*)(ws + L.vscal);
+    uint8_t *fsum = ws + L.fsum, *winsum = ws + L.winsum, *flags = ws + L.flags, *vtab = ws + L.vtab;
+    int8_t *digits = (int8_t*)(ws + L.digits), *vdigits = (int8_t*)(ws + L.vdigits);
+    const int nvar = 2 + 2 * k + 3;
     cudaStream_t st = (cudaStream_t)stream;
     prof_begin(BPK_PROF_VERIFY_TOTAL, st);
     for (size_t done = 0; done < num_proofs; done += chunk) {
@@ -559,10 +640,16 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         const uint8_t* ve = d_V ? (const uint8_t*)d_V + done * 128 : nullptr;
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
+        verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>(vscal, (uint32_t)n, k, digits, vdigits);
+        CBP_CHECK_LAUNCH();
         prof_begin(BPK_PROF_VERIFY_MSM, st);
-        verify_msm_kernel<<<cnt, kVThreads, 0, st>>>((const uint8_t*)d_gens_ws, pr, rec, (uint32_t)n, k, vscal, fsum,
-                                                     winsum);
+        verify_fixed_kernel<<<(cnt * 32 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits, (uint32_t)n,
+                                                                    cnt, fsum);
         prof_end(BPK_PROF_VERIFY_MSM, st);
+        CBP_CHECK_LAUNCH();
+        verify_vtab_kernel<<<(cnt * nvar * 8 + 127) / 128, 128, 0, st>>>(pr, rec, k, vscal, cnt, vtab);
+        CBP_CHECK_LAUNCH();
+        verify_winsum_kernel<<<(cnt * 128 + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, cnt, winsum);
         CBP_CHECK_LAUNCH();
         verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
         CBP_CHECK_LAUNCH();
