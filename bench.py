@@ -368,13 +368,18 @@ def run_cuda(args):
         chunks = max(1, k_n // vsteps)
         rejected = int((acc == 0).sum().item())
         ok = rejected == len(bad) and bool((acc[torch.from_numpy(bad).to(dev)] == 0).all().item())
-        # algorithmic IMAD per proof: 131 bases x 32 windows mixed additions (504) + 17 points x 64 windows x 8M (576)
-        # + 2 x (252 doublings (464) + 64 additions (648)) Horner
-        imad = (131 * 32 * 504 + 17 * 64 * 576 + 2 * (252 * 464 + 64 * 648)) * 1.0
-        per_launch = imad * (m / chunks)
-        roofline = {"bound": "int", "kernel": "verify_msm_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
+        # algorithmic IMAD (SURVEY.md §8d units).  Whole proof: 131 bases x 32 windows mixed additions (504)
+        # + 17 points x 64 windows x 8M (576) + 2 x (252 doublings (464) + 64 additions (648)) Horner.
+        # The timed kernel (verify_fixed_kernel, warp per proof) does the first term plus two 5-level
+        # shuffle trees of 9M additions per warp.
+        imad_proof = (131 * 32 * 504 + 17 * 64 * 576 + 2 * (252 * 464 + 64 * 648)) * 1.0
+        imad_kernel = 131 * 32 * 504 + 2 * 5 * 32 * 648.0
+        per_launch = imad_kernel * (m / chunks)
+        roofline = {"bound": "int", "kernel": "verify_fixed_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": per_launch / (k_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
-                    "traffic": None, "launch_ms": k_ms, "launches_timed": k_n, "algorithmic_imad_per_proof": imad}
+                    "traffic": None, "launch_ms": k_ms, "launches_timed": k_n,
+                    "algorithmic_imad_per_launch": per_launch, "algorithmic_imad_per_proof_total": imad_proof,
+                    "whole_batch_frac": imad_proof * m / (ms / vsteps * 1e-3) / 1e12 / INT_PEAK_TIMAD}
         # e2e: proof records in pinned host memory -> device -> accept mask back on the host
         h_proofs = torch.empty_like(proofs, device="cpu").pin_memory()
         h_proofs.copy_(proofs)

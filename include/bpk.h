@@ -36,7 +36,7 @@ uint64_t bpk_kernel_launches(void);
  * around the named kernel of every call while enabled; read returns the mean duration in ms ---- */
 #define BPK_PROF_MSM_ACCUMULATE 0 /* msm_accumulate_kernel  */
 #define BPK_PROF_MSM_TOTAL 1      /* whole bpk_msm_device   */
-#define BPK_PROF_VERIFY_MSM 2     /* verify_msm_kernel      */
+#define BPK_PROF_VERIFY_MSM 2     /* verify_fixed_kernel    */
 #define BPK_PROF_VERIFY_TOTAL 3   /* whole bpk_range_verify_batch_device */
 #define BPK_PROF_MSM_PRECOMPUTE 4 /* msm_precompute_kernel (HBM streaming) */
 #define BPK_PROF_KINDS 5
