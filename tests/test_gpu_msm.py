@@ -136,3 +136,21 @@ def test_msm_full_size_scalar_identity(oracle, log_n):
     # atomics reorder bucket contents between runs; the group element must not change
     again = msm(sc, pts).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, again)
+
+
+def test_msm_adversarial_equal_scalars_large(oracle):
+    """All scalars equal: every window has ONE bucket holding all N entries.  Segment splitting bounds the
+    serial work per thread; the result must equal k * (sum of points) = k * (sum k_i) * B."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    n = 1 << 16
+    pts, ks = cbp.synth_points(n, seed=77)
+    k = 0x0123456789ABCDEF_FEDCBA9876543210_0F1E2D3C4B5A6978_13579BDF02468ACE % (2**253)
+    one = torch.from_numpy(np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8).copy()).cuda()
+    sc = one.repeat(n, 1).contiguous()
+    got = cbp.Msm(n)(sc, pts).cpu().numpy().view(np.uint64).copy()
+    total = int(ks.cpu().numpy().astype(np.uint64).astype(object).sum()) % L
+    want = np.zeros(16, dtype=np.uint64)
+    oracle.ge25519_scalarmult_base(ob.ptr(want), ((k % L) * total % L).to_bytes(32, "little"))
+    oracle.ge25519_normalize(ob.ptr(want))
+    assert np.array_equal(got, want)
