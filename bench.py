@@ -284,6 +284,8 @@ def run_cuda(args):
         launches = lib.bpk_kernel_launches() - launches0 + (args.steps if world > 1 else 0)
         acc_ms, acc_n = prof_read(0)
         pre_ms, _ = prof_read(4)
+        phases = {"front_ms": prof_read(5)[0], "accumulate_ms": acc_ms, "tail_ms": prof_read(6)[0],
+                  "total_ms": prof_read(1)[0], "table_build_ms_overlapped": pre_ms}
         result_hex = bytes(res.cpu().numpy().tobytes()[:64]).hex()
         W = (256 + msm.window_bits - 1) // msm.window_bits
         imad_acc = n * W * 504.0  # 7 fe_mul x 72 IMAD per mixed addition, N*W additions
@@ -315,7 +317,7 @@ def run_cuda(args):
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e_hex = h_out.tobytes()[:64].hex()
         return {"ms": ms, "n": n, "clocks": clocks, "launches": int(launches), "roofline": roofline,
-                "roofline_hbm": roofline_hbm, "window_bits": msm.window_bits,
+                "roofline_hbm": roofline_hbm, "window_bits": msm.window_bits, "phases": phases,
                 "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "points/s",
                         "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": 128,
                         "api": "cuda_point_vector_multi_scalar_mul (host pointers, pinned)", "ms_per_step": e2e_ms / e2e_steps,
@@ -431,7 +433,8 @@ def run_cuda(args):
                                "parallelism": f"point-range x{world}" if world > 1 else "single GPU",
                                "combine": "NCCL all_gather of 128 B partial points + point-sum kernel" if world > 1 else None},
                     "e2e": msm_res["e2e"], "gpu_launches": msm_res["launches"], "clocks": msm_res["clocks"],
-                    "roofline": msm_res["roofline"], "roofline_hbm": msm_res["roofline_hbm"], "cpu_baseline": cpu,
+                    "roofline": msm_res["roofline"], "roofline_hbm": msm_res["roofline_hbm"], "phases": msm_res["phases"],
+                    "cpu_baseline": cpu,
                     "result_xy": msm_res["result_xy"]}
             if ver_res is not None:
                 line["secondary"] = ver_res

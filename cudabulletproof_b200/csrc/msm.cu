@@ -102,23 +102,43 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
     load_scalar_canon(k, scalars + i * 32);
     uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1);
-    for (int w = 0; w < W; w++) {
-        uint32_t d = raw_digit(k, w, c) + carry;
-        uint32_t neg = 0;
-        carry = 0;
-        if (d > half) {
-            d = (1u << c) - d;
-            neg = 1;
-            carry = 1;
-        }
-        if (d != 0) {
-            uint32_t id = (uint32_t)w * B + (d - 1);
-            if (SCATTER) {
-                uint32_t pos = atomicAdd(&counters[id], 1u);
-                entries[pos] = ((uint32_t)i << 1) | neg;
-            } else {
-                atomicAdd(&counters[id], 1u);
+    // windows in batches of 4: the 4 atomics of a batch are issued back to back (independent), only then
+    // are their return values consumed — the scatter pass is bound by atomic round-trip latency otherwise
+    for (int w0 = 0; w0 < W; w0 += 4) {
+        uint32_t id[4], val[4];
+        bool live[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int w = w0 + j;
+            live[j] = false;
+            if (w < W) {
+                uint32_t d = raw_digit(k, w, c) + carry;
+                uint32_t neg = 0;
+                carry = 0;
+                if (d > half) {
+                    d = (1u << c) - d;
+                    neg = 1;
+                    carry = 1;
+                }
+                if (d != 0) {
+                    live[j] = true;
+                    id[j] = (uint32_t)w * B + (d - 1);
+                    val[j] = ((uint32_t)i << 1) | neg;
+                }
             }
+        }
+        if (SCATTER) {
+            uint32_t pos[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (live[j]) pos[j] = atomicAdd(&counters[id[j]], 1u);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (live[j]) entries[pos[j]] = val[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (live[j]) atomicAdd(&counters[id[j]], 1u);
         }
     }
 }
@@ -676,6 +696,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         CBP_LAUNCH_CHECK(); nl++;
         if (kit && (e = cudaEventRecord(kit->ev_ready, ps)) != cudaSuccess) return (int)e;
     }
+    prof_begin(BPK_PROF_MSM_FRONT, st);
     unsigned dgrid = (unsigned)((n + 255) / 256);
     msm_digits_kernel<false><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, counts, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
@@ -706,6 +727,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins, order);
     CBP_LAUNCH_CHECK(); nl++;
 
+    prof_end(BPK_PROF_MSM_FRONT, st);
     if (kit) {  // join the table build (side stream) before the first accumulation
         if ((e = cudaStreamWaitEvent(st, kit->ev_ready, 0)) != cudaSuccess) return (int)e;
     }
@@ -718,7 +740,10 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, offsets, segoff,
                                                                                   p.seg_shift, order, binstart, g, buckets,
                                                                                   segsums);
-        if (g == gm.ngroups - 1) prof_end(BPK_PROF_MSM_ACCUMULATE, st);
+        if (g == gm.ngroups - 1) {
+            prof_end(BPK_PROF_MSM_ACCUMULATE, st);
+            prof_begin(BPK_PROF_MSM_TAIL, st);
+        }
         CBP_LAUNCH_CHECK(); nl++;
         if (kit) {
             if ((e = cudaEventRecord(kit->ev_group[g], st)) != cudaSuccess) return (int)e;
@@ -775,6 +800,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if ((e = cudaEventRecord(kit->ev_done, kit->aux)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamWaitEvent(st, kit->ev_done, 0)) != cudaSuccess) return (int)e;
     }
+    prof_end(BPK_PROF_MSM_TAIL, st);
     prof_end(BPK_PROF_MSM_TOTAL, st);
     if (launches) *launches = nl;
     return 0;

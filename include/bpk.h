@@ -39,7 +39,9 @@ uint64_t bpk_kernel_launches(void);
 #define BPK_PROF_VERIFY_MSM 2     /* verify_fixed_kernel    */
 #define BPK_PROF_VERIFY_TOTAL 3   /* whole bpk_range_verify_batch_device */
 #define BPK_PROF_MSM_PRECOMPUTE 4 /* msm_precompute_kernel (HBM streaming) */
-#define BPK_PROF_KINDS 5
+#define BPK_PROF_MSM_FRONT 5      /* recode, histogram, scans, scatter, segment sort (main stream) */
+#define BPK_PROF_MSM_TAIL 6       /* end of the last accumulation -> result ready */
+#define BPK_PROF_KINDS 7
 int bpk_profile_enable(int enable);
 int bpk_profile_reset(void);
 int bpk_profile_read(int kind, float* mean_ms, int* samples); /* synchronises the recorded events */
