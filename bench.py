@@ -291,7 +291,12 @@ def run_cuda(args):
         imad_acc = n * W * 504.0  # 7 fe_mul x 72 IMAD per mixed addition, N*W additions
         roofline = {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": imad_acc / (acc_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": imad_acc / (acc_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
-                    "traffic": None, "launch_ms": acc_ms, "launches_timed": acc_n,
+                    "traffic": 1.243e9 if args.log_n == 20 else None,
+                    "traffic_note": "dram__bytes_read+write summed over the 5 window-group launches of one 2^20 MSM, "
+                                    "ncu --set full (profiles/r01_hot_kernels_ncu_raw.csv); algorithmic gather bytes "
+                                    "N*W*100 = 1.68e9, the rest is L2 hits",
+                    "launch_ms": acc_ms, "launches_timed": acc_n, "launch_note": "span of the 5 group launches per MSM",
+                    "ncu": {"sm__pipe_fmaheavy_cycles_active_pct": 84.5, "stall_top": "math_pipe_throttle"},
                     "peak_source": "measured IMAD.WIDE.U32 issue rate (profiles/r01_microbench_int_pipe.jsonl)",
                     "algorithmic_imad_per_launch": imad_acc}
         roofline_hbm = {"bound": "hbm", "kernel": "msm_precompute_kernel", "achieved": n * 224.0 / (pre_ms * 1e-3) / 1e9,

@@ -143,6 +143,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
     }
 }
 
+static constexpr int kMaxGroups = 8;
+struct GroupMap {
+    int ngroups;
+    int log2B;                               // buckets per window = 2^log2B
+    int w_hi[kMaxGroups], w_lo[kMaxGroups];  // processed top window first
+    uint8_t group_of_window[64];
+    uint8_t seg_shift_of_window[64];         // log2 segment length; smaller for the small last groups so that
+                                             // their accumulation still fills the machine
+};
+
 // ---- 3. exclusive scan over `total` counters (three small kernels) -------------------------------
 static constexpr int kScanThreads = 256, kScanPer = 16, kScanTile = kScanThreads * kScanPer;
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem, uint32_t& block_total) {
@@ -170,18 +180,21 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     return warp_off + x - v;
 }
 // SEG = true scans the per-bucket SEGMENT counts ceil(count / kSegLen) (>= 1) instead of the counts
+__device__ __forceinline__ uint32_t seg_count(uint32_t c, int seg_shift) {
+    return c ? (c + (1u << seg_shift) - 1u) >> seg_shift : 1u;
+}
 template <bool SEG>
-__device__ __forceinline__ uint32_t scan_input(uint32_t c, int seg_shift) {
-    return SEG ? (c ? (c + (1u << seg_shift) - 1u) >> seg_shift : 1u) : c;
+__device__ __forceinline__ uint32_t scan_input(uint32_t c, uint32_t id, const GroupMap& gm) {
+    return SEG ? seg_count(c, gm.seg_shift_of_window[id >> gm.log2B]) : c;
 }
 template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint32_t total,
-                                                                      int seg_shift, uint32_t* __restrict__ tile_sums) {
+                                                                      GroupMap gm, uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t smem[64];
     uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPer, s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++)
-        if (base + j < total) s += scan_input<SEG>(in[base + j], seg_shift);
+        if (base + j < total) s += scan_input<SEG>(in[base + j], base + j, gm);
     uint32_t bt;
     block_exclusive_scan(s, smem, bt);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = bt;
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t* tile_sums, u
 }
 template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t total,
-                                                                  int seg_shift, const uint32_t* __restrict__ tile_sums,
+                                                                  GroupMap gm, const uint32_t* __restrict__ tile_sums,
                                                                   uint32_t* __restrict__ offsets,
                                                                   uint32_t* __restrict__ cursors) {
     __shared__ uint32_t smem[64];
@@ -203,7 +216,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
     uint32_t v[kScanPer], s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++) {
-        v[j] = base + j < total ? scan_input<SEG>(in[base + j], seg_shift) : 0;
+        v[j] = base + j < total ? scan_input<SEG>(in[base + j], base + j, gm) : 0;
         s += v[j];
     }
     uint32_t bt;
@@ -243,52 +256,46 @@ __device__ __forceinline__ void ge_warp_sum(ge_p3& v) {  // result in lane 0
 // length (counting sort, longest first, grouped by window group), the 32 segments of a warp run in
 // lockstep instead of waiting for the longest of 32 Poisson-distributed runs.
 static constexpr uint32_t kMinSegLen = 64;  // segment length = max(64, 2 * mean run length), a power of two
-static constexpr int kMaxGroups = 8;
 static constexpr int kSegBinsPerGroup = 65;  // length classes ceil(64 len / seglen), longest first
 static constexpr int kSegBins = 1024;  // >= kMaxGroups * kSegBinsPerGroup, = threads of the bin scan
 
-struct GroupMap {
-    int ngroups;
-    int w_hi[kMaxGroups], w_lo[kMaxGroups];  // processed top window first
-    uint8_t group_of_window[64];
-};
 
 __global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restrict__ counts,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ segoff, uint32_t nbuckets,
-                                                        uint32_t B, int seg_shift, GroupMap gm, uint2* __restrict__ desc,
+                                                        uint32_t B, GroupMap gm, uint2* __restrict__ desc,
                                                         uint32_t* __restrict__ heavy, uint32_t* __restrict__ heavy_cnt) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= nbuckets) return;
-    uint32_t c = counts[id], ns = scan_input<true>(c, seg_shift), so = segoff[id], start = offsets[id];
+    const int seg_shift = gm.seg_shift_of_window[id >> gm.log2B];
+    uint32_t c = counts[id], ns = seg_count(c, seg_shift), so = segoff[id], start = offsets[id];
     for (uint32_t q = 0; q < ns; q++) desc[so + q] = make_uint2(start + (q << seg_shift), id);
     if (ns > 1) {
-        uint32_t w = id / B;
-        int g = gm.group_of_window[w];
+        int g = gm.group_of_window[id >> gm.log2B];
         uint32_t idx = atomicAdd(&heavy_cnt[g], 1u);
         heavy[(uint32_t)gm.w_lo[g] * B + idx] = id;
     }
 }
-__device__ __forceinline__ uint32_t seg_length(uint2 d, const uint32_t* __restrict__ offsets, int seg_shift) {
-    uint32_t rest = offsets[d.y + 1] - d.x, cap = 1u << seg_shift;
+__device__ __forceinline__ uint32_t seg_length(uint2 d, const uint32_t* __restrict__ offsets, const GroupMap& gm) {
+    uint32_t rest = offsets[d.y + 1] - d.x, cap = 1u << gm.seg_shift_of_window[d.y >> gm.log2B];
     return rest < cap ? rest : cap;
 }
-__device__ __forceinline__ uint32_t seg_bin(uint2 d, const uint32_t* __restrict__ offsets, int seg_shift, uint32_t B,
-                                            const GroupMap& gm) {
-    uint32_t len = seg_length(d, offsets, seg_shift), w = d.y / B;
+__device__ __forceinline__ uint32_t seg_bin(uint2 d, const uint32_t* __restrict__ offsets, const GroupMap& gm) {
+    uint32_t len = seg_length(d, offsets, gm), w = d.y >> gm.log2B;
+    const int seg_shift = gm.seg_shift_of_window[w];
     uint32_t cls = (len * 64u + (1u << seg_shift) - 1u) >> seg_shift;  // 0..64
     return (uint32_t)gm.group_of_window[w] * kSegBinsPerGroup + (64u - cls);  // longest first within a group
 }
 __global__ void __launch_bounds__(256) seg_hist_kernel(const uint2* __restrict__ desc,
                                                        const uint32_t* __restrict__ offsets,
-                                                       const uint32_t* __restrict__ nsegs_p, uint32_t B, int seg_shift,
-                                                       GroupMap gm, uint32_t* __restrict__ hist) {
+                                                       const uint32_t* __restrict__ nsegs_p, GroupMap gm,
+                                                       uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[kSegBins];
     for (int i = threadIdx.x; i < kSegBins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     uint32_t nsegs = *nsegs_p;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsegs; i += gridDim.x * blockDim.x)
-        atomicAdd(&sh[seg_bin(desc[i], offsets, seg_shift, B, gm)], 1u);
+        atomicAdd(&sh[seg_bin(desc[i], offsets, gm)], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < kSegBins; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
@@ -305,13 +312,13 @@ __global__ void __launch_bounds__(kSegBins) seg_bin_scan_kernel(uint32_t* __rest
 }
 __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint2* __restrict__ desc,
                                                           const uint32_t* __restrict__ offsets,
-                                                          const uint32_t* __restrict__ nsegs_p, uint32_t B,
-                                                          int seg_shift, GroupMap gm, uint32_t* __restrict__ cursors,
+                                                          const uint32_t* __restrict__ nsegs_p, GroupMap gm,
+                                                          uint32_t* __restrict__ cursors,
                                                           uint32_t* __restrict__ order) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nsegs = *nsegs_p;
     bool live = i < nsegs;
-    uint32_t bin = live ? seg_bin(desc[i], offsets, seg_shift, B, gm) : 0xffffffffu;
+    uint32_t bin = live ? seg_bin(desc[i], offsets, gm) : 0xffffffffu;
     uint32_t active = __ballot_sync(0xffffffffu, live);
     if (!live) return;
     uint32_t peers = __match_any_sync(active, bin);  // warp-aggregated atomics
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint2* __restric
 __global__ void __launch_bounds__(128, 4)
     msm_accumulate_kernel(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
                           const uint2* __restrict__ desc, const uint32_t* __restrict__ offsets,
-                          const uint32_t* __restrict__ segoff, int seg_shift, const uint32_t* __restrict__ order,
+                          const uint32_t* __restrict__ segoff, GroupMap gm, const uint32_t* __restrict__ order,
                           const uint32_t* __restrict__ binstart, int group,
                           uint8_t* __restrict__ bucket_sums, uint8_t* __restrict__ seg_sums) {
     uint32_t lo = binstart[group * kSegBinsPerGroup], hi = binstart[(group + 1) * kSegBinsPerGroup];
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(128, 4)
     if (t >= hi - lo) return;
     uint32_t seg = order[lo + t];
     uint2 d = desc[seg];
-    uint32_t e = d.x, end = d.x + seg_length(d, offsets, seg_shift), id = d.y;
+    uint32_t e = d.x, end = d.x + seg_length(d, offsets, gm), id = d.y;
     ge_p3 acc;
     ge_p3_0(acc);
     if (e < end) {
@@ -358,7 +365,29 @@ __global__ void __launch_bounds__(128, 4)
     bool single = segoff[id + 1] - segoff[id] == 1;
     ge_store(single ? bucket_sums + (size_t)id * 128 : seg_sums + (size_t)seg * 128, acc);
 }
-// buckets cut into several segments: one warp adds the segment sums
+// buckets cut into several segments: a thread adds up to kHeavySeq segment sums itself, larger buckets
+// are left to one warp each (lane-strided partial sums + shuffle tree)
+static constexpr uint32_t kHeavySeq = 8;
+__global__ void __launch_bounds__(128) msm_heavy_small_kernel(const uint32_t* __restrict__ heavy,
+                                                              const uint32_t* __restrict__ heavy_cnt, int group,
+                                                              uint32_t heavy_base, const uint32_t* __restrict__ segoff,
+                                                              const uint8_t* __restrict__ seg_sums,
+                                                              uint8_t* __restrict__ bucket_sums) {
+    uint32_t cnt = heavy_cnt[group];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        uint32_t id = heavy[heavy_base + i];
+        uint32_t s0 = segoff[id], s1 = segoff[id + 1];
+        if (s1 - s0 > kHeavySeq) continue;
+        ge_p3 acc;
+        ge_load(acc, seg_sums + (size_t)s0 * 128);
+        for (uint32_t q = s0 + 1; q < s1; q++) {
+            ge_p3 x;
+            ge_load(x, seg_sums + (size_t)q * 128);
+            ge_add(acc, acc, x);
+        }
+        ge_store(bucket_sums + (size_t)id * 128, acc);
+    }
+}
 __global__ void __launch_bounds__(128) msm_heavy_fix_kernel(const uint32_t* __restrict__ heavy,
                                                             const uint32_t* __restrict__ heavy_cnt, int group,
                                                             uint32_t heavy_base, const uint32_t* __restrict__ segoff,
@@ -370,6 +399,7 @@ __global__ void __launch_bounds__(128) msm_heavy_fix_kernel(const uint32_t* __re
     for (; gw < cnt; gw += (gridDim.x * blockDim.x) >> 5) {
         uint32_t id = heavy[heavy_base + gw];
         uint32_t s0 = segoff[id], s1 = segoff[id + 1];
+        if (s1 - s0 <= kHeavySeq) continue;  // warp-uniform
         ge_p3 acc;
         ge_p3_0(acc);
         for (uint32_t q = s0 + lane; q < s1; q += 32) {
@@ -547,7 +577,8 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     // segment length: a power of two, at least 64 and at least twice the mean run length n / B
     p->seg_shift = 6;
     while (((size_t)1 << p->seg_shift) < 2 * (n / p->B + 1) && p->seg_shift < 20) p->seg_shift++;
-    p->max_segs = (size_t)p->nbuckets + ((n * (size_t)p->W) >> p->seg_shift) + 1;
+    int min_shift = p->seg_shift >= 6 ? p->seg_shift - 2 : 4;  // small window groups use shorter segments
+    p->max_segs = (size_t)p->nbuckets + ((n * (size_t)p->W) >> min_shift) + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -617,8 +648,9 @@ StreamKit* stream_kit() {
 // windows are processed top-down in groups of halving size (.., 4, 2, 1, 1): while the lower groups are
 // still being accumulated, the upper groups are reduced and folded into the Horner chain on a second
 // stream, so only the last (single-window) group's reduction latency is exposed.
-static void make_groups(GroupMap* gm, int W, bool pipeline) {
+static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline) {
     gm->ngroups = 0;
+    gm->log2B = c - 1;
     int hi = W - 1;
     if (!pipeline) {
         gm->w_hi[0] = hi;
@@ -636,8 +668,21 @@ static void make_groups(GroupMap* gm, int W, bool pipeline) {
             remaining -= take;
         }
     }
-    for (int g = 0; g < gm->ngroups; g++)
-        for (int w = gm->w_lo[g]; w <= gm->w_hi[g]; w++) gm->group_of_window[w] = (uint8_t)g;
+    for (int g = 0; g < gm->ngroups; g++) {
+        int nwin = gm->w_hi[g] - gm->w_lo[g] + 1;
+        // a group's accumulation has ~nwin * 2^(c-1) threads; with few windows, shorter segments keep the
+        // SMs full (the extra partial sums are folded by msm_heavy_small_kernel)
+        int shift = seg_shift;
+        if (pipeline && gm->ngroups > 1) {
+            if (nwin <= 1) shift -= 2;
+            else if (nwin <= 3) shift -= 1;
+        }
+        if (shift < 4) shift = 4;
+        for (int w = gm->w_lo[g]; w <= gm->w_hi[g]; w++) {
+            gm->group_of_window[w] = (uint8_t)g;
+            gm->seg_shift_of_window[w] = (uint8_t)shift;
+        }
+    }
 }
 
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
@@ -672,7 +717,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     }
     StreamKit* kit = n >= (1u << 15) ? stream_kit() : nullptr;
     GroupMap gm;
-    make_groups(&gm, p.W, kit != nullptr);
+    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr);
 
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
@@ -701,30 +746,30 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     msm_digits_kernel<false><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, counts, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
     uint32_t ntiles = (p.nbuckets + 1 + kScanTile - 1) / kScanTile;  // +1: the sentinel slot
-    scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, 0, tiles);
+    scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, 0, tiles, offsets, cursors);
+    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles, offsets, cursors);
     CBP_LAUNCH_CHECK(); nl++;
     msm_digits_kernel<true><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, cursors, entries);
     CBP_LAUNCH_CHECK(); nl++;
     // segments
-    scan_tile_sums_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, p.seg_shift, tiles);
+    scan_tile_sums_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, p.seg_shift, tiles, segoff, nullptr);
+    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles, segoff, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
     const uint32_t* nsegs_p = segoff + p.nbuckets;
     unsigned bgrid = (p.nbuckets + 255) / 256, sgrid = (unsigned)((p.max_segs + 255) / 256);
-    seg_build_kernel<<<bgrid, 256, 0, st>>>(counts, offsets, segoff, p.nbuckets, p.B, p.seg_shift, gm, desc, heavy, heavy_cnt);
+    seg_build_kernel<<<bgrid, 256, 0, st>>>(counts, offsets, segoff, p.nbuckets, p.B, gm, desc, heavy, heavy_cnt);
     CBP_LAUNCH_CHECK(); nl++;
-    seg_hist_kernel<<<sgrid < 1184 ? sgrid : 1184, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins);
+    seg_hist_kernel<<<sgrid < 1184 ? sgrid : 1184, 256, 0, st>>>(desc, offsets, nsegs_p, gm, bins);
     CBP_LAUNCH_CHECK(); nl++;
     seg_bin_scan_kernel<<<1, kSegBins, 0, st>>>(bins, binstart);
     CBP_LAUNCH_CHECK(); nl++;
-    seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, p.B, p.seg_shift, gm, bins, order);
+    seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, gm, bins, order);
     CBP_LAUNCH_CHECK(); nl++;
 
     prof_end(BPK_PROF_MSM_FRONT, st);
@@ -735,10 +780,11 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         cudaStream_t tail = kit ? kit->red[g] : st;
         int nwin = gm.w_hi[g] - gm.w_lo[g] + 1, w_lo = gm.w_lo[g];
         // upper bound on this group's segments: its buckets + its share of the entries
-        size_t seg_bound = (size_t)nwin * p.B + ((n * (size_t)nwin) >> p.seg_shift) + 1;
+        const int gshift = gm.seg_shift_of_window[w_lo];
+        size_t seg_bound = (size_t)nwin * p.B + ((n * (size_t)nwin) >> gshift) + 1;
         if (g == 0) prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
         msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, offsets, segoff,
-                                                                                  p.seg_shift, order, binstart, g, buckets,
+                                                                                  gm, order, binstart, g, buckets,
                                                                                   segsums);
         if (g == gm.ngroups - 1) {
             prof_end(BPK_PROF_MSM_ACCUMULATE, st);
@@ -749,7 +795,12 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
             if ((e = cudaEventRecord(kit->ev_group[g], st)) != cudaSuccess) return (int)e;
             if ((e = cudaStreamWaitEvent(tail, kit->ev_group[g], 0)) != cudaSuccess) return (int)e;
         }
-        size_t heavy_bound = ((n * (size_t)nwin) >> p.seg_shift) + 1;
+        size_t heavy_bound = ((n * (size_t)nwin) >> gshift) + 1;
+        if (heavy_bound > (size_t)nwin * p.B) heavy_bound = (size_t)nwin * p.B;
+        unsigned sgrid_h = (unsigned)((heavy_bound + 127) / 128);
+        msm_heavy_small_kernel<<<sgrid_h < 4736 ? sgrid_h : 4736, 128, 0, tail>>>(heavy, heavy_cnt, g, (uint32_t)w_lo * p.B,
+                                                                                  segoff, segsums, buckets);
+        CBP_LAUNCH_CHECK(); nl++;
         unsigned hgrid = (unsigned)((heavy_bound * 32 + 127) / 128);
         msm_heavy_fix_kernel<<<hgrid < 2368 ? hgrid : 2368, 128, 0, tail>>>(heavy, heavy_cnt, g, (uint32_t)w_lo * p.B, segoff,
                                                                             segsums, buckets);
