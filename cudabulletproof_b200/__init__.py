@@ -53,6 +53,7 @@ SIGNATURES = {
     "bpk_version": (C.c_char_p, []),
     "bpk_last_error": (_i, []),
     "bpk_last_cuda_error": (_i, []),
+    "bpk_clear_last_error": (_i, []),
     "bpk_kernel_launches": (_u64, []),
     "bpk_profile_enable": (_i, [_i]),
     "bpk_profile_reset": (_i, []),

@@ -89,6 +89,10 @@ extern "C" {
 const char* bpk_version(void) { return "cudabulletproof_b200 0.1 (sm_100a)"; }
 int bpk_last_error(void) { return g_last_error.load(); }
 int bpk_last_cuda_error(void) { return g_last_cuda_error.load(); }
+int bpk_clear_last_error(void) {
+    g_last_cuda_error.store(0);
+    return g_last_error.exchange(0);
+}
 uint64_t bpk_kernel_launches(void) { return g_launches.load(); }
 
 int bpk_msm_window_bits(size_t n) { return msm_pick_window(n); }

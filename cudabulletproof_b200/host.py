@@ -25,6 +25,19 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _guard(fn, *args):
+    """Call a host-pointer drop-in (which cannot return a status) and fail loudly on a CUDA error.
+    Argument errors keep the reference's behaviour: message on stderr, outputs untouched, no exception."""
+    lib = _lib()
+    lib.bpk_clear_last_error()
+    rv = fn(*args)
+    cuda_err = lib.bpk_last_cuda_error()
+    if lib.bpk_last_error() == 2:
+        from . import BpkError
+        raise BpkError(f"{fn.__name__}: CUDA error {cuda_err} (no CPU fallback)")
+    return rv
+
+
 def _fv(a):
     from . import FieldVector
     return FieldVector(a.ctypes.data, a.shape[0])
@@ -48,7 +61,7 @@ def cuda_point_vector_multi_scalar_mul(scalars, points, shared=False, result=Non
     out = np.zeros(16, dtype=np.uint64) if result is None else result
     fv, pv = _fv(s), _pv(p)
     fn = _lib().cuda_point_vector_multi_scalar_mul_shared if shared else _lib().cuda_point_vector_multi_scalar_mul
-    fn(_ptr(out), C.byref(fv), C.byref(pv))
+    _guard(fn, _ptr(out), C.byref(fv), C.byref(pv))
     return out
 
 
@@ -57,14 +70,14 @@ def cuda_field_vector_inner_product(a, b, shared=False, result=None):
     out = np.zeros(4, dtype=np.uint64) if result is None else result
     fa, fb = _fv(a), _fv(b)
     fn = _lib().cuda_field_vector_inner_product_shared if shared else _lib().cuda_field_vector_inner_product
-    fn(_ptr(out), C.byref(fa), C.byref(fb))
+    _guard(fn, _ptr(out), C.byref(fa), C.byref(fb))
     return out
 
 
 def _batch2(name, a, b):
     a, b = _c(a, 4), _c(b, 4)
     out = np.zeros_like(a)
-    getattr(_lib(), name)(_ptr(out), _ptr(a), _ptr(b), a.shape[0])
+    _guard(getattr(_lib(), name), _ptr(out), _ptr(a), _ptr(b), a.shape[0])
     return out
 
 
@@ -87,14 +100,14 @@ def cuda_soa_field_add(a, b):
 def cuda_batch_field_square(a):
     a = _c(a, 4)
     out = np.zeros_like(a)
-    _lib().cuda_batch_field_square(_ptr(out), _ptr(a), a.shape[0])
+    _guard(_lib().cuda_batch_field_square, _ptr(out), _ptr(a), a.shape[0])
     return out
 
 
 def cuda_batch_field_invert(a):
     a = _c(a, 4)
     out = np.zeros_like(a)
-    _lib().cuda_batch_field_invert(_ptr(out), _ptr(a), a.shape[0])
+    _guard(_lib().cuda_batch_field_invert, _ptr(out), _ptr(a), a.shape[0])
     return out
 
 
@@ -239,7 +252,7 @@ def cuda_range_proof_verify(proof, V, n, G, H, g, h):
     V = np.ascontiguousarray(V, dtype=np.uint64)
     g = np.ascontiguousarray(g, dtype=np.uint64)
     h = np.ascontiguousarray(h, dtype=np.uint64)
-    return bool(_lib().cuda_range_proof_verify(C.byref(proof), _ptr(V), n, C.byref(gv), C.byref(hv), _ptr(g), _ptr(h)))
+    return bool(_guard(_lib().cuda_range_proof_verify, C.byref(proof), _ptr(V), n, C.byref(gv), C.byref(hv), _ptr(g), _ptr(h)))
 
 
 def cuda_inner_product_verify(proof, P, G, H, Q):
@@ -247,7 +260,7 @@ def cuda_inner_product_verify(proof, P, G, H, Q):
     gv, hv = _pv(G), _pv(H)
     P = np.ascontiguousarray(P, dtype=np.uint64)
     Q = np.ascontiguousarray(Q, dtype=np.uint64)
-    return bool(_lib().cuda_inner_product_verify(C.byref(proof), _ptr(P), C.byref(gv), C.byref(hv), _ptr(Q)))
+    return bool(_guard(_lib().cuda_inner_product_verify, C.byref(proof), _ptr(P), C.byref(gv), C.byref(hv), _ptr(Q)))
 
 
 def ipa_fold_scalars(a, b, u, u_inv, stream=None):

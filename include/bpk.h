@@ -29,6 +29,8 @@ const char* bpk_version(void);
 /* last error recorded by any entry point of this library in this process (0 = none) */
 int bpk_last_error(void);
 int bpk_last_cuda_error(void);
+/* returns the recorded error and resets it (the host-pointer drop-ins cannot return a status) */
+int bpk_clear_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t bpk_kernel_launches(void);
 

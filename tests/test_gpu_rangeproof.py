@@ -230,3 +230,69 @@ def test_batch_verify_larger_batch_with_one_percent_tampered(oracle, gens64):
     for i in bad_idx[:2] + [0, 7]:
         proof, V, keep = record_to_struct(h[i], 64)
         assert oracle_verify(oracle, gens64, proof, V) == bool(got[i])
+
+
+def test_ipa_n4096_config4(oracle):
+    """BASELINE config 4 (aggregated m = 64 x 64-bit: IPA over n = 4096, 12 rounds): one folding round of the
+    a/b and G/H vectors at full size against the oracle, and stand-alone verification of an oracle-made
+    4096-wide inner-product proof (accept, then reject after tampering)."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    from tests.helpers import gen_points
+    rng = random.Random(0xA66E0040)
+    n = 4096
+    # generators: additive walk (cheap for the CPU oracle), all in the prime-order subgroup
+    base, step = pyref.pt_mul(rng.getrandbits(128) | 1, pyref.B), pyref.pt_mul(rng.getrandbits(128) | 1, pyref.B)
+    pts, cur = [], base
+    for _ in range(2 * n + 1):
+        pts.append(ob.affine_to_ge(*cur))
+        cur = pyref.pt_add(cur, step)
+    G, H, Q = np.stack(pts[:n]), np.stack(pts[n:2 * n]), pts[2 * n]
+    a = ob.ints_to_fe([rng.getrandbits(252) for _ in range(n)])
+    b = ob.ints_to_fe([rng.getrandbits(252) for _ in range(n)])
+
+    def dev(x):
+        return torch.from_numpy(x.view(np.uint8).reshape(-1)).cuda()
+
+    # one folding round at full width
+    u_int = rng.getrandbits(252) % L
+    u, ui = ob.int_to_fe(u_int), ob.int_to_fe(pow(u_int, L - 2, L))
+    nh = n // 2
+    wa, wb = np.zeros((nh, 4), np.uint64), np.zeros((nh, 4), np.uint64)
+    oracle.ipa_fold_scalars(ob.ptr(wa), ob.ptr(wb), ob.ptr(a), ob.ptr(b), nh, ob.ptr(u), ob.ptr(ui))
+    ga, gb = cbp.ipa_fold_scalars(dev(a), dev(b), dev(u), dev(ui))
+    assert np.array_equal(ga.cpu().numpy().view(np.uint64).reshape(nh, 4), wa)
+    assert np.array_equal(gb.cpu().numpy().view(np.uint64).reshape(nh, 4), wb)
+    sub = 64  # the point fold is 4 scalar multiplications per output on the CPU: check a 64-wide slice of it
+    idx = np.r_[0:sub // 2, nh:nh + sub // 2]
+    Gs, Hs = G[idx].copy(), H[idx].copy()
+    wG, wH = np.zeros((sub // 2, 16), np.uint64), np.zeros((sub // 2, 16), np.uint64)
+    oracle.ipa_fold_points(ob.ptr(wG), ob.ptr(wH), ob.ptr(Gs), ob.ptr(Hs), sub // 2, ob.ptr(u), ob.ptr(ui))
+    gG, gH = cbp.ipa_fold_points(dev(G), dev(H), dev(u), dev(ui))
+    assert np.array_equal(gG.cpu().numpy().view(np.uint64).reshape(nh, 16)[:sub // 2], wG)
+    assert np.array_equal(gH.cpu().numpy().view(np.uint64).reshape(nh, 16)[:sub // 2], wH)
+
+    # full 12-round proof from the oracle, verified by the single-MSM device verifier
+    av, bv, Gv, Hv = ob.field_vector(a), ob.field_vector(b), ob.point_vector(G), ob.point_vector(H)
+    c = np.zeros(4, dtype=np.uint64)
+    oracle.field_vector_inner_product(ob.ptr(c), C.byref(av), C.byref(bv))
+    assert np.array_equal(cbp.cuda_field_vector_inner_product(a, b), c)
+    P1, P2, P3, P = (np.zeros(16, dtype=np.uint64) for _ in range(4))
+    sc_all = np.concatenate([a, b, c.reshape(1, 4)])
+    pt_all = np.concatenate([G, H, Q.reshape(1, 16)])
+    P = cbp.cuda_point_vector_multi_scalar_mul(sc_all, pt_all)  # P = <a,G> + <b,H> + c Q (GPU MSM, 8193 points)
+    s64, p64 = sc_all[:64].copy(), pt_all[:64].copy()  # keep alive: the vector structs hold raw pointers
+    fv, pv = ob.field_vector(s64), ob.point_vector(p64)
+    oracle.point_vector_multi_scalar_mul(ob.ptr(P1), C.byref(fv), C.byref(pv))
+    assert np.array_equal(cbp.cuda_point_vector_multi_scalar_mul(s64, p64), P1)
+    proof = ob.InnerProductProof()
+    oracle.inner_product_prove(C.byref(proof), C.byref(av), C.byref(bv), C.byref(Gv), C.byref(Hv), ob.ptr(Q), ob.ptr(c),
+                               bytes(32))
+    assert proof.L_len == 12
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is True
+    proof.R.elements[7].X.limbs[0] ^= 1
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
+    proof.R.elements[7].X.limbs[0] ^= 1
+    proof.a.elements[0].limbs[0] ^= 1
+    assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
+    oracle.inner_product_proof_free(C.byref(proof))
