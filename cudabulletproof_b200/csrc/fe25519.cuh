@@ -171,7 +171,125 @@ __device__ __forceinline__ void fe_mul(fe& r, const fe& a, const fe& b) {
     mul_wide(w, a, b);
     fe_fold(r, w);
 }
-__device__ __forceinline__ void fe_sq(fe& r, const fe& a) { fe_mul(r, a, a); }
+// ---- dedicated squaring: 28 off-diagonal products, doubled, plus 8 squares = 36 wide multiplies
+// (+8 for the fold) instead of 64 (+8) ----------------------------------------------------------------
+__device__ __forceinline__ void mul_row3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& c4,
+                                         uint32_t& c5, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t b) {
+    asm("mul.lo.u32 %0, %6, %9;\n\t"
+        "mul.hi.u32 %1, %6, %9;\n\t"
+        "mul.lo.u32 %2, %7, %9;\n\t"
+        "mul.hi.u32 %3, %7, %9;\n\t"
+        "mul.lo.u32 %4, %8, %9;\n\t"
+        "mul.hi.u32 %5, %8, %9;"
+        : "=&r"(c0), "=&r"(c1), "=&r"(c2), "=&r"(c3), "=&r"(c4), "=&r"(c5)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(b));
+}
+// c[0..5] (+carry into c6) += {x0,x1,x2} * b
+__device__ __forceinline__ void mad_row3(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& c4,
+                                         uint32_t& c5, uint32_t& c6, uint32_t x0, uint32_t x1, uint32_t x2,
+                                         uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32       %6, %6, 0;"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(b));
+}
+__device__ __forceinline__ void mad_row2(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& c4,
+                                         uint32_t x0, uint32_t x1, uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32       %4, %4, 0;"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
+        : "r"(x0), "r"(x1), "r"(b));
+}
+__device__ __forceinline__ void mad_row1(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t x0, uint32_t b) {
+    asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32       %2, %2, 0;"
+        : "+r"(c0), "+r"(c1), "+r"(c2)
+        : "r"(x0), "r"(b));
+}
+__device__ __forceinline__ void sq_wide(uint32_t (&w)[16], const fe& a) {
+    const uint32_t* x = a.v;
+    // off-diagonal products x_i x_j (i < j) at word position i + j: even positions in E, odd in O (O[k] = word k+1)
+    uint32_t E[16], O[15];
+#pragma unroll
+    for (int i = 0; i < 16; i++) E[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) O[i] = 0;
+    mul_row4(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], x[1], x[3], x[5], x[7], x[0]);  // pos 1,3,5,7
+    mul_row3(E[2], E[3], E[4], E[5], E[6], E[7], x[2], x[4], x[6], x[0]);                    // pos 2,4,6
+    mad_row3(O[2], O[3], O[4], O[5], O[6], O[7], O[8], x[2], x[4], x[6], x[1]);              // pos 3,5,7
+    mad_row3(E[4], E[5], E[6], E[7], E[8], E[9], E[10], x[3], x[5], x[7], x[1]);             // pos 4,6,8
+    mad_row3(O[4], O[5], O[6], O[7], O[8], O[9], O[10], x[3], x[5], x[7], x[2]);             // pos 5,7,9
+    mad_row2(E[6], E[7], E[8], E[9], E[10], x[4], x[6], x[2]);                               // pos 6,8
+    mad_row2(O[6], O[7], O[8], O[9], O[10], x[4], x[6], x[3]);                               // pos 7,9
+    mad_row2(E[8], E[9], E[10], E[11], E[12], x[5], x[7], x[3]);                             // pos 8,10
+    mad_row2(O[8], O[9], O[10], O[11], O[12], x[5], x[7], x[4]);                             // pos 9,11
+    mad_row1(E[10], E[11], E[12], x[6], x[4]);                                               // pos 10
+    mad_row1(O[10], O[11], O[12], x[6], x[5]);                                               // pos 11
+    mad_row1(E[12], E[13], E[14], x[7], x[5]);                                               // pos 12
+    mad_row1(O[12], O[13], O[14], x[7], x[6]);                                               // pos 13
+    // S = E + (O << 32)
+    uint32_t S[16];
+    S[0] = 0;  // no product lands on word 0
+    asm("add.cc.u32  %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32    %14, %29, %44;"
+        : "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "=&r"(S[7]), "=&r"(S[8]),
+          "=&r"(S[9]), "=&r"(S[10]), "=&r"(S[11]), "=&r"(S[12]), "=&r"(S[13]), "=&r"(S[14]), "=&r"(S[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]), "r"(O[2]),
+          "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]),
+          "r"(O[12]), "r"(O[13]), "r"(O[14]));
+    // w = 2 S (S < 2^511) ...
+#pragma unroll
+    for (int i = 15; i > 0; i--) w[i] = __funnelshift_l(S[i - 1], S[i], 1);
+    w[0] = 0;
+    // ... + the squares x_i^2 at words (2i, 2i+1): one carry chain
+    asm("mad.lo.cc.u32  %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32    %15, %23, %23, %15;"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]),
+          "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+}
+__device__ __forceinline__ void fe_sq(fe& r, const fe& a) {
+    uint32_t w[16];
+    sq_wide(w, a);
+    fe_fold(r, w);
+}
 
 // r = a + b (weakly reduced)
 __device__ __forceinline__ void fe_add(fe& r, const fe& a, const fe& b) {
