@@ -63,56 +63,65 @@ __device__ __forceinline__ void sc_sub_l9(uint32_t (&r)[9]) {
     r[8] -= (uint32_t)borrow;
 }
 
-// r = x mod l for a 512-bit x (16 words).  Barrett: q3 = floor(floor(x / b^7) * mu / b^9),
-// r = (x - q3 l) mod b^9, then at most two subtractions of l.
+// r = x mod l for a 512-bit x (16 words), using l = 2^252 + delta with delta < 2^125 (the structure
+// ref10's sc_reduce exploits): 2^252 = -delta (mod l), so with x = lo + 2^252 hi
+//     x = lo - hi delta,  and the 385-bit product hi*delta is folded the same way twice more:
+//     x = lo - lo1 + lo2 - P3 (mod l),   P1 = hi delta, P2 = (P1 >> 252) delta, P3 = (P2 >> 252) delta.
+// 36 + 20 + 4 = 60 word products instead of Barrett's 126, no quotient estimate.
+// (A first Barrett version in plain C compiled to ~640 instructions per reduction.)
+__device__ __forceinline__ void sc_mul_delta(uint32_t* out, int nout, const uint32_t* h, int nh) {
+    // out[0..nout) = h[0..nh) * delta (4 words); row-wise schoolbook, every partial sum fits 64 bits
+    const uint32_t d[4] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu};
+#pragma unroll
+    for (int i = 0; i < nout; i++) out[i] = 0;
+#pragma unroll
+    for (int i = 0; i < nh; i++) {
+        uint32_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i + j < nout) {
+                uint64_t m = (uint64_t)h[i] * d[j] + out[i + j] + carry;
+                out[i + j] = (uint32_t)m;
+                carry = (uint32_t)(m >> 32);
+            }
+        }
+        if (i + 4 < nout) out[i + 4] = carry;
+    }
+}
+// words of (v >> 252) for a little-endian word array v of nv words; nres result words
+__device__ __forceinline__ void sc_shr252(uint32_t* res, int nres, const uint32_t* v, int nv) {
+#pragma unroll
+    for (int i = 0; i < nres; i++) {
+        uint32_t lo = 7 + i < nv ? v[7 + i] : 0, hi = 8 + i < nv ? v[8 + i] : 0;
+        res[i] = (lo >> 28) | (hi << 4);
+    }
+}
 __device__ __forceinline__ void sc_reduce512(sc& out, const uint32_t (&x)[16]) {
-    // q2 = q1 * mu, only words >= 9 are needed (q3); compute full columns from 7 up for exact carries
-    uint32_t q3[9];
-    {
-        uint64_t acc_lo = 0, acc_hi = 0;  // 128-bit column accumulator
-#pragma unroll
-        for (int col = 0; col < 18; col++) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-                int j = col - i;
-                if (j < 0 || j > 8) continue;
-                uint64_t pr = (uint64_t)x[7 + i] * kScMu[j];
-                acc_lo += pr;
-                acc_hi += (acc_lo < pr);
-            }
-            if (col >= 9) q3[col - 9] = (uint32_t)acc_lo;
-            acc_lo = (acc_lo >> 32) | (acc_hi << 32);
-            acc_hi >>= 32;
-        }
-    }
-    // r2 = (q3 * l) mod b^9
-    uint32_t r2[9];
-    {
-        uint64_t acc_lo = 0, acc_hi = 0;
-#pragma unroll
-        for (int col = 0; col < 9; col++) {
-#pragma unroll
-            for (int i = 0; i < 9; i++) {
-                int j = col - i;
-                if (j < 0 || j > 7) continue;
-                if (j >= 4 && j <= 6) continue;  // zero words of l
-                uint64_t pr = (uint64_t)q3[i] * kScL[j];
-                acc_lo += pr;
-                acc_hi += (acc_lo < pr);
-            }
-            r2[col] = (uint32_t)acc_lo;
-            acc_lo = (acc_lo >> 32) | (acc_hi << 32);
-            acc_hi >>= 32;
-        }
-    }
+    uint32_t hi[9], P1[13], hi1[5], P2[9], hi2[1], P3[5];
+    sc_shr252(hi, 9, x, 16);       // 260 bits
+    sc_mul_delta(P1, 13, hi, 9);   // 385 bits
+    sc_shr252(hi1, 5, P1, 13);     // 133 bits
+    sc_mul_delta(P2, 9, hi1, 5);   // 258 bits
+    sc_shr252(hi2, 1, P2, 9);      // 6 bits
+    sc_mul_delta(P3, 5, hi2, 1);   // 131 bits
+    // v = lo + lo2 + 2l - lo1 - P3  in (0, 4l): signed 64-bit column arithmetic
+    const uint32_t two_l[8] = {0xb9eba7dau, 0xb024c634u, 0x45ef39acu, 0x29bdf3bdu, 0u, 0u, 0u, 0x20000000u};
     uint32_t r[9];
-    uint64_t borrow = 0;
+    int64_t c = 0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) {
-        uint64_t d = (uint64_t)x[i] - r2[i] - borrow;
-        r[i] = (uint32_t)d;
-        borrow = (d >> 63) & 1;
+    for (int i = 0; i < 8; i++) {
+        uint32_t lo = x[i], lo1 = P1[i], lo2 = P2[i];
+        if (i == 7) {
+            lo &= 0x0fffffffu;
+            lo1 &= 0x0fffffffu;
+            lo2 &= 0x0fffffffu;
+        }
+        c += (int64_t)lo + (int64_t)lo2 + (int64_t)two_l[i] - (int64_t)lo1 - (int64_t)(i < 5 ? P3[i] : 0u);
+        r[i] = (uint32_t)c;
+        c >>= 32;  // arithmetic shift: floor division
     }
+    r[8] = (uint32_t)c;
+    if (sc_geq_l9(r)) sc_sub_l9(r);
     if (sc_geq_l9(r)) sc_sub_l9(r);
     if (sc_geq_l9(r)) sc_sub_l9(r);
 #pragma unroll
