@@ -93,6 +93,77 @@ __device__ __forceinline__ void ge_dbl(ge_p3& r, const ge_p3& p) {
     fe_mul(r.T, E, H);
 }
 
+// ---- quad-cooperative point operations --------------------------------------------------------------
+// A dependent chain of point operations run by ONE lane is bound by the latency of its 8-9 sequential
+// field multiplications (~600 cycles each in a lone warp).  Here four adjacent lanes (a "quad",
+// role = lane & 3) hold identical copies of the operands and each computes one of the four independent
+// products of a stage; the results are exchanged with shuffles.  Depth per addition: 3 multiplications
+// instead of 9; per doubling: 2 instead of 8.  Used by the latency-bound tails (bucket-reduction levels,
+// Horner chain); every lane of the quad ends with the full result.
+__device__ __forceinline__ void fe_quad_exchange(fe& r0, fe& r1, fe& r2, fe& r3, const fe& mine) {
+    const int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r0.v[i] = __shfl_sync(0xffffffffu, mine.v[i], base + 0);
+        r1.v[i] = __shfl_sync(0xffffffffu, mine.v[i], base + 1);
+        r2.v[i] = __shfl_sync(0xffffffffu, mine.v[i], base + 2);
+        r3.v[i] = __shfl_sync(0xffffffffu, mine.v[i], base + 3);
+    }
+}
+__device__ __forceinline__ void fe_select4(fe& r, int role, const fe& a0, const fe& a1, const fe& a2, const fe& a3) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t lo = (role & 1) ? a1.v[i] : a0.v[i];
+        uint32_t hi = (role & 1) ? a3.v[i] : a2.v[i];
+        r.v[i] = (role & 2) ? hi : lo;
+    }
+}
+// r = p + q (unified); all four lanes of the quad must call this with identical p, q
+__device__ __forceinline__ void ge_add_quad(ge_p3& r, const ge_p3& p, const ge_p3& q) {
+    const int role = threadIdx.x & 3;
+    fe s1, a1, s2, a2, x, y, prod;
+    fe_sub(s1, p.Y, p.X);
+    fe_add(a1, p.Y, p.X);
+    fe_sub(s2, q.Y, q.X);
+    fe_add(a2, q.Y, q.X);
+    fe_select4(x, role, s1, a1, p.T, p.Z);
+    fe_select4(y, role, s2, a2, q.T, q.Z);
+    fe_mul(prod, x, y);  // role 0: A, 1: B, 2: T1 T2, 3: Z1 Z2
+    fe A, B, C, D;
+    fe_quad_exchange(A, B, C, D, prod);
+    fe_mul(C, C, fe_const_2d());
+    fe_dbl(D, D);
+    fe E, F, G, H;
+    fe_sub(E, B, A);
+    fe_sub(F, D, C);
+    fe_add(G, D, C);
+    fe_add(H, B, A);
+    fe_select4(x, role, E, G, F, E);
+    fe_select4(y, role, F, H, G, H);
+    fe_mul(prod, x, y);  // role 0: X3 = E F, 1: Y3 = G H, 2: Z3 = F G, 3: T3 = E H
+    fe_quad_exchange(r.X, r.Y, r.Z, r.T, prod);
+}
+// r = 2p
+__device__ __forceinline__ void ge_dbl_quad(ge_p3& r, const ge_p3& p) {
+    const int role = threadIdx.x & 3;
+    fe xy, x, prod;
+    fe_add(xy, p.X, p.Y);
+    fe_select4(x, role, p.X, p.Y, p.Z, xy);
+    fe_sq(prod, x);  // XX, YY, ZZ, (X+Y)^2
+    fe XX, YY, ZZ, S;
+    fe_quad_exchange(XX, YY, ZZ, S, prod);
+    fe E, F, G, H, y;
+    fe_dbl(ZZ, ZZ);
+    fe_add(H, YY, XX);
+    fe_sub(G, YY, XX);
+    fe_sub(E, S, H);
+    fe_sub(F, ZZ, G);
+    fe_select4(x, role, E, G, F, E);
+    fe_select4(y, role, F, H, G, H);
+    fe_mul(prod, x, y);
+    fe_quad_exchange(r.X, r.Y, r.Z, r.T, prod);
+}
+
 __device__ __forceinline__ void ge_neg(ge_p3& r, const ge_p3& p) {
     fe_neg(r.X, p.X);
     r.Y = p.Y;

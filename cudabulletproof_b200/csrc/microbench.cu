@@ -101,6 +101,36 @@ __global__ void __launch_bounds__(128, 4) k_ge_dbl(uint32_t* out, uint32_t seed)
     out[blockIdx.x * blockDim.x + threadIdx.x] = p.X.v[0] ^ p.T.v[1] ^ p.Y.v[2] ^ p.Z.v[3];
 }
 
+// latency probes: ONE warp per SM, dependent chain of point operations
+__global__ void __launch_bounds__(32) k_lat_add(uint32_t* out, uint32_t seed, int quad) {
+    ge_p3 p, q;
+    ge_p3_0(p);
+    ge_p3_0(q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { p.X.v[i] = seed + i + (threadIdx.x >> 2); q.X.v[i] = seed * 3 + i; q.T.v[i] = seed * 5 + blockIdx.x; }
+    for (int it = 0; it < 256; it++) {
+        if (quad) ge_add_quad(p, p, q); else ge_add(p, p, q);
+    }
+    out[blockIdx.x * 32 + threadIdx.x] = p.X.v[0] ^ p.T.v[1] ^ p.Y.v[2] ^ p.Z.v[3];
+}
+__global__ void __launch_bounds__(32) k_lat_dbl(uint32_t* out, uint32_t seed, int quad) {
+    ge_p3 p;
+    ge_p3_0(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { p.X.v[i] = seed + i + (threadIdx.x >> 2); p.Y.v[i] = seed * 9 + blockIdx.x; }
+    for (int it = 0; it < 256; it++) {
+        if (quad) ge_dbl_quad(p, p); else ge_dbl(p, p);
+    }
+    out[blockIdx.x * 32 + threadIdx.x] = p.X.v[0] ^ p.T.v[1] ^ p.Y.v[2] ^ p.Z.v[3];
+}
+__global__ void __launch_bounds__(32) k_lat_inv(uint32_t* out, uint32_t seed) {
+    fe a, r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = seed + i + threadIdx.x;
+    fe_invert(r, a);
+    out[blockIdx.x * 32 + threadIdx.x] = r.v[0];
+}
+
 template <typename F>
 static double time_ms(F launch, int reps) {
     cudaEvent_t e0, e1;
@@ -153,6 +183,16 @@ int main() {
         ms = time_ms([&] { k_ge_dbl<<<grid, 128>>>((uint32_t*)buf, 99); }, 5);
         printf("{\"bench\": \"ge_dbl\", \"blocks_per_sm\": %d, \"ms\": %.4f, \"Gops\": %.3f}\n", bps, ms,
                threads * (ITERS / 16) / ms / 1e6);
+    }
+    for (int quad = 0; quad < 2; quad++) {
+        double ms = time_ms([&] { k_lat_add<<<sms, 32>>>((uint32_t*)buf, 99, quad); }, 5);
+        printf("{\"bench\": \"latency_ge_add%s\", \"us_per_op\": %.3f}\n", quad ? "_quad" : "", ms * 1e3 / 256);
+        ms = time_ms([&] { k_lat_dbl<<<sms, 32>>>((uint32_t*)buf, 99, quad); }, 5);
+        printf("{\"bench\": \"latency_ge_dbl%s\", \"us_per_op\": %.3f}\n", quad ? "_quad" : "", ms * 1e3 / 256);
+    }
+    {
+        double ms = time_ms([&] { k_lat_inv<<<sms, 32>>>((uint32_t*)buf, 99); }, 5);
+        printf("{\"bench\": \"latency_fe_invert\", \"us\": %.3f}\n", ms * 1e3);
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
