@@ -334,7 +334,9 @@ def run_cuda(args):
         nbits, m = 64, args.proofs
         distinct = min(m, args.distinct_proofs)
         gpts, _ = cbp.synth_points(2 * nbits + 2, seed=0xB0070002, device=dev)
-        gens = cbp.Generators(gpts[:nbits], gpts[nbits:2 * nbits], gpts[2 * nbits], gpts[2 * nbits + 1], device=dev)
+        gens = cbp.Generators(gpts[:nbits], gpts[nbits:2 * nbits], gpts[2 * nbits], gpts[2 * nbits + 1], device=dev,
+                              window_bits=args.fixed_window_bits)
+        nwin = 256 // args.fixed_window_bits
         rng = np.random.default_rng(0xC5 + rank)
         vals = rng.integers(0, 2**63, size=distinct, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=distinct, dtype=np.uint64)
         gam = rng.integers(0, 2**63, size=(distinct, 4), dtype=np.uint64)
@@ -377,12 +379,12 @@ def run_cuda(args):
         chunks = max(1, k_n // vsteps)
         rejected = int((acc == 0).sum().item())
         ok = rejected == len(bad) and bool((acc[torch.from_numpy(bad).to(dev)] == 0).all().item())
-        # algorithmic IMAD (SURVEY.md §8d units).  Whole proof: 131 bases x 32 windows mixed additions (504)
+        # algorithmic IMAD (SURVEY.md §8d units).  Whole proof: 131 bases x nwin windows mixed additions (504)
         # + 17 points x 64 windows x 8M (576) + 2 x (252 doublings (464) + 64 additions (648)) Horner.
-        # The timed kernel (verify_fixed_kernel, warp per proof) does the first term plus two 5-level
-        # shuffle trees of 9M additions per warp.
-        imad_proof = (131 * 32 * 504 + 17 * 64 * 576 + 2 * (252 * 464 + 64 * 648)) * 1.0
-        imad_kernel = 131 * 32 * 504 + 2 * 5 * 32 * 648.0
+        # The timed kernel (verify_fixed_kernel, nwin lanes per proof) does the first term plus two
+        # log2(nwin)-level shuffle trees of 9M additions.
+        imad_proof = (131 * nwin * 504 + 17 * 64 * 576 + 2 * (252 * 464 + 64 * 648)) * 1.0
+        imad_kernel = 131 * nwin * 504 + 2 * (nwin.bit_length() - 1) * nwin * 648.0
         per_launch = imad_kernel * (m / chunks)
         roofline = {"bound": "int", "kernel": "verify_fixed_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": per_launch / (k_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
@@ -410,7 +412,8 @@ def run_cuda(args):
                         "api": "bpk_range_verify_batch_device on records staged from pinned host memory"},
                 "config": {"workload": f"batch verification of 2^{m.bit_length() - 1} 64-bit range proofs per GPU, 1% tampered "
                                        "(BASELINE.json configs[4]); records prover-generated on device, "
-                                       f"{distinct} distinct proofs tiled"}}
+                                       f"{distinct} distinct proofs; generator tables with {args.fixed_window_bits}-bit windows"},
+                "fixed_window_bits": args.fixed_window_bits}
 
     msm_res = bench_msm() if args.workload in ("msm", "both") else None
     ver_res = bench_verify() if args.workload in ("verify", "both") else None
@@ -462,7 +465,11 @@ def main():
     ap.add_argument("--workload", default="both", choices=["msm", "verify", "both"])
     ap.add_argument("--log-n", type=int, default=LOG_N_DEFAULT)
     ap.add_argument("--proofs", type=int, default=VERIFY_PROOFS_DEFAULT)
-    ap.add_argument("--distinct-proofs", type=int, default=1024)
+    ap.add_argument("--distinct-proofs", type=int, default=VERIFY_PROOFS_DEFAULT,
+                    help="distinct prover-generated records per GPU (default: all distinct, so that table reads "
+                         "are as uncorrelated as in production)")
+    ap.add_argument("--fixed-window-bits", type=int, default=16, choices=[8, 16],
+                    help="window width of the generator tables (8: 51 MB in L2; 16: 6.5 GB in HBM, half the additions)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="points per host thread for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -58,13 +58,13 @@ __device__ __forceinline__ void cta_sc_sum(sc& v, sc* sred) {
     __syncthreads();
 }
 // sum over all rows of digits * table, normalised, valid in thread 0 (and stored to out, 128 B)
-__device__ __forceinline__ void cta_fixed_msm(ge_p3& result, const uint8_t* __restrict__ table, int nrows,
-                                              int8_t (*digits)[kFixWin], ge_p3* red) {
+__device__ __forceinline__ void cta_fixed_msm(ge_p3& result, const FixTab& table, int nrows,
+                                              int8_t (*digits)[kFixRowBytes], ge_p3* red) {
     ge_p3 acc;
     ge_p3_0(acc);
-    for (int item = threadIdx.x; item < nrows * kFixWin; item += kPThreads) {
-        int row = item / kFixWin, win = item % kFixWin;
-        fixed_base_madd(acc, table, (uint32_t)row, win, digits[row][win]);
+    for (int item = threadIdx.x; item < nrows * table.nwin; item += kPThreads) {
+        int row = item / table.nwin, win = item % table.nwin;
+        fixed_base_madd(acc, table, (uint32_t)row, win, digits[row]);
     }
     cta_point_sum(acc, red);
     if (threadIdx.x == 0) ge_normalize(acc);
@@ -72,7 +72,7 @@ __device__ __forceinline__ void cta_fixed_msm(ge_p3& result, const uint8_t* __re
 }
 __device__ __forceinline__ void zero_row(int8_t* row) {
 #pragma unroll
-    for (int i = 0; i < kFixWin; i++) row[i] = 0;
+    for (int i = 0; i < kFixRowBytes; i++) row[i] = 0;
 }
 __device__ __forceinline__ void hash_xy(Sha256& sh, const ge_p3& P) {  // P normalised, canonical
     sh.update_words(P.X.v);
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
                                                                 uint8_t* __restrict__ proofs, size_t rec_bytes) {
     __shared__ sc sa[kMaxN], sb[kMaxN], swG[kMaxN], swH[kMaxN], sl1[kMaxN], sr1[kMaxN];
     __shared__ sc sred[kPThreads];
-    __shared__ int8_t digits[2 * kMaxN + 2][kFixWin];
+    __shared__ __align__(16) int8_t digits[2 * kMaxN + 2][kFixRowBytes];
     __shared__ ge_p3 red[kPThreads];
     __shared__ sc sh_y, sh_z, sh_x, sh_u, sh_uinv, sh_yinv;
     __shared__ sc sh_ypow[kMaxK + 1], sh_yinvpow[kMaxK + 1];
@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
 
     const int t = threadIdx.x;
     const uint32_t p = blockIdx.x;
-    const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
-    const uint8_t* table = gens + gh->table_off;
+    const FixTab table = fixtab_of(gens);
     uint8_t* rec = proofs + (size_t)p * rec_bytes;
     const uint64_t v = values[p], seed = seeds[p];
     const int nrows = 2 * (int)n + 2, row_g = 2 * (int)n, row_h = 2 * (int)n + 1;
@@ -142,8 +141,8 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         sc_set0(vs);
         vs.v[0] = (uint32_t)v;
         vs.v[1] = (uint32_t)(v >> 32);
-        sc_recode_signed<8>(digits[row_g], vs, kFixWin);
-        sc_recode_signed<8>(digits[row_h], gamma, kFixWin);
+        fix_recode(digits[row_g], vs, table.wbits);
+        fix_recode(digits[row_h], gamma, table.wbits);
     }
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
@@ -154,12 +153,12 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     __syncthreads();
     // ---- A = alpha h + <aL, G> + <aR, H> (:1267-1276) ----
     if (t < (int)n) {
-        sc_recode_signed<8>(digits[t], aL, kFixWin);
-        sc_recode_signed<8>(digits[n + t], aR, kFixWin);
+        fix_recode(digits[t], aL, table.wbits);
+        fix_recode(digits[n + t], aR, table.wbits);
     }
     if (t == 0) {
         zero_row(digits[row_g]);
-        sc_recode_signed<8>(digits[row_h], alpha, kFixWin);
+        fix_recode(digits[row_h], alpha, table.wbits);
     }
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
@@ -170,10 +169,10 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     __syncthreads();
     // ---- S = rho h + <sL, G> + <sR, H> (:1279-1288) ----
     if (t < (int)n) {
-        sc_recode_signed<8>(digits[t], sL, kFixWin);
-        sc_recode_signed<8>(digits[n + t], sR, kFixWin);
+        fix_recode(digits[t], sL, table.wbits);
+        fix_recode(digits[n + t], sR, table.wbits);
     }
-    if (t == 0) sc_recode_signed<8>(digits[row_h], rho, kFixWin);
+    if (t == 0) fix_recode(digits[row_h], rho, table.wbits);
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
     if (t == 0) {
@@ -253,16 +252,16 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     for (int r = t; r < nrows; r += kPThreads) zero_row(digits[r]);
     __syncthreads();
     if (t == 0) {
-        sc_recode_signed<8>(digits[row_g], t1, kFixWin);
-        sc_recode_signed<8>(digits[row_h], tau1, kFixWin);
+        fix_recode(digits[row_g], t1, table.wbits);
+        fix_recode(digits[row_h], tau1, table.wbits);
     }
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
     if (t == 0) {
         ge_store(rec + kRecT1, P);
         sh_pts[0] = P;
-        sc_recode_signed<8>(digits[row_g], t2, kFixWin);
-        sc_recode_signed<8>(digits[row_h], tau2, kFixWin);
+        fix_recode(digits[row_g], t2, table.wbits);
+        fix_recode(digits[row_h], tau2, table.wbits);
     }
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
@@ -341,12 +340,12 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
                 bool g_on = side == 0 ? hi : !hi;  // L uses G_R and H_L; R uses G_L and H_R
                 if (g_on) sc_mul(cg, sa[side == 0 ? m - np : m + np], swG[t]);
                 else sc_mul(ch, sb[side == 0 ? m + np : m - np], swH[t]);
-                sc_recode_signed<8>(digits[t], cg, kFixWin);
-                sc_recode_signed<8>(digits[n + t], ch, kFixWin);
+                fix_recode(digits[t], cg, table.wbits);
+                fix_recode(digits[n + t], ch, table.wbits);
             }
             if (t == 0) {
                 zero_row(digits[row_g]);
-                sc_recode_signed<8>(digits[row_h], side == 0 ? cL : cR, kFixWin);
+                fix_recode(digits[row_h], side == 0 ? cL : cR, table.wbits);
             }
             __syncthreads();
             cta_fixed_msm(P, table, nrows, digits, red);

@@ -10,17 +10,19 @@
 //   (t - delta) g + taux h                       ==  z^2 V + x T1 + x^2 T2
 //   sum (a s_i + z) G_i + sum ((b s_i^-1 - z^2 2^i) y^-i - z) H_i + (mu + ab - t) h
 //                                                ==  A + x S + sum u_j^2 L_j + sum u_j^-2 R_j
-// as multi-scalar sums: the 2n+2 shared generators through precomputed 8-bit fixed-base tables
-// (no doublings), the 2 log n + 5 per-proof points with 4-bit windows.
+// as multi-scalar sums: the 2n+2 shared generators through precomputed fixed-base tables (8- or 16-bit
+// windows, no doublings), the 2 log n + 5 per-proof points with 4-bit windows.
 //
-// Kernels per batch:
+// Kernels per batch (see the block comment above verify_coeff_kernel for the middle ones):
 //   verify_transcript  1 thread / proof : on-curve checks, SHA-256 challenges, scalar inversions
-//   verify_msm         1 CTA    / proof : coefficients, fixed-base sums, per-window variable sums
+//   verify_coeff / verify_fixed / verify_vtab / verify_winsum : the two multi-scalar sums, by phase
 //   verify_finish      1 thread / (proof, identity): Horner over the 64 windows, equality test
 //   verify_combine     accept bits
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
+#include <unordered_map>
 #include "../../include/cuda_bulletproof.h"
 #include "common.h"
 #include "rangeproof.cuh"
@@ -29,8 +31,9 @@
 namespace cbp {
 
 // ---- generator tables -----------------------------------------------------------------------------
+// pow_out[b][j] = 2^(wbits j) Base_b
 __global__ void gens_pow_kernel(const uint8_t* __restrict__ G, const uint8_t* __restrict__ H,
-                                const uint8_t* __restrict__ g, const uint8_t* __restrict__ h, uint32_t n,
+                                const uint8_t* __restrict__ g, const uint8_t* __restrict__ h, uint32_t n, int wbits,
                                 uint8_t* __restrict__ pow_out, uint8_t* __restrict__ bases_out) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nb = 2 * n + 2;
@@ -41,40 +44,49 @@ __global__ void gens_pow_kernel(const uint8_t* __restrict__ G, const uint8_t* __
     ge_p3 Pn = P;
     ge_normalize(Pn);
     ge_store(bases_out + (size_t)b * 128, Pn);
-    for (int j = 0; j < kFixWin; j++) {
-        ge_store(pow_out + ((size_t)b * kFixWin + j) * 128, P);
-        for (int s = 0; s < 8; s++) ge_dbl(P, P);
+    const int nwin = fix_nwin(wbits);
+    for (int j = 0; j < nwin; j++) {
+        ge_store(pow_out + ((size_t)b * nwin + j) * 128, P);
+        for (int s = 0; s < wbits; s++) ge_dbl(P, P);
     }
 }
-// one thread per (base, window): multiples 1..128 of 2^(8 win) Base, normalised with one inversion
+// One thread per run of kTabRun consecutive multiples of M = 2^(wbits win) Base: the first one by
+// double-and-add, the rest by repeated addition of M, then ONE field inversion for the run (Montgomery's
+// trick, prefix products kept in local memory) to write the affine precomputed form (y+x, y-x, 2dxy).
+static constexpr int kTabRun = 32;
 __global__ void __launch_bounds__(64) gens_table_kernel(const uint8_t* __restrict__ pow_in, uint32_t nbases,
-                                                        uint8_t* __restrict__ table, uint8_t* __restrict__ prefix) {
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= nbases * kFixWin) return;
+                                                        int nwin, uint32_t entries, uint8_t* __restrict__ table) {
+    const uint32_t runs = entries / kTabRun;
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (size_t)nbases * nwin * runs) return;
+    const size_t bw = id / runs;
+    const uint32_t run_idx = (uint32_t)(id % runs);
     ge_p3 M, acc;
-    ge_load(M, pow_in + (size_t)id * 128);
-    acc = M;
-    uint8_t* slot = table + (size_t)id * kFixEntries * 96;
-    uint8_t* pre = prefix + (size_t)id * kFixEntries * 32;
+    ge_load(M, pow_in + bw * 128);
+    uint32_t m0 = run_idx * kTabRun + 1;
+    ge_scalarmult_bits(acc, &m0, 32 - __clz(m0), M);
+    uint8_t* slot = table + (bw * entries + (m0 - 1)) * 96;
+    fe pre[kTabRun];
     fe run;
     fe_set1(run);
-    for (int d = 0; d < kFixEntries; d++) {
+#pragma unroll 1
+    for (int d = 0; d < kTabRun; d++) {
         fe_store(slot + d * 96, acc.X);
         fe_store(slot + d * 96 + 32, acc.Y);
         fe_store(slot + d * 96 + 64, acc.Z);
-        fe_store(pre + d * 32, run);
+        pre[d] = run;
         fe_mul(run, run, acc.Z);
         ge_add(acc, acc, M);
     }
     fe inv;
     fe_invert(inv, run);
-    for (int d = kFixEntries - 1; d >= 0; d--) {
-        fe X, Y, Z, p, zi;
+#pragma unroll 1
+    for (int d = kTabRun - 1; d >= 0; d--) {
+        fe X, Y, Z, zi;
         fe_load(X, slot + d * 96);
         fe_load(Y, slot + d * 96 + 32);
         fe_load(Z, slot + d * 96 + 64);
-        fe_load(p, pre + d * 32);
-        fe_mul(zi, inv, p);
+        fe_mul(zi, inv, pre[d]);
         fe_mul(inv, inv, Z);
         fe_mul(X, X, zi);
         fe_mul(Y, Y, zi);
@@ -320,48 +332,24 @@ __device__ __forceinline__ int var_point_offset(int q, int k) {  // record offse
            q == nvar2 + 1 ? kRecT1 : kRecT2;
 }
 
-__global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const VScal* __restrict__ vscal, uint32_t n, int k,
+__global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8_t* __restrict__ gens,
+                                                                     const VScal* __restrict__ vscal, uint32_t n, int k,
                                                                      int8_t* __restrict__ digits,
                                                                      int8_t* __restrict__ vdigits) {
+    __shared__ sc s_sh[kMaxN], y_sh[kMaxN];
     const uint32_t p = blockIdx.x;
     const int t = threadIdx.x;
     const VScal& vs = vscal[p];
-    if (!vs.valid) return;
-    int8_t* drow = digits + (size_t)p * kRowsMax * kFixWin;
+    if (!vs.valid) return;  // whole CTA
+    const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
+    int8_t* drow = digits + (size_t)p * kRowsMax * kFixRowBytes;
     int8_t* vrow = vdigits + (size_t)p * kVarMax * 64;
     const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
-    if (t < (int)n) {
-        // s_t = prod_j u_j^(+-1) built from s_0 = prod u_j^-1: multiply by u_j^2 for every set bit;
-        // s_(n-1-t) is the same with the bits complemented.  y^-t from the y^-(2^m) ladder.
-        sc s = vs.s0, sr = vs.s0, yp;
-        sc_set1(yp);
-#pragma unroll 1
-        for (int m = 0; m < k; m++) {
-            sc u2 = vs.usq[k - 1 - m];
-            if ((t >> m) & 1) {
-                sc_mul(s, s, u2);
-                sc_mul(yp, yp, vs.ypow[m]);
-            } else {
-                sc_mul(sr, sr, u2);
-            }
-        }
-        sc cg, ch, tmp, two_i;
-        sc_mul(cg, vs.a, s);
-        sc_add(cg, cg, vs.z);
-        sc_set0(two_i);
-        two_i.v[t >> 5] = 1u << (t & 31);
-        sc_mul(tmp, vs.z2, two_i);
-        sc_mul(ch, vs.b, sr);
-        sc_sub(ch, ch, tmp);
-        sc_mul(ch, ch, yp);
-        sc_sub(ch, ch, vs.z);
-        sc_recode_signed<8>(drow + (size_t)t * kFixWin, cg, kFixWin);
-        sc_recode_signed<8>(drow + (size_t)(n + t) * kFixWin, ch, kFixWin);
-    } else if (t < (int)n + 3) {
+    if (t >= (int)n && t < (int)n + 3) {
         int r = t - (int)n;  // row 2n: h (mu + ab - t), 2n+1: g (t - delta), 2n+2: h (taux)
         sc v = r == 0 ? vs.h2 : r == 1 ? vs.g1 : vs.h1;
-        sc_recode_signed<8>(drow + (size_t)(2 * n + r) * kFixWin, v, kFixWin);
-    } else if (t - (int)n - 3 < nvar) {
+        fix_recode(drow + (size_t)(2 * n + r) * kFixRowBytes, v, wbits);
+    } else if (t >= (int)n + 3 && t - (int)n - 3 < nvar) {
         int q = t - (int)n - 3;  // positive scalars of the per-proof points (the two sides are compared)
         sc sv;
         if (q == 0) sc_set1(sv);
@@ -373,11 +361,47 @@ __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const VScal
         else sv = vs.x2;
         sc_recode_signed<4>(vrow + (size_t)q * 64, sv, 64);
     }
+    // s_t = prod_j u_j^(+-1) = s_0 * prod over the set bits m of t of u_(k-1-m)^2, and y^-t from the
+    // y^-(2^m) ladder, by doubling the filled prefix: level m fills [2^m, 2^(m+1)) from [0, 2^m)
+    if (t == 0) {
+        s_sh[0] = vs.s0;
+        sc one;
+        sc_set1(one);
+        y_sh[0] = one;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int m = 0; m < k; m++) {
+        const int half = 1 << m;
+        if (t >= half && t < 2 * half) {
+            sc a = s_sh[t - half], b = y_sh[t - half];
+            sc_mul(a, a, vs.usq[k - 1 - m]);
+            sc_mul(b, b, vs.ypow[m]);
+            s_sh[t] = a;
+            y_sh[t] = b;
+        }
+        __syncthreads();
+    }
+    if (t < (int)n) {
+        sc cg, ch, tmp, two_i;
+        sc_mul(cg, vs.a, s_sh[t]);
+        sc_add(cg, cg, vs.z);
+        sc_set0(two_i);
+        two_i.v[t >> 5] = 1u << (t & 31);
+        sc_mul(tmp, vs.z2, two_i);
+        sc_mul(ch, vs.b, s_sh[n - 1 - t]);  // s_(n-1-t) = s_t^-1: the bits complemented
+        sc_sub(ch, ch, tmp);
+        sc_mul(ch, ch, y_sh[t]);
+        sc_sub(ch, ch, vs.z);
+        fix_recode(drow + (size_t)t * kFixRowBytes, cg, wbits);
+        fix_recode(drow + (size_t)(n + t) * kFixRowBytes, ch, wbits);
+    }
 }
 
-// One warp per proof, lane = 8-bit window: for every row the warp reads its 32 digits with one 32-byte
-// access and each lane adds digit * 2^(8 lane) * Base from the table (7M, next operand prefetched).
-// 131 perfectly balanced additions per lane, no shared memory, no CTA barrier; 5-level shuffle tree.
+// One (half-)warp per proof, lane = window: for every row the lanes read their digits with one 32-byte
+// access and each adds digit * 2^(wbits lane) * Base from the table (7M, next operand prefetched).
+// 2n+3 perfectly balanced additions per lane, no shared memory, no CTA barrier; shuffle-tree at the end.
+// WBITS = 8: 32 lanes per proof, table in L2.  WBITS = 16: 16 lanes per proof, 96-byte reads from HBM.
 __device__ __forceinline__ void ge_shfl_xor(ge_p3& out, const ge_p3& in, int mask) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -387,21 +411,35 @@ __device__ __forceinline__ void ge_shfl_xor(ge_p3& out, const ge_p3& in, int mas
         out.T.v[j] = __shfl_xor_sync(0xffffffffu, in.T.v[j], mask);
     }
 }
+template <int WBITS>
 __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __restrict__ gens,
                                                               const VScal* __restrict__ vscal,
                                                               const int8_t* __restrict__ digits, uint32_t n,
                                                               uint32_t num, uint8_t* __restrict__ fsum) {
-    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (p >= num || !vscal[p].valid) return;  // whole warp
+    constexpr int LP = 256 / WBITS;  // lanes (= windows) per proof
+    constexpr uint32_t E = 1u << (WBITS - 1);
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) / LP;
+    const int win = threadIdx.x & (LP - 1);
+    const bool live = p < num && vscal[p < num ? p : 0].valid;
+    if (!__any_sync(0xffffffffu, live)) return;  // dead lanes of a live warp idle through the shuffles
     const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
-    const uint8_t* table = gens + gh->table_off + (size_t)lane * kFixEntries * 96;  // this lane's window
-    const int8_t* drow = digits + (size_t)p * kRowsMax * kFixWin + lane;
+    const uint8_t* table = gens + gh->table_off + (size_t)win * E * 96;  // this lane's window
+    const int8_t* drow = digits + (size_t)(live ? p : 0) * kRowsMax * kFixRowBytes;
     const int nrows2 = 2 * (int)n + 1, nrows = nrows2 + 2;
     // sequence: the two identity-1 rows (g, h) first, then the 2n+1 identity-2 rows — one accumulator live
     auto row_of = [&](int sidx) { return sidx < 2 ? nrows2 + sidx : sidx - 2; };
     auto base_of = [&](int row) {
         return row < 2 * (int)n ? (uint32_t)row : row == 2 * (int)n ? 2 * n + 1 : 2 * n + (uint32_t)(row - nrows2);
+    };
+    auto digit_of = [&](int row, uint32_t& mag, bool& neg) {
+        if (!live) {
+            mag = 0;
+            neg = false;
+        } else if (WBITS == 8) {
+            fixed_digit(drow[(size_t)row * kFixRowBytes + win], mag, neg);
+        } else {
+            fixed_digit16(reinterpret_cast<const int16_t*>(drow + (size_t)row * kFixRowBytes)[win], mag, neg);
+        }
     };
     ge_p3 acc;
     ge_p3_0(acc);
@@ -410,8 +448,8 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
     ge_niels q;
     {
         int r0 = row_of(0);
-        fixed_digit(drow[(size_t)r0 * kFixWin], mag, neg);
-        if (mag) ge_niels_load(q, table + ((size_t)base_of(r0) * kFixWin * kFixEntries + (mag - 1)) * 96);
+        digit_of(r0, mag, neg);
+        if (mag) ge_niels_load(q, table + ((size_t)base_of(r0) * LP * E + (mag - 1)) * 96);
     }
 #pragma unroll 1
     for (int sidx = 0; sidx < nrows; sidx++) {
@@ -420,18 +458,18 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
         ge_niels cur = q;
         if (sidx + 1 < nrows) {  // prefetch the next operand while this addition runs
             int nr = row_of(sidx + 1);
-            fixed_digit(drow[(size_t)nr * kFixWin], mag, neg);
-            if (mag) ge_niels_load(q, table + ((size_t)base_of(nr) * kFixWin * kFixEntries + (mag - 1)) * 96);
+            digit_of(nr, mag, neg);
+            if (mag) ge_niels_load(q, table + ((size_t)base_of(nr) * LP * E + (mag - 1)) * 96);
         }
         if (cmag) ge_madd(acc, acc, cur, cneg);
-        if (sidx == 1 || sidx == nrows - 1) {  // end of an identity: butterfly sum over the 32 windows
+        if (sidx == 1 || sidx == nrows - 1) {  // end of an identity: butterfly sum over the windows
 #pragma unroll 1
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = LP / 2; o > 0; o >>= 1) {
                 ge_p3 other;
                 ge_shfl_xor(other, acc, o);
                 ge_add(acc, acc, other);
             }
-            if (lane == 0) ge_store(fsum + ((size_t)p * 2 + (sidx == 1 ? 0 : 1)) * 128, acc);
+            if (live && win == 0) ge_store(fsum + ((size_t)p * 2 + (sidx == 1 ? 0 : 1)) * 128, acc);
             ge_p3_0(acc);
         }
     }
@@ -550,40 +588,67 @@ size_t bpk_proof_record_bytes(size_t n) {
     while (((size_t)1 << k) < n) k++;
     return proof_record_bytes(k);
 }
-int bpk_gens_workspace_bytes(size_t n, size_t* bytes) {
-    if (!bytes || n == 0 || n > kMaxN || (n & (n - 1))) return fail(BPK_ERR_ARG);
-    size_t nb = 2 * n + 2;
-    size_t table = nb * kFixWin * kFixEntries * 96;
-    size_t scratch = nb * kFixWin * kFixEntries * 32 + nb * kFixWin * 128;
+static bool wbits_ok(int wbits) { return wbits == 8 || wbits == 16; }
+int bpk_gens_workspace_bytes_ex(size_t n, int window_bits, size_t* bytes) {
+    if (!bytes || n == 0 || n > kMaxN || (n & (n - 1)) || !wbits_ok(window_bits)) return fail(BPK_ERR_ARG);
+    size_t nb = 2 * n + 2, nwin = (size_t)fix_nwin(window_bits);
+    size_t table = nb * nwin * fix_entries(window_bits) * 96;
+    size_t scratch = nb * nwin * 128;
     *bytes = 256 + align256(table) + align256(scratch) + align256(nb * 128);
     return BPK_OK;
 }
-int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
-                         const void* d_h, size_t n, void* stream) {
+int bpk_gens_workspace_bytes(size_t n, size_t* bytes) { return bpk_gens_workspace_bytes_ex(n, 8, bytes); }
+
+// window width of every table built by this process, by device address (the verifier sizes its launch
+// from it without reading the device-side header back)
+static std::mutex g_gens_mu;
+static std::unordered_map<const void*, int> g_gens_wbits;
+static int gens_wbits_of(const void* d_gens_ws) {
+    std::lock_guard<std::mutex> lk(g_gens_mu);
+    auto it = g_gens_wbits.find(d_gens_ws);
+    return it == g_gens_wbits.end() ? 0 : it->second;
+}
+
+int bpk_gens_init_device_ex(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
+                            const void* d_h, size_t n, int window_bits, void* stream) {
     size_t need = 0;
-    if (bpk_gens_workspace_bytes(n, &need) != BPK_OK) return BPK_ERR_ARG;
+    if (bpk_gens_workspace_bytes_ex(n, window_bits, &need) != BPK_OK) return BPK_ERR_ARG;
     if (!d_gens_ws || !d_G || !d_H || !d_g || !d_h) return fail(BPK_ERR_ARG);
     if (ws_bytes < need) return fail(BPK_ERR_WORKSPACE);
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t nb = (uint32_t)(2 * n + 2);
+    const int nwin = fix_nwin(window_bits);
+    const uint32_t entries = fix_entries(window_bits);
     GensHeader hd;
     memset(&hd, 0, sizeof hd);
     hd.magic = kGensMagic;
     hd.n = (uint32_t)n;
     hd.nbases = nb;
+    hd.wbits = (uint32_t)window_bits;
+    hd.nwin = (uint32_t)nwin;
+    hd.entries = entries;
     hd.table_off = 256;
-    hd.scratch_off = hd.table_off + align256((size_t)nb * kFixWin * kFixEntries * 96);
-    hd.bases_off = hd.scratch_off + align256((size_t)nb * kFixWin * kFixEntries * 32 + (size_t)nb * kFixWin * 128);
+    hd.scratch_off = hd.table_off + align256((size_t)nb * nwin * entries * 96);
+    hd.bases_off = hd.scratch_off + align256((size_t)nb * nwin * 128);
     uint8_t* ws = (uint8_t*)d_gens_ws;
     CBP_CUDA(cudaMemcpyAsync(ws, &hd, sizeof hd, cudaMemcpyHostToDevice, st));
-    uint8_t* prefix = ws + hd.scratch_off;
-    uint8_t* pow = prefix + (size_t)nb * kFixWin * kFixEntries * 32;
+    uint8_t* pow = ws + hd.scratch_off;
     gens_pow_kernel<<<(nb + 63) / 64, 64, 0, st>>>((const uint8_t*)d_G, (const uint8_t*)d_H, (const uint8_t*)d_g,
-                                                  (const uint8_t*)d_h, (uint32_t)n, pow, ws + hd.bases_off);
+                                                  (const uint8_t*)d_h, (uint32_t)n, window_bits, pow,
+                                                  ws + hd.bases_off);
     CBP_CHECK_LAUNCH();
-    gens_table_kernel<<<(nb * kFixWin + 63) / 64, 64, 0, st>>>(pow, nb, ws + hd.table_off, prefix);
+    size_t threads = (size_t)nb * nwin * (entries / kTabRun);
+    gens_table_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(pow, nb, nwin, entries, ws + hd.table_off);
     CBP_CHECK_LAUNCH();
+    {
+        std::lock_guard<std::mutex> lk(g_gens_mu);
+        g_gens_wbits[d_gens_ws] = window_bits;
+    }
     return BPK_OK;
+}
+int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
+                         const void* d_h, size_t n, void* stream) {
+    return bpk_gens_init_device_ex(d_gens_ws, ws_bytes, d_G, d_H, d_g, d_h, n, 8, stream);
 }
 
 struct VerifyLayout {
@@ -601,7 +666,7 @@ static VerifyLayout verify_layout(size_t chunk) {
     L.fsum = take(chunk * 2 * 128);
     L.winsum = take(chunk * 2 * 64 * 128);
     L.flags = take(chunk * 2);
-    L.digits = take(chunk * kRowsMax * kFixWin);
+    L.digits = take(chunk * kRowsMax * kFixRowBytes);
     L.vdigits = take(chunk * kVarMax * 64);
     L.vtab = take(chunk * kVarMax * 8 * 128);
     L.total = off;
@@ -622,6 +687,8 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     if (!num_proofs) return BPK_OK;
     if (!d_gens_ws || !d_proofs || !d_accept || !d_workspace) return fail(BPK_ERR_ARG);
     if (workspace_bytes < need) return fail(BPK_ERR_WORKSPACE);
+    const int wbits = gens_wbits_of(d_gens_ws);
+    if (!wbits) return fail(BPK_ERR_ARG);  // not a table built by bpk_gens_init_device[_ex]
     int k = 0;
     while (((size_t)1 << k) < n) k++;
     size_t rec = proof_record_bytes(k);
@@ -640,11 +707,16 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         const uint8_t* ve = d_V ? (const uint8_t*)d_V + done * 128 : nullptr;
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
-        verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>(vscal, (uint32_t)n, k, digits, vdigits);
+        verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits,
+                                                           vdigits);
         CBP_CHECK_LAUNCH();
         prof_begin(BPK_PROF_VERIFY_MSM, st);
-        verify_fixed_kernel<<<(cnt * 32 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits, (uint32_t)n,
-                                                                    cnt, fsum);
+        if (wbits == 8)
+            verify_fixed_kernel<8><<<(cnt * 32 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
+                                                                           (uint32_t)n, cnt, fsum);
+        else
+            verify_fixed_kernel<16><<<(cnt * 16 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
+                                                                            (uint32_t)n, cnt, fsum);
         prof_end(BPK_PROF_VERIFY_MSM, st);
         CBP_CHECK_LAUNCH();
         verify_vtab_kernel<<<(cnt * nvar * 8 + 127) / 128, 128, 0, st>>>(pr, rec, k, vscal, cnt, vtab);

@@ -181,11 +181,14 @@ def proof_record_bytes(n):
 
 class Generators:
     """Device-resident generator set (G[n], H[n], g, h) with its fixed-base tables.
-    G, H: (n, 16) uint64 numpy arrays or (n,128) uint8 cuda tensors; g, h: (16,) / (128,)."""
+    G, H: (n, 16) uint64 numpy arrays or (n,128) uint8 cuda tensors; g, h: (16,) / (128,).
+    window_bits: 8 (51 MB of tables at n = 64, L2-resident) or 16 (6.5 GB, HBM-resident, half the point
+    additions per fixed-base scalar multiplication); results do not depend on it."""
 
-    def __init__(self, G, H, g, h, device="cuda", stream=None):
+    def __init__(self, G, H, g, h, device="cuda", stream=None, window_bits=8):
         import torch
         self.device = torch.device(device)
+        self.window_bits = int(window_bits)
 
         def dev(a):
             if isinstance(a, np.ndarray):
@@ -196,11 +199,13 @@ class Generators:
         self.n = dG.numel() // 128
         assert dH.numel() == self.n * 128 and dg.numel() == 128 and dh.numel() == 128
         nbytes = C.c_size_t(0)
-        _check(_lib().bpk_gens_workspace_bytes(self.n, C.byref(nbytes)), "bpk_gens_workspace_bytes")
+        _check(_lib().bpk_gens_workspace_bytes_ex(self.n, self.window_bits, C.byref(nbytes)),
+               "bpk_gens_workspace_bytes_ex")
         self.workspace = _dev_u8(nbytes.value, self.device)
-        _check(_lib().bpk_gens_init_device(self.workspace.data_ptr(), self.workspace.numel(), dG.data_ptr(),
-                                           dH.data_ptr(), dg.data_ptr(), dh.data_ptr(), self.n, _stream_ptr(stream)),
-               "bpk_gens_init_device")
+        _check(_lib().bpk_gens_init_device_ex(self.workspace.data_ptr(), self.workspace.numel(), dG.data_ptr(),
+                                              dH.data_ptr(), dg.data_ptr(), dh.data_ptr(), self.n, self.window_bits,
+                                              _stream_ptr(stream)),
+               "bpk_gens_init_device_ex")
         torch.cuda.current_stream().synchronize()  # inputs may be temporaries
         self.record_bytes = proof_record_bytes(self.n)
 

@@ -88,10 +88,18 @@ int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, co
 /* Flat proof record, uint64 words (n-bit proof, k = log2 n):
  *   V,A,S,T1,T2 (5 x 128 B) | taux,mu,t (3 x 32 B) | a,b,c,x (4 x 32 B) | L[0..k) (k x 128 B) | R[0..k) (k x 128 B) */
 size_t bpk_proof_record_bytes(size_t n);
-/* generator set shared by every proof: G[n], H[n], g, h (ge25519, AoS).  Builds device tables. */
+/* generator set shared by every proof: G[n], H[n], g, h (ge25519, AoS).  Builds device tables of the
+ * signed multiples d * 2^(w j) * Base for every window j, so that a fixed-base scalar multiplication is
+ * 256/w table additions and no doublings.  window_bits w = 8: 32 windows x 128 multiples (51 MB at n = 64,
+ * L2-resident; cheap to build — what the plain entry points use).  w = 16: 16 windows x 32768 multiples
+ * (6.5 GB at n = 64, HBM-resident): half the additions per proof, for long-lived batch verifiers/provers.
+ * Proof bytes and accept decisions do not depend on w. */
 int bpk_gens_workspace_bytes(size_t n, size_t* bytes);
 int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
                          const void* d_h, size_t n, void* stream);
+int bpk_gens_workspace_bytes_ex(size_t n, int window_bits, size_t* bytes);
+int bpk_gens_init_device_ex(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
+                            const void* d_h, size_t n, int window_bits, void* stream);
 /* d_accept[i] = 1 iff proof i verifies (exact checks, bit-exact with the CPU oracle's range_proof_verify).
  * d_V (optional, num_proofs ge25519): the caller's commitments, each must equal its proof's V
  * (bulletproof_range_proof.cu:1729-1740); NULL skips that check. */

@@ -27,20 +27,28 @@ def gens64(oracle):
     return Gens(oracle, 64)
 
 
-def dev_gens(g):
+_DEV_GENS = {}
+
+
+def dev_gens(g, window_bits=8):
+    """device generator tables, built once per (n, window width): the 16-bit tables are 6.5 GB at n = 64"""
     import cudabulletproof_b200 as cbp
-    return cbp.Generators(g.G, g.H, g.g, g.h)
+    key = (len(g.G), window_bits)
+    if key not in _DEV_GENS:
+        _DEV_GENS[key] = cbp.Generators(g.G, g.H, g.g, g.h, window_bits=window_bits)
+    return _DEV_GENS[key]
 
 
 def gamma_for(seed):
     return (0x1234567 + seed * 7919) % (2**252)
 
 
+@pytest.mark.parametrize("window_bits", [8, 16])
 @pytest.mark.parametrize("n", [16, 64])
-def test_gpu_prover_is_byte_identical_to_oracle(oracle, gens16, gens64, n):
+def test_gpu_prover_is_byte_identical_to_oracle(oracle, gens16, gens64, n, window_bits):
     import cudabulletproof_b200 as cbp
     g = gens16 if n == 16 else gens64
-    dg = dev_gens(g)
+    dg = dev_gens(g, window_bits)
     cases = [(42, 1), (0, 2), (2**n - 1, 3), (0xBEEF & (2**n - 1), 4)]
     vals = [v for v, _ in cases]
     seeds = [s for _, s in cases]
@@ -75,12 +83,13 @@ def tamper_cases(rec_bytes, k, rng):
     return offs
 
 
+@pytest.mark.parametrize("window_bits", [8, 16])
 @pytest.mark.parametrize("n", [16, 64])
-def test_batch_verify_matches_oracle_honest_and_tampered(oracle, gens16, gens64, n):
+def test_batch_verify_matches_oracle_honest_and_tampered(oracle, gens16, gens64, n, window_bits):
     import torch
     import cudabulletproof_b200 as cbp
     g = gens16 if n == 16 else gens64
-    dg = dev_gens(g)
+    dg = dev_gens(g, window_bits)
     k = n.bit_length() - 1
     rng = random.Random(n)
     recs, expect, structs = [], [], []
@@ -212,7 +221,7 @@ def test_batch_verify_larger_batch_with_one_percent_tampered(oracle, gens64):
     oracle's on a sample and all honest proofs must accept."""
     import torch
     import cudabulletproof_b200 as cbp
-    dg = dev_gens(gens64)
+    dg = dev_gens(gens64, 16)
     m = 256
     rng = random.Random(5)
     vals = [rng.getrandbits(64) for _ in range(m)]
