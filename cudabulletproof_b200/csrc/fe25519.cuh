@@ -432,6 +432,7 @@ __device__ __forceinline__ bool fe_equal(const fe& a, const fe& b) {
 
 __device__ __forceinline__ void fe_sqn(fe& r, const fe& a, int n) {
     fe_sq(r, a);
+#pragma unroll 1  // a dependent chain: unrolling only bloats the code (an inversion was 300 KB of SASS)
     for (int i = 1; i < n; i++) fe_sq(r, r);
 }
 // z^(2^250-1), z^11: shared prefix of inversion and square-root chains

@@ -141,6 +141,9 @@ __device__ __forceinline__ void sc_load_reduce(sc& r, const void* p) {
     sc_reduce(r, t);
 }
 
+// out-of-line scalar multiplication for the transcript kernel: ~45 call sites of 9 KB each otherwise
+static __device__ __noinline__ void sc_mul_nf(sc& r, const sc& a, const sc& b) { sc_mul(r, a, b); }
+
 __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes,
                                                                const uint8_t* __restrict__ Vext, uint32_t n, int k,
                                                                uint32_t num, VScal* __restrict__ out) {
@@ -149,13 +152,22 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
     const uint8_t* rec = proofs + (size_t)p * rec_bytes;
     VScal& vs = out[p];
     bool valid = true;
-    fe px[5], py[5];
+    // every point of the record through ONE loop body (on-curve check, affine coordinates for hashing):
+    // q = 0..4: V, A, S, T1, T2; then L_0..L_(k-1), R_0..R_(k-1)
+    uint32_t ax[5 + 2 * kMaxK][8], ay[5 + 2 * kMaxK][8];
     ge_p3 V;
-    for (int q = 0; q < 5; q++) {
+#pragma unroll 1
+    for (int q = 0; q < 5 + 2 * k; q++) {
         ge_p3 P;
-        ge_load(P, rec + q * 128);
+        ge_load(P, rec + (q < 5 ? q * 128 : kRecL + (q - 5) * 128));
         valid = valid && ge_is_on_curve(P);
-        affine_xy(px[q], py[q], P);
+        fe x, y;
+        affine_xy(x, y, P);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ax[q][i] = x.v[i];
+            ay[q][i] = y.v[i];
+        }
         if (q == 0) V = P;
     }
     if (Vext) {  // bulletproof_range_proof.cu:1729-1740: the caller's V must be the proof's V
@@ -168,16 +180,15 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
         fe_mul(d, V.Y, E.Z);
         valid = valid && ge_is_on_curve(E) && fe_equal(a, b) && fe_equal(c, d);
     }
-    uint32_t w[8], yb[8], zb[8], xb[8];
+    uint32_t yb[8], zb[8], xb[8];
     Sha256 sh;
     // y: bulletproof_challenge.cu:24-44
     sh.init();
     sh.update_str("BulletproofYChal", 16);
+#pragma unroll 1
     for (int q = 0; q < 3; q++) {
-        words_of(w, px[q]);
-        sh.update_words(w);
-        words_of(w, py[q]);
-        sh.update_words(w);
+        sh.update_words(ax[q]);
+        sh.update_words(ay[q]);
     }
     sh.update_str("y_ch", 4);
     sh.final_challenge(yb);
@@ -190,11 +201,10 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
     // x: :61-77 (only 4 bytes of "xchal" are hashed)
     sh.init();
     sh.update_str("BulletproofXChal", 16);
+#pragma unroll 1
     for (int q = 3; q < 5; q++) {
-        words_of(w, px[q]);
-        sh.update_words(w);
-        words_of(w, py[q]);
-        sh.update_words(w);
+        sh.update_words(ax[q]);
+        sh.update_words(ay[q]);
     }
     sh.update_str("xcha", 4);
     sh.final_challenge(xb);
@@ -223,21 +233,13 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
     sh.update_words(mu.v);
     sh.final_challenge(tr);
     sc u[kMaxK];
+#pragma unroll 1
     for (int j = 0; j < k; j++) {
-        ge_p3 Lp, Rp;
-        ge_load(Lp, rec + kRecL + (size_t)j * 128);
-        ge_load(Rp, rec + kRecL + (size_t)(k + j) * 128);
-        valid = valid && ge_is_on_curve(Lp) && ge_is_on_curve(Rp);
-        fe lx, ly, rx, ry;
-        affine_xy(lx, ly, Lp);
-        affine_xy(rx, ry, Rp);
         sh.init();
         sh.update_str("InnerProductChal", 16);
         sh.update_words(tr);
-        words_of(w, lx);
-        sh.update_words(w);
-        words_of(w, rx);
-        sh.update_words(w);
+        sh.update_words(ax[5 + j]);      // L_j.x
+        sh.update_words(ax[5 + k + j]);  // R_j.x
         sh.final_challenge(tr);
         if (j == 0) {  // stored first-round challenge must be the recomputed one (D15)
             fe xs;
@@ -254,63 +256,67 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
     sc pre[kMaxK + 1], run, inv;
     sc_set1(run);
     pre[0] = run;
-    sc_mul(run, run, y);
+    sc_mul_nf(run, run, y);
     for (int j = 0; j < k; j++) {
         pre[j + 1] = run;
-        sc_mul(run, run, u[j]);
+        sc_mul_nf(run, run, u[j]);
     }
     sc_invert(inv, run);
     sc uinv[kMaxK], yinv;
     for (int j = k - 1; j >= 0; j--) {
-        sc_mul(uinv[j], inv, pre[j + 1]);
-        sc_mul(inv, inv, u[j]);
+        sc_mul_nf(uinv[j], inv, pre[j + 1]);
+        sc_mul_nf(inv, inv, u[j]);
     }
     yinv = inv;  // pre[0] = 1
 
     vs.z = z;
-    sc_mul(vs.z2, z, z);
+    sc_mul_nf(vs.z2, z, z);
     vs.x = x;
-    sc_mul(vs.x2, x, x);
+    sc_mul_nf(vs.x2, x, x);
     vs.a = a;
     vs.b = b;
     // delta = (z - z^2) sum y^i - z^3 (2^n - 1): bulletproof_range_proof.cu:315-374
     sc sum_y, cur, zmz2, z3, two_n, delta, tmp;
+    // sum_{i < 2^k} y^i = prod_{m < k} (1 + y^(2^m))
     sc_set1(sum_y);
-    sc_set1(cur);
-    for (uint32_t i = 1; i < n; i++) {
-        sc_mul(cur, cur, y);
-        sc_add(sum_y, sum_y, cur);
+    cur = y;
+#pragma unroll 1
+    for (int m = 0; m < k; m++) {
+        sc_set1(tmp);
+        sc_add(tmp, tmp, cur);
+        sc_mul_nf(sum_y, sum_y, tmp);
+        sc_mul_nf(cur, cur, cur);
     }
     sc_sub(zmz2, z, vs.z2);
-    sc_mul(z3, vs.z2, z);
+    sc_mul_nf(z3, vs.z2, z);
     sc_set0(two_n);
     two_n.v[n >> 5] = 1u << (n & 31);  // n <= 64 < 252
     sc one;
     sc_set1(one);
     sc_sub(two_n, two_n, one);
-    sc_mul(delta, zmz2, sum_y);
-    sc_mul(tmp, z3, two_n);
+    sc_mul_nf(delta, zmz2, sum_y);
+    sc_mul_nf(tmp, z3, two_n);
     sc_sub(delta, delta, tmp);
     sc_sub(vs.g1, t, delta);
     vs.h1 = taux;
-    sc_mul(tmp, a, b);
+    sc_mul_nf(tmp, a, b);
     sc_sub(tmp, tmp, t);
     sc_add(vs.h2, tmp, mu);
     sc s0;
     sc_set1(s0);
     for (int j = 0; j < k; j++) {
-        sc_mul(s0, s0, uinv[j]);
-        sc_mul(vs.usq[j], u[j], u[j]);
-        sc_mul(vs.uinvsq[j], uinv[j], uinv[j]);
+        sc_mul_nf(s0, s0, uinv[j]);
+        sc_mul_nf(vs.usq[j], u[j], u[j]);
+        sc_mul_nf(vs.uinvsq[j], uinv[j], uinv[j]);
     }
     vs.s0 = s0;
     vs.ypow[0] = yinv;
-    for (int m = 1; m <= k; m++) sc_mul(vs.ypow[m], vs.ypow[m - 1], vs.ypow[m - 1]);
+    for (int m = 1; m <= k; m++) sc_mul_nf(vs.ypow[m], vs.ypow[m - 1], vs.ypow[m - 1]);
     vs.valid = valid ? 1u : 0u;
 #ifdef CBP_DEBUG_VSCAL
     if (k <= 4) {
         vs.ypow[5] = sum_y; vs.ypow[6] = delta; vs.usq[4] = zmz2; vs.usq[5] = z3; vs.uinvsq[4] = two_n;
-        sc dbg; sc_mul(dbg, uinv[0], uinv[1]); vs.uinvsq[5] = dbg;
+        sc dbg; sc_mul_nf(dbg, uinv[0], uinv[1]); vs.uinvsq[5] = dbg;
     }
 #endif
 }
@@ -411,6 +417,7 @@ __device__ __forceinline__ void ge_shfl_xor(ge_p3& out, const ge_p3& in, int mas
         out.T.v[j] = __shfl_xor_sync(0xffffffffu, in.T.v[j], mask);
     }
 }
+static constexpr int kFixAhead = 4;  // rows of L2 prefetch distance (16-bit tables)
 template <int WBITS>
 __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __restrict__ gens,
                                                               const VScal* __restrict__ vscal,
@@ -460,6 +467,17 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
             int nr = row_of(sidx + 1);
             digit_of(nr, mag, neg);
             if (mag) ge_niels_load(q, table + ((size_t)base_of(nr) * LP * E + (mag - 1)) * 96);
+        }
+        if (WBITS == 16 && sidx + kFixAhead < nrows) {  // HBM-resident table: pull a later entry into L2 now
+            int fr = row_of(sidx + kFixAhead);
+            uint32_t fmag;
+            bool fneg;
+            digit_of(fr, fmag, fneg);
+            if (fmag) {
+                const uint8_t* e = table + ((size_t)base_of(fr) * LP * E + (fmag - 1)) * 96;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(e + 64));
+            }
         }
         if (cmag) ge_madd(acc, acc, cur, cneg);
         if (sidx == 1 || sidx == nrows - 1) {  // end of an identity: butterfly sum over the windows
@@ -551,11 +569,10 @@ __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restri
     ge_p3 acc;
     ge_p3_0(acc);
     const uint8_t* ws = winsum + (size_t)id * 64 * 128;
+#pragma unroll 1
     for (int w = 63; w >= 0; w--) {
-        ge_dbl(acc, acc);
-        ge_dbl(acc, acc);
-        ge_dbl(acc, acc);
-        ge_dbl(acc, acc);
+#pragma unroll 1  // keep the loop body small: this kernel is latency-bound and was stalling on instruction fetch
+        for (int d = 0; d < 4; d++) ge_dbl(acc, acc);
         ge_p3 x;
         ge_load(x, ws + (size_t)w * 128);
         ge_add(acc, acc, x);

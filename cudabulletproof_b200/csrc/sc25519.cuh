@@ -191,6 +191,7 @@ __device__ __noinline__ static void sc_invert(sc& r, const sc& a) {
     const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0, 0, 0, 0x10000000u};
     sc acc;
     sc_set1(acc);
+#pragma unroll 1
     for (int bit = 252; bit >= 0; bit--) {
         sc_sq(acc, acc);
         if ((e[bit >> 5] >> (bit & 31)) & 1) sc_mul(acc, acc, a);
