@@ -388,7 +388,10 @@ def run_cuda(args):
         per_launch = imad_kernel * (m / chunks)
         roofline = {"bound": "int", "kernel": "verify_fixed_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": per_launch / (k_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
-                    "traffic": None, "launch_ms": k_ms, "launches_timed": k_n,
+                    "traffic": 6.26e9 if (args.fixed_window_bits == 16 and m == 16384) else None,
+                    "traffic_note": "dram__bytes_read.sum of one 16384-proof launch, profiles/r01_verify16_ncu_raw.csv; "
+                                    "algorithmic table bytes 3.3e9 (96 B per addition, fetched as two 64 B DRAM atoms)",
+                    "launch_ms": k_ms, "launches_timed": k_n,
                     "algorithmic_imad_per_launch": per_launch, "algorithmic_imad_per_proof_total": imad_proof,
                     "whole_batch_frac": imad_proof * m / (ms / vsteps * 1e-3) / 1e12 / INT_PEAK_TIMAD}
         # e2e: proof records in pinned host memory -> device -> accept mask back on the host

@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8
         const int half = 1 << m;
         if (t >= half && t < 2 * half) {
             sc a = s_sh[t - half], b = y_sh[t - half];
-            sc_mul(a, a, vs.usq[k - 1 - m]);
-            sc_mul(b, b, vs.ypow[m]);
+            sc_mul_nf(a, a, vs.usq[k - 1 - m]);
+            sc_mul_nf(b, b, vs.ypow[m]);
             s_sh[t] = a;
             y_sh[t] = b;
         }
@@ -390,14 +390,14 @@ __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8
     }
     if (t < (int)n) {
         sc cg, ch, tmp, two_i;
-        sc_mul(cg, vs.a, s_sh[t]);
+        sc_mul_nf(cg, vs.a, s_sh[t]);
         sc_add(cg, cg, vs.z);
         sc_set0(two_i);
         two_i.v[t >> 5] = 1u << (t & 31);
-        sc_mul(tmp, vs.z2, two_i);
-        sc_mul(ch, vs.b, s_sh[n - 1 - t]);  // s_(n-1-t) = s_t^-1: the bits complemented
+        sc_mul_nf(tmp, vs.z2, two_i);
+        sc_mul_nf(ch, vs.b, s_sh[n - 1 - t]);  // s_(n-1-t) = s_t^-1: the bits complemented
         sc_sub(ch, ch, tmp);
-        sc_mul(ch, ch, y_sh[t]);
+        sc_mul_nf(ch, ch, y_sh[t]);
         sc_sub(ch, ch, vs.z);
         fix_recode(drow + (size_t)t * kFixRowBytes, cg, wbits);
         fix_recode(drow + (size_t)(n + t) * kFixRowBytes, ch, wbits);
@@ -496,8 +496,7 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
 // multiples m = 1..8 of per-proof point q, as cached points; threads are grouped by m so that the
 // double-and-add pattern is uniform within a warp
 __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, int k,
-                                                          const VScal* __restrict__ vscal, uint32_t num,
-                                                          uint8_t* __restrict__ vtab) {
+                                                          uint32_t num, uint8_t* __restrict__ vtab) {
     const int nvar = 2 + 2 * k + 3;
     uint32_t per_m = num * (uint32_t)nvar;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,7 +504,8 @@ __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restr
     int mlt = (int)(id / per_m) + 1;
     uint32_t rem = id % per_m, p = rem / (uint32_t)nvar;
     int q = (int)(rem % (uint32_t)nvar);
-    if (!vscal[p].valid) return;
+    // no dependency on the transcript (runs concurrently with it): records that later turn out invalid
+    // just produce unused table entries
     ge_p3 P, acc;
     ge_load(P, proofs + (size_t)p * rec_bytes + var_point_offset(q, k));
     acc = P;
@@ -696,6 +696,26 @@ int bpk_range_verify_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes)
     *bytes = verify_layout(chunk).total;
     return BPK_OK;
 }
+// one side stream per device for the work that does not depend on the transcript
+struct VerifySide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool ok = false;
+};
+static VerifySide g_vside[16];
+static VerifySide* verify_side() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    VerifySide& v = g_vside[dev];
+    if (!v.ok) {
+        if (cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&v.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&v.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        v.ok = true;
+    }
+    return &v;
+}
+
 int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, const void* d_V, size_t n,
                                   size_t num_proofs, uint8_t* d_accept, void* d_workspace, size_t workspace_bytes,
                                   void* stream) {
@@ -717,13 +737,23 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     int8_t *digits = (int8_t*)(ws + L.digits), *vdigits = (int8_t*)(ws + L.vdigits);
     const int nvar = 2 + 2 * k + 3;
     cudaStream_t st = (cudaStream_t)stream;
+    VerifySide* side = verify_side();
+    if (!side) return fail(BPK_ERR_CUDA);
     prof_begin(BPK_PROF_VERIFY_TOTAL, st);
     for (size_t done = 0; done < num_proofs; done += chunk) {
         uint32_t cnt = (uint32_t)((num_proofs - done) < chunk ? (num_proofs - done) : chunk);
         const uint8_t* pr = (const uint8_t*)d_proofs + done * rec;
         const uint8_t* ve = d_V ? (const uint8_t*)d_V + done * 128 : nullptr;
+        // side stream: the per-proof point tables need only the records, so they are built while the
+        // latency-bound transcript / coefficient kernels run
+        cudaStream_t ss = side->stream;
+        CBP_CUDA(cudaEventRecord(side->ev_fork, st));
+        CBP_CUDA(cudaStreamWaitEvent(ss, side->ev_fork, 0));
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
+        verify_vtab_kernel<<<(cnt * nvar * 8 + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab);
+        CBP_CHECK_LAUNCH();
+        CBP_CUDA(cudaEventRecord(side->ev_join, ss));
         verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits,
                                                            vdigits);
         CBP_CHECK_LAUNCH();
@@ -736,8 +766,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
                                                                             (uint32_t)n, cnt, fsum);
         prof_end(BPK_PROF_VERIFY_MSM, st);
         CBP_CHECK_LAUNCH();
-        verify_vtab_kernel<<<(cnt * nvar * 8 + 127) / 128, 128, 0, st>>>(pr, rec, k, vscal, cnt, vtab);
-        CBP_CHECK_LAUNCH();
+        CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
         verify_winsum_kernel<<<(cnt * 128 + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, cnt, winsum);
         CBP_CHECK_LAUNCH();
         verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
