@@ -1,7 +1,9 @@
 // capi_msm.cu — C ABI for the MSM path: device-resident bpk_msm_device and the host-pointer
 // drop-ins cuda_point_vector_multi_scalar_mul{,_shared} (reference cuda_bulletproof_kernels.cu:62-207).
 #include <stdio.h>
+#include <stdlib.h>
 #include <mutex>
+#include <vector>
 #include "../../include/cuda_bulletproof.h"
 #include "common.h"
 #include "ge25519.cuh"
@@ -141,15 +143,25 @@ int bpk_synth_scalars_device(void* d_scalars, size_t n, uint64_t seed, int bits,
 // ---- host-pointer drop-ins --------------------------------------------------------------------
 // The reference wrapper mallocs, copies, synchronises and frees on every call
 // (cuda_bulletproof_kernels.cu:77-115).  Here the device buffers are a grow-only cache (one per
-// process, guarded by a mutex), the scalars are uploaded first so that digit recoding / sorting
-// overlaps the (4x larger) point upload on a second stream, and there is one synchronisation.
+// process, guarded by a mutex) and there is one synchronisation.  The upload (160 B per point over PCIe)
+// costs more than the whole MSM, so inputs of 2^20 points and more are cut into chunks of kHostChunk
+// points: one stream copies chunk after chunk while up to kMsmKits earlier chunks are being multiplied,
+// each as an independent MSM with its own workspace and side streams.  The partial results are summed
+// and normalised by one last kernel.
 namespace {
+// measured on B200 at n = 2^20 (tools/probe_e2e.py): chunks of 2^17 / 2^18 / 2^19 / one piece = 7.3 / 5.8 / 4.6 / 5.3 ms
+// (a mid-size MSM is latency-bound, ~1.4 ms; uploading 2^19 points takes 1.5 ms)
+constexpr size_t kHostChunk = (size_t)1 << 19;
+constexpr size_t kHostChunkMin = (size_t)1 << 20;  // below this a single MSM (scalars first) is faster
+constexpr int kMaxChunks = 4096;
 struct HostPath {
     std::mutex mu;
-    uint8_t *d_s = nullptr, *d_p = nullptr, *d_ws = nullptr, *d_r = nullptr;
-    size_t cap_s = 0, cap_p = 0, cap_ws = 0;
-    cudaStream_t main = nullptr, copy = nullptr;
-    cudaEvent_t ev_points = nullptr;
+    uint8_t *d_s = nullptr, *d_p = nullptr, *d_r = nullptr, *d_partial = nullptr;
+    uint8_t* d_ws[kMsmKits] = {};
+    size_t cap_s = 0, cap_p = 0, cap_partial = 0, cap_ws[kMsmKits] = {};
+    cudaStream_t main = nullptr, copy = nullptr, lane[kMsmKits] = {};
+    cudaEvent_t ev_points = nullptr, ev_lane[kMsmKits] = {};
+    std::vector<cudaEvent_t> ev_chunk;
     bool ok = false;
 };
 HostPath g_hp;
@@ -166,8 +178,6 @@ cudaError_t grow(uint8_t** p, size_t* cap, size_t need) {
 
 static int msm_host(ge25519* result, const FieldVector* scalars, const PointVector* points) {
     size_t n = scalars->length;
-    MsmPlan p;
-    msm_make_plan(&p, n, 0);
     std::lock_guard<std::mutex> lock(g_hp.mu);
     HostPath& hp = g_hp;
     cudaError_t e;
@@ -177,21 +187,84 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
             (e = cudaEventCreateWithFlags(&hp.ev_points, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaMalloc(&hp.d_r, 256)) != cudaSuccess)
             return fail(BPK_ERR_CUDA, e);
+        for (int i = 0; i < kMsmKits; i++)
+            if ((e = cudaStreamCreateWithFlags(&hp.lane[i], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&hp.ev_lane[i], cudaEventDisableTiming)) != cudaSuccess)
+                return fail(BPK_ERR_CUDA, e);
         hp.ok = true;
     }
     if (n) {
-        if ((e = grow(&hp.d_s, &hp.cap_s, n * 32)) != cudaSuccess || (e = grow(&hp.d_p, &hp.cap_p, n * 128)) != cudaSuccess ||
-            (e = grow(&hp.d_ws, &hp.cap_ws, p.workspace_bytes)) != cudaSuccess)
-            return fail(BPK_ERR_CUDA, e);
-        if ((e = cudaMemcpyAsync(hp.d_s, scalars->elements, n * 32, cudaMemcpyHostToDevice, hp.main)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(hp.d_p, points->elements, n * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
-            (e = cudaEventRecord(hp.ev_points, hp.copy)) != cudaSuccess)
+        if ((e = grow(&hp.d_s, &hp.cap_s, n * 32)) != cudaSuccess || (e = grow(&hp.d_p, &hp.cap_p, n * 128)) != cudaSuccess)
             return fail(BPK_ERR_CUDA, e);
     }
     int launches = 0;
-    int rc = msm_run(p, hp.d_s, hp.d_p, hp.d_r, hp.d_ws, 1, hp.main, &launches, n ? hp.ev_points : nullptr);
-    count_launches(launches);
-    if (rc) return fail_cuda(rc);
+    const uint8_t* h_s = (const uint8_t*)scalars->elements;
+    const uint8_t* h_p = (const uint8_t*)points->elements;
+    if (n < kHostChunkMin) {
+        // one MSM; the scalars go first so that digit recoding / sorting overlaps the (4x larger) point upload
+        MsmPlan p;
+        msm_make_plan(&p, n, 0);
+        if (n) {
+            if ((e = grow(&hp.d_ws[0], &hp.cap_ws[0], p.workspace_bytes)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(hp.d_s, h_s, n * 32, cudaMemcpyHostToDevice, hp.main)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(hp.d_p, h_p, n * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
+                (e = cudaEventRecord(hp.ev_points, hp.copy)) != cudaSuccess)
+                return fail(BPK_ERR_CUDA, e);
+        }
+        int rc = msm_run(p, hp.d_s, hp.d_p, hp.d_r, hp.d_ws[0], 1, hp.main, &launches, n ? hp.ev_points : nullptr);
+        count_launches(launches);
+        if (rc) return fail_cuda(rc);
+    } else {
+        size_t chunk = kHostChunk;
+        if (const char* ev = getenv("CBP_HOST_CHUNK_LOG2")) {  // tuning knob
+            int lg = atoi(ev);
+            if (lg >= 15 && lg <= 26) chunk = (size_t)1 << lg;
+        }
+        size_t nchunks = (n + chunk - 1) / chunk;
+        if (nchunks > (size_t)kMaxChunks) {  // keep the event pool bounded for enormous inputs
+            nchunks = kMaxChunks;
+            chunk = (n + nchunks - 1) / nchunks;
+            nchunks = (n + chunk - 1) / chunk;
+        }
+        MsmPlan p_full, p_last;
+        msm_make_plan(&p_full, chunk, 0);
+        const size_t last_n = n - (nchunks - 1) * chunk;
+        msm_make_plan(&p_last, last_n, 0);
+        const size_t ws_need = p_full.workspace_bytes > p_last.workspace_bytes ? p_full.workspace_bytes : p_last.workspace_bytes;
+        for (int i = 0; i < kMsmKits; i++)
+            if ((e = grow(&hp.d_ws[i], &hp.cap_ws[i], ws_need)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+        if ((e = grow(&hp.d_partial, &hp.cap_partial, nchunks * 128)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+        while (hp.ev_chunk.size() < nchunks) {
+            cudaEvent_t ev;
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+            hp.ev_chunk.push_back(ev);
+        }
+        for (size_t c = 0; c < nchunks; c++) {
+            const size_t lo = c * chunk, cnt = c + 1 == nchunks ? last_n : chunk;
+            const int lane = (int)(c % kMsmKits);
+            if ((e = cudaMemcpyAsync(hp.d_s + lo * 32, h_s + lo * 32, cnt * 32, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(hp.d_p + lo * 128, h_p + lo * 128, cnt * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
+                (e = cudaEventRecord(hp.ev_chunk[c], hp.copy)) != cudaSuccess ||
+                (e = cudaStreamWaitEvent(hp.lane[lane], hp.ev_chunk[c], 0)) != cudaSuccess)
+                return fail(BPK_ERR_CUDA, e);
+            int nl = 0;
+            int rc = msm_run(c + 1 == nchunks ? p_last : p_full, hp.d_s + lo * 32, hp.d_p + lo * 128, hp.d_partial + c * 128,
+                             hp.d_ws[lane], 0, hp.lane[lane], &nl, nullptr, lane);
+            launches += nl;
+            if (rc) {
+                count_launches(launches);
+                return fail_cuda(rc);
+            }
+        }
+        for (int i = 0; i < kMsmKits; i++)
+            if ((e = cudaEventRecord(hp.ev_lane[i], hp.lane[i])) != cudaSuccess ||
+                (e = cudaStreamWaitEvent(hp.main, hp.ev_lane[i], 0)) != cudaSuccess)
+                return fail(BPK_ERR_CUDA, e);
+        point_sum_kernel<<<1, 32, 0, hp.main>>>(hp.d_partial, nchunks, 1, hp.d_r);
+        launches++;
+        count_launches(launches);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+    }
     ge25519 tmp;
     e = cudaMemcpyAsync(&tmp, hp.d_r, 128, cudaMemcpyDeviceToHost, hp.main);
     if (e == cudaSuccess) e = cudaStreamSynchronize(hp.main);

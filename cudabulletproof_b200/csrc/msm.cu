@@ -742,11 +742,11 @@ struct StreamKit {
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     bool ok = false;
 };
-StreamKit g_kits[16];
-StreamKit* stream_kit() {
+StreamKit g_kits[16][kMsmKits];
+StreamKit* stream_kit(int idx) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    StreamKit& k = g_kits[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || idx < 0 || idx >= kMsmKits) return nullptr;
+    StreamKit& k = g_kits[dev][idx];
     if (!k.ok) {
         if (cudaStreamCreateWithFlags(&k.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (int i = 0; i < kMaxGroups; i++) {
@@ -804,7 +804,7 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
 
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
-            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready) {
+            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index) {
     uint8_t* ws = (uint8_t*)d_ws;
     uint8_t* table = ws + p.off_table;
     uint32_t* counts = (uint32_t*)(ws + p.off_counts);
@@ -832,7 +832,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
-    StreamKit* kit = n >= (1u << 15) ? stream_kit() : nullptr;
+    StreamKit* kit = n >= (1u << 15) ? stream_kit(kit_index) : nullptr;
     GroupMap gm;
     make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr);
 

@@ -23,8 +23,11 @@ struct MsmPlan {
 int msm_pick_window(size_t n);
 void msm_make_plan(MsmPlan* p, size_t n, int c /* 0 = auto */);
 // points_ready (optional): event after which d_points may be read (lets the caller overlap the point
-// upload with the scalar-only front end: digit recoding, histogram, sort)
+// upload with the scalar-only front end: digit recoding, histogram, sort).
+// kit_index < kMsmKits selects the set of internal side streams: MSMs that are in flight at the same time
+// on one device (the chunked host path) must use different sets and different workspaces.
+constexpr int kMsmKits = 3;
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
-            int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready);
+            int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready, int kit_index = 0);
 
 }  // namespace cbp

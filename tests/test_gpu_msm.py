@@ -156,3 +156,28 @@ def test_msm_adversarial_equal_scalars_large(oracle):
     oracle.ge25519_scalarmult_base(ob.ptr(want), ((k % L) * total % L).to_bytes(32, "little"))
     oracle.ge25519_normalize(ob.ptr(want))
     assert np.array_equal(got, want)
+
+
+def test_msm_host_pointer_chunked_upload(oracle):
+    """The host-pointer drop-in cuts inputs of >= 2^20 points into chunks that are multiplied while later
+    chunks are still being uploaded; the sum of the partial MSMs must be the same group element
+    (checked against one CPU scalar multiplication, ragged last chunk included)."""
+    import cudabulletproof_b200 as cbp
+    n = (1 << 20) + 12345
+    pts, ks = cbp.synth_points(n, seed=0xE2E)
+    sc = cbp.synth_scalars(n, seed=0x5EED, bits=253)
+    h_pts = pts.cpu().numpy().view(np.uint64).reshape(n, 16)
+    h_sc = sc.cpu().numpy().view(np.uint64).reshape(n, 4)
+    got = cbp.cuda_point_vector_multi_scalar_mul(h_sc, h_pts)
+    ks_h = ks.cpu().numpy().astype(np.uint64)
+    acc = 0
+    for i in range(n):
+        acc += (int(h_sc[i, 0]) | int(h_sc[i, 1]) << 64 | int(h_sc[i, 2]) << 128 | int(h_sc[i, 3]) << 192) * int(ks_h[i])
+    acc %= L
+    want = np.zeros(16, dtype=np.uint64)
+    oracle.ge25519_scalarmult_base(ob.ptr(want), acc.to_bytes(32, "little"))
+    oracle.ge25519_normalize(ob.ptr(want))
+    assert np.array_equal(got, want)
+    # and it agrees with the device-resident single MSM
+    dev = cbp.Msm(n)(sc, pts).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, dev)
