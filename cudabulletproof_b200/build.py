@@ -11,7 +11,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcudabulletproof_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--use_fast_math"] + (["-DCBP_DEBUG_VSCAL"] if os.environ.get("CBP_DEBUG_VSCAL") else [])
+         "--use_fast_math"] + (["-DCBP_DEBUG_VSCAL"] if os.environ.get("CBP_DEBUG_VSCAL") else []) + \
+    os.environ.get("CBP_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -1,0 +1,236 @@
+// codec.cu — batched point encoding / decoding and generator derivation on the device.
+//
+// Replaces, for whole arrays at a time, the reference's host-side
+//   ge25519_pack   (curve25519_ops.cu:449-468)  point -> 32 B: y little-endian, bit 255 = lsb(x)
+//   ge25519_unpack (curve25519_ops.cu:470-531)  32 B -> point, with the checks the reference omits
+//                                               (canonical y, square-root test, x = 0 with sign; D7, D8)
+// and the generator derivation of complete_bulletproof_test.cu:33-63 in the corrected form of the
+// oracle (oracle_hash_to_point): SHA-256(seed || index_be [|| counter_be]) -> try to decode -> x8 ->
+// reject the identity -> normalise.  Results are bit-exact with oracle/ref_corrected.c.
+#include <string.h>
+#include "common.h"
+#include "ge25519.cuh"
+#include "sha256.cuh"
+
+namespace cbp {
+
+int fe_batch_invert_strided(uint8_t* d_out, const uint8_t* d_in, size_t in_stride, size_t count, cudaStream_t st);
+
+// out[i] holds 1/Z_i on entry (0 for Z = 0, as fe25519_invert gives) and the encoding on exit
+__global__ void __launch_bounds__(256) point_pack_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ pts,
+                                                         size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fe X, Y, zi, x, y;
+    fe_load_nc(X, pts + i * 128);
+    fe_load_nc(Y, pts + i * 128 + 32);
+    fe_load(zi, out + i * 32);
+    fe_mul(x, X, zi);
+    fe_mul(y, Y, zi);
+    fe_canon(x);
+    fe_canon(y);
+    y.v[7] |= (x.v[0] & 1u) << 31;
+    fe_store(out + i * 32, y);
+}
+
+// RFC 8032 5.1.3 decoding; false for a non-canonical y, a non-square (y^2-1)/(dy^2+1), or x = 0 with sign 1
+__device__ __forceinline__ bool ge_unpack(ge_p3& r, const uint32_t (&w)[8]) {
+    fe y;
+#pragma unroll
+    for (int i = 0; i < 8; i++) y.v[i] = w[i];
+    const uint32_t sign = y.v[7] >> 31;
+    y.v[7] &= 0x7FFFFFFFu;
+    {  // y >= p  <=>  y + 19 >= 2^255
+        uint64_t c = 19;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c += y.v[i];
+            if (i == 7 && ((uint32_t)c >> 31)) return false;
+            c >>= 32;
+        }
+    }
+    fe one, y2, u, v, v3, v7, x, t, chk;
+    fe_set1(one);
+    fe_sq(y2, y);
+    fe_sub(u, y2, one);
+    fe_mul(v, y2, fe_const_d());
+    fe_add(v, v, one);
+    fe_sq(v3, v);
+    fe_mul(v3, v3, v);
+    fe_sq(v7, v3);
+    fe_mul(v7, v7, v);
+    fe_mul(t, u, v7);
+    fe_pow2523(t, t);
+    fe_mul(x, u, v3);
+    fe_mul(x, x, t);
+    fe_sq(chk, x);
+    fe_mul(chk, chk, v);
+    if (!fe_equal(chk, u)) {
+        fe nu;
+        fe_neg(nu, u);
+        if (!fe_equal(chk, nu)) return false;
+        fe_mul(x, x, fe_const_sqrtm1());
+    }
+    fe_canon(x);
+    if (fe_iszero(x) && sign) return false;
+    if ((x.v[0] & 1u) != sign) {
+        fe_neg(x, x);
+        fe_canon(x);
+    }
+    r.X = x;
+    r.Y = y;
+    fe_set1(r.Z);
+    fe_mul(r.T, x, y);
+    fe_canon(r.T);
+    return true;
+}
+
+__global__ void __launch_bounds__(128) point_unpack_kernel(uint8_t* __restrict__ pts, uint8_t* __restrict__ ok,
+                                                           const uint8_t* __restrict__ in, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    fe raw;
+    fe_load_nc(raw, in + i * 32);
+    ge_p3 P;
+    bool good = ge_unpack(P, raw.v);
+    if (!good) ge_p3_0(P);  // the reference leaves the output untouched; a defined value is kinder
+    ge_store(pts + i * 128, P);
+    if (ok) ok[i] = good ? 1 : 0;
+}
+
+struct Seed32 {
+    uint32_t w[8];  // the 32 seed bytes as little-endian words
+};
+__global__ void __launch_bounds__(64) gens_derive_kernel(uint8_t* __restrict__ pts, Seed32 seed, uint32_t first_index,
+                                                         size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t index = first_index + (uint32_t)i;
+    for (uint32_t ctr = 0;; ctr++) {
+        Sha256 sh;
+        sh.init();
+        sh.update_words(seed.w);
+        sh.put((uint8_t)(index >> 24));  // big-endian index, as the reference's hash_input[32..35]
+        sh.put((uint8_t)(index >> 16));
+        sh.put((uint8_t)(index >> 8));
+        sh.put((uint8_t)index);
+        if (ctr != 0) {  // counter 0 hashes exactly the reference's 36 bytes
+            sh.put((uint8_t)(ctr >> 24));
+            sh.put((uint8_t)(ctr >> 16));
+            sh.put((uint8_t)(ctr >> 8));
+            sh.put((uint8_t)ctr);
+        }
+        uint32_t h[8], w[8];
+        sh.final_words(h);
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = __byte_perm(h[j], 0, 0x0123);  // digest bytes as little-endian words
+        ge_p3 P;
+        if (!ge_unpack(P, w)) continue;
+        ge_dbl(P, P);
+        ge_dbl(P, P);
+        ge_dbl(P, P);  // clear the cofactor
+        if (ge_is_identity(P)) continue;
+        ge_normalize(P);
+        ge_store(pts + i * 128, P);
+        return;
+    }
+}
+
+// test hook: elementwise group operations on arrays of extended points (un-normalised outputs)
+__global__ void __launch_bounds__(128) ge_op_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                    uint8_t* __restrict__ out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    ge_p3 P, Q, R;
+    ge_load(P, a + i * 128);
+    if (b) ge_load(Q, b + i * 128);
+    else Q = P;
+    if (op == 0) ge_dbl(R, P);
+    else if (op == 1) ge_add(R, P, Q);
+    else {
+        R = P;
+        ge_dbl(R, R);
+        ge_dbl(R, R);
+        ge_dbl(R, R);
+    }
+    ge_store(out + i * 128, R);
+}
+
+// test hook: field arithmetic on COMPILE-TIME constants.  Inline-asm carry chains whose read-write operands
+// are not early-clobber ("+r" instead of "+&r") compute garbage exactly here, because the compiler may then
+// give an input and an accumulator that hold the same known value (0) one register; every other test feeds
+// run-time data and cannot see that.  out: sq(1), mul(1,1), 1+1, sq(2), 1-2, 2*2d  (6 x 8 words)
+__global__ void const_operand_kernel(uint32_t* __restrict__ out) {
+    fe one, two, r;
+    fe_set1(one);
+    fe_sq(r, one);
+    for (int i = 0; i < 8; i++) out[i] = r.v[i];
+    fe_mul(r, one, one);
+    for (int i = 0; i < 8; i++) out[8 + i] = r.v[i];
+    fe_add(two, one, one);
+    for (int i = 0; i < 8; i++) out[16 + i] = two.v[i];
+    fe_sq(r, two);
+    for (int i = 0; i < 8; i++) out[24 + i] = r.v[i];
+    fe_sub(r, one, two);
+    fe_canon(r);
+    for (int i = 0; i < 8; i++) out[32 + i] = r.v[i];
+    fe_mul(r, two, fe_const_2d());
+    fe_canon(r);
+    for (int i = 0; i < 8; i++) out[40 + i] = r.v[i];
+}
+
+}  // namespace cbp
+
+using namespace cbp;
+
+extern "C" {
+
+int bpk_point_pack_device(void* d_out, const void* d_points, size_t count, void* stream) {
+    if (!count) return BPK_OK;
+    if (!d_out || !d_points) return fail(BPK_ERR_ARG);
+    cudaStream_t st = (cudaStream_t)stream;
+    // 1/Z for the whole array with one field inversion per 4096 points, parked in the output buffer
+    int rc = fe_batch_invert_strided((uint8_t*)d_out, (const uint8_t*)d_points + 64, 128, count, st);
+    if (rc != BPK_OK) return rc;
+    point_pack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((uint8_t*)d_out, (const uint8_t*)d_points, count);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+int bpk_point_unpack_device(void* d_points, uint8_t* d_ok, const void* d_in, size_t count, void* stream) {
+    if (!count) return BPK_OK;
+    if (!d_points || !d_in) return fail(BPK_ERR_ARG);
+    point_unpack_kernel<<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (uint8_t*)d_points, d_ok, (const uint8_t*)d_in, count);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+int bpk_debug_ge_op_device(int op, const void* d_a, const void* d_b, void* d_out, size_t count, void* stream) {
+    if (!count) return BPK_OK;
+    if (!d_a || !d_out || op < 0 || op > 2) return fail(BPK_ERR_ARG);
+    ge_op_kernel<<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(op, (const uint8_t*)d_a,
+                                                                                     (const uint8_t*)d_b, (uint8_t*)d_out, count);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+int bpk_debug_const_operands_device(uint32_t* d_out48, void* stream) {
+    if (!d_out48) return fail(BPK_ERR_ARG);
+    const_operand_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_out48);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+int bpk_gens_derive_device(void* d_points, const uint8_t seed[32], uint32_t first_index, size_t count, void* stream) {
+    if (!count) return BPK_OK;
+    if (!d_points || !seed) return fail(BPK_ERR_ARG);
+    Seed32 s;
+    memcpy(s.w, seed, 32);
+    gens_derive_kernel<<<(unsigned)((count + 63) / 64), 64, 0, (cudaStream_t)stream>>>((uint8_t*)d_points, s, first_index,
+                                                                                        count);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+}  // extern "C"

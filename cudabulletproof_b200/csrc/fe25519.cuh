@@ -21,9 +21,13 @@ struct fe {
 
 // ------------------------------------------------------------------------------------------
 // carry-chain building blocks (one asm block per chain: the CC flag is implicit state).
-// Write-only outputs are early-clobber ("=&r"): each block is several instructions and writes its
-// first outputs before it has read its last inputs, so an output must never share a register with
-// an input (without '&' the compiler may coalesce them, which silently corrupts the chain).
+// EVERY written operand is early-clobber ("=&r", "+&r"): each block is several instructions and writes
+// its first outputs before it has read its last inputs, so a written operand must never share a register
+// with an input.  Without '&' the compiler may coalesce them: for write-only outputs always, for
+// read-write accumulators whenever it knows that an input holds the same VALUE as the accumulator's
+// initial contents (e.g. both the constant 0) — which silently corrupts the chain.  That second case only
+// shows up with compile-time-known operands (squaring the constant 1 returned 39 * (1 + 2^64 + ...));
+// tests/test_gpu_codec.py::test_field_ops_on_compile_time_constants guards it.
 // ------------------------------------------------------------------------------------------
 
 // acc[0..7] (+carry into acc[8]) += {x0,x1,x2,x3} * b, product k landing on words (2k, 2k+1)
@@ -39,7 +43,7 @@ __device__ __forceinline__ void mad_row4(uint32_t& c0, uint32_t& c1, uint32_t& c
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.u32       %8, %8, 0;"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7), "+r"(c8)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(c6), "+&r"(c7), "+&r"(c8)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
 }
 // same without the carry-out word (used where the bound on the total proves it is zero)
@@ -54,7 +58,7 @@ __device__ __forceinline__ void mad_row4_nc(uint32_t& c0, uint32_t& c1, uint32_t
         "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
         "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
         "madc.hi.u32    %7, %11, %12, %7;"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(c6), "+&r"(c7)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
 }
 // first row: plain products, no incoming accumulator
@@ -89,7 +93,7 @@ __device__ __forceinline__ void fe_fold(fe& r, const uint32_t (&w)[16]) {
         "addc.cc.u32 %5, %5, %14;\n\t"
         "addc.cc.u32 %6, %6, %15;\n\t"
         "addc.u32    %7, %8, %16;"
-        : "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=&r"(top)
+        : "+&r"(e1), "+&r"(e2), "+&r"(e3), "+&r"(e4), "+&r"(e5), "+&r"(e6), "+&r"(e7), "=&r"(top)
         : "r"(e8), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(o7), "r"(o8));
     // value = e[0..7] + top * 2^256 with top <= 38: fold again, then once more for the final carry
     uint32_t t = top * 38u, c;
@@ -102,7 +106,7 @@ __device__ __forceinline__ void fe_fold(fe& r, const uint32_t (&w)[16]) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32    %8, 0, 0;"
-        : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=&r"(c)
+        : "+&r"(e0), "+&r"(e1), "+&r"(e2), "+&r"(e3), "+&r"(e4), "+&r"(e5), "+&r"(e6), "+&r"(e7), "=&r"(c)
         : "r"(t));
     e0 += c * 38u;  // after a wrap the low words are < 2^12, so this cannot carry
     r.v[0] = e0; r.v[1] = e1; r.v[2] = e2; r.v[3] = e3; r.v[4] = e4; r.v[5] = e5; r.v[6] = e6; r.v[7] = e7;
@@ -195,7 +199,7 @@ __device__ __forceinline__ void mad_row3(uint32_t& c0, uint32_t& c1, uint32_t& c
         "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
         "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
         "addc.u32       %6, %6, 0;"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(c6)
         : "r"(x0), "r"(x1), "r"(x2), "r"(b));
 }
 __device__ __forceinline__ void mad_row2(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& c4,
@@ -205,14 +209,14 @@ __device__ __forceinline__ void mad_row2(uint32_t& c0, uint32_t& c1, uint32_t& c
         "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
         "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
         "addc.u32       %4, %4, 0;"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4)
         : "r"(x0), "r"(x1), "r"(b));
 }
 __device__ __forceinline__ void mad_row1(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t x0, uint32_t b) {
     asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
         "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
         "addc.u32       %2, %2, 0;"
-        : "+r"(c0), "+r"(c1), "+r"(c2)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2)
         : "r"(x0), "r"(b));
 }
 __device__ __forceinline__ void sq_wide(uint32_t (&w)[16], const fe& a) {
@@ -281,8 +285,8 @@ __device__ __forceinline__ void sq_wide(uint32_t (&w)[16], const fe& a) {
         "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
         "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
         "madc.hi.u32    %15, %23, %23, %15;"
-        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]),
-          "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+        : "+&r"(w[0]), "+&r"(w[1]), "+&r"(w[2]), "+&r"(w[3]), "+&r"(w[4]), "+&r"(w[5]), "+&r"(w[6]), "+&r"(w[7]), "+&r"(w[8]),
+          "+&r"(w[9]), "+&r"(w[10]), "+&r"(w[11]), "+&r"(w[12]), "+&r"(w[13]), "+&r"(w[14]), "+&r"(w[15])
         : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
 }
 __device__ __forceinline__ void fe_sq(fe& r, const fe& a) {
@@ -317,8 +321,8 @@ __device__ __forceinline__ void fe_add(fe& r, const fe& a, const fe& b) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32    %8, 0, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
-          "+r"(r.v[7]), "=&r"(c2)
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]),
+          "+&r"(r.v[7]), "=&r"(c2)
         : "r"(t));
     r.v[0] += c2 * 38u;
 }
@@ -350,8 +354,8 @@ __device__ __forceinline__ void fe_sub(fe& r, const fe& a, const fe& b) {
         "subc.cc.u32 %6, %6, 0;\n\t"
         "subc.cc.u32 %7, %7, 0;\n\t"
         "subc.u32    %8, 0, 0;"
-        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
-          "+r"(r.v[7]), "=&r"(b2)
+        : "+&r"(r.v[0]), "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]),
+          "+&r"(r.v[7]), "=&r"(b2)
         : "r"(t));
     r.v[0] -= b2 & 38u;  // after a second wrap the value is >= 2^256 - 38, so this cannot borrow
 }
@@ -396,8 +400,8 @@ __device__ __forceinline__ void fe_add_small(fe& t, uint32_t k) {
         "addc.cc.u32 %5, %5, 0;\n\t"
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.u32    %7, %7, 0;"
-        : "+r"(t.v[0]), "+r"(t.v[1]), "+r"(t.v[2]), "+r"(t.v[3]), "+r"(t.v[4]), "+r"(t.v[5]), "+r"(t.v[6]),
-          "+r"(t.v[7])
+        : "+&r"(t.v[0]), "+&r"(t.v[1]), "+&r"(t.v[2]), "+&r"(t.v[3]), "+&r"(t.v[4]), "+&r"(t.v[5]), "+&r"(t.v[6]),
+          "+&r"(t.v[7])
         : "r"(k));
 }
 // unique representative in [0, p).  2^255 = 19 (mod p): fold bit 255 twice, then one conditional

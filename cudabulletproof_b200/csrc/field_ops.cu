@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) fe_batch_kernel(uint8_t* __restrict__ out
 // the backward pass turns prefixes into inverses.  Zero inputs are skipped and map to zero.
 static constexpr int kInvThreads = 256, kInvPer = 16, kInvTile = kInvThreads * kInvPer;
 __global__ void __launch_bounds__(kInvThreads) fe_batch_invert_kernel(uint8_t* __restrict__ out,
-                                                                      const uint8_t* __restrict__ in, size_t count) {
+                                                                      const uint8_t* __restrict__ in, size_t in_stride,
+                                                                      size_t count) {
     __shared__ fe s_pre[kInvThreads];
     __shared__ fe s_suf[kInvThreads];
     __shared__ fe s_inv;
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(kInvThreads) fe_batch_invert_kernel(uint8_t* _
             size_t i = tile + (size_t)j * kInvThreads + t;
             if (i < count) {
                 fe x;
-                fe_load_nc(x, in + i * 32);
+                fe_load_nc(x, in + i * in_stride);
                 fe_store(out + i * 32, acc);
                 if (!fe_iszero(x)) fe_mul(acc, acc, x);
             }
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kInvThreads) fe_batch_invert_kernel(uint8_t* _
             size_t i = tile + (size_t)j * kInvThreads + t;
             if (i < count) {
                 fe x, pre, r;
-                fe_load_nc(x, in + i * 32);
+                fe_load_nc(x, in + i * in_stride);
                 fe_load(pre, out + i * 32);
                 if (fe_iszero(x)) {
                     fe_set0(r);
@@ -290,6 +291,20 @@ int bpk_fe_batch_device(int op, void* d_out, const void* d_a, const void* d_b, s
     CBP_CHECK_LAUNCH();
     return BPK_OK;
 }
+}  // extern "C"
+namespace cbp {
+// out[i] = 1 / fe at (in + i * in_stride), 0 for 0; out is dense (32 B per element) and must not alias in
+int fe_batch_invert_strided(uint8_t* d_out, const uint8_t* d_in, size_t in_stride, size_t count, cudaStream_t st) {
+    if (!count) return BPK_OK;
+    size_t tiles = (count + kInvTile - 1) / kInvTile;
+    size_t cap = (size_t)num_sms() * 4;
+    unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    fe_batch_invert_kernel<<<grid, kInvThreads, 0, st>>>(d_out, d_in, in_stride, count);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+}  // namespace cbp
+extern "C" {
 int bpk_fe_batch_invert_workspace_bytes(size_t count, size_t* bytes) {
     (void)count;
     if (!bytes) return fail(BPK_ERR_ARG);
@@ -305,7 +320,7 @@ int bpk_fe_batch_invert_device(void* d_out, const void* d_in, size_t count, void
     size_t tiles = (count + kInvTile - 1) / kInvTile;
     size_t cap = (size_t)num_sms() * 4;
     unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    fe_batch_invert_kernel<<<grid, kInvThreads, 0, (cudaStream_t)stream>>>((uint8_t*)d_out, (const uint8_t*)d_in, count);
+    fe_batch_invert_kernel<<<grid, kInvThreads, 0, (cudaStream_t)stream>>>((uint8_t*)d_out, (const uint8_t*)d_in, 32, count);
     CBP_CHECK_LAUNCH();
     return BPK_OK;
 }

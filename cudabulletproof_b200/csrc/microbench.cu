@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "ge25519.cuh"
 using namespace cbp;
 
@@ -193,6 +194,19 @@ int main() {
     {
         double ms = time_ms([&] { k_lat_inv<<<sms, 32>>>((uint32_t*)buf, 99); }, 5);
         printf("{\"bench\": \"latency_fe_invert\", \"us\": %.3f}\n", ms * 1e3);
+    }
+    {  // PCIe: contiguous upload of 2^20 points (128 B each) against a pitched upload of X,Y,Z only (96 of 128 B)
+        const size_t n = (size_t)1 << 20;
+        void *h = nullptr, *d = nullptr;
+        if (cudaMallocHost(&h, n * 128) == cudaSuccess && cudaMalloc(&d, n * 128) == cudaSuccess) {
+            memset(h, 1, n * 128);
+            double ms = time_ms([&] { cudaMemcpyAsync(d, h, n * 128, cudaMemcpyHostToDevice, 0); }, 5);
+            printf("{\"bench\": \"h2d_contiguous_128B\", \"ms\": %.4f, \"GBps\": %.2f}\n", ms, n * 128 / ms / 1e6);
+            ms = time_ms([&] { cudaMemcpy2DAsync(d, 96, h, 128, 96, n, cudaMemcpyHostToDevice, 0); }, 5);
+            printf("{\"bench\": \"h2d_pitched_96_of_128B\", \"ms\": %.4f, \"useful_GBps\": %.2f}\n", ms, n * 96 / ms / 1e6);
+            ms = time_ms([&] { cudaMemcpy2DAsync(d, 128, h, 128, 96, n, cudaMemcpyHostToDevice, 0); }, 5);
+            printf("{\"bench\": \"h2d_pitched_96_of_128B_dst128\", \"ms\": %.4f, \"useful_GBps\": %.2f}\n", ms, n * 96 / ms / 1e6);
+        }
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }

@@ -289,3 +289,49 @@ def ipa_fold_points(G, H, u, u_inv, stream=None):
                                              u.data_ptr(), u_inv.data_ptr(), _stream_ptr(stream)),
            "bpk_ipa_fold_points_device")
     return Go, Ho
+
+
+# ---- point codec and generator derivation (include/bpk.h) ----------------------
+def _as_dev_u8(a, width, device="cuda"):
+    """numpy (rows of uint64 / uint8) or cuda tensor -> contiguous (count, width) uint8 cuda tensor"""
+    import torch
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1, width))
+    return a.to(device).contiguous().view(torch.uint8).reshape(-1, width)
+
+
+def point_pack(points, stream=None):
+    """(count, 128) extended points -> (count, 32) uint8 cuda tensor of RFC 8032 encodings
+    (ge25519_pack, curve25519_ops.cu:449-468, batched)."""
+    import torch
+    d = _as_dev_u8(points, 128)
+    out = torch.empty((d.shape[0], 32), dtype=torch.uint8, device=d.device)
+    _check(_lib().bpk_point_pack_device(out.data_ptr(), d.data_ptr(), d.shape[0], _stream_ptr(stream)),
+           "bpk_point_pack_device")
+    return out
+
+
+def point_unpack(encodings, stream=None):
+    """(count, 32) encodings -> ((count, 128) uint8 cuda tensor of points with Z = 1, (count,) uint8 validity mask)
+    (ge25519_unpack, curve25519_ops.cu:470-531, batched, with the validity checks of RFC 8032)."""
+    import torch
+    d = _as_dev_u8(encodings, 32)
+    pts = torch.empty((d.shape[0], 128), dtype=torch.uint8, device=d.device)
+    ok = torch.empty((d.shape[0],), dtype=torch.uint8, device=d.device)
+    _check(_lib().bpk_point_unpack_device(pts.data_ptr(), ok.data_ptr(), d.data_ptr(), d.shape[0], _stream_ptr(stream)),
+           "bpk_point_unpack_device")
+    return pts, ok
+
+
+def derive_generators(seed, count, first_index=0, device="cuda", stream=None):
+    """Generators first_index .. first_index+count-1 of the family `seed` (32 bytes) as a (count, 128) uint8
+    cuda tensor: prime-order points with the reference test's derivation labels
+    (complete_bulletproof_test.cu:33-41,79-88), derived on the device."""
+    import torch
+    seed = bytes(seed)
+    assert len(seed) == 32
+    out = torch.empty((count, 128), dtype=torch.uint8, device=device)
+    _check(_lib().bpk_gens_derive_device(out.data_ptr(), seed, first_index, count, _stream_ptr(stream)),
+           "bpk_gens_derive_device")
+    torch.cuda.current_stream().synchronize()
+    return out

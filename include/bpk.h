@@ -84,6 +84,26 @@ int bpk_ipa_fold_scalars_device(void* d_a_out, void* d_b_out, const void* d_a, c
 int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, const void* d_H, size_t n_half,
                                const void* d_u, const void* d_u_inv, void* stream);
 
+/* ---- point codec and generator derivation (N2, N4) ---- */
+/* d_out[i] (32 B) = RFC 8032 encoding of d_points[i] (ge25519, any Z): y little-endian, bit 255 = lsb(x).
+ * Replaces ge25519_pack (curve25519_ops.cu:449-468) on arrays; one field inversion per 4096 points. */
+int bpk_point_pack_device(void* d_out, const void* d_points, size_t count, void* stream);
+/* d_points[i] = decoded point (Z = 1, canonical limbs), d_ok[i] = 1; or the identity and d_ok[i] = 0 when the
+ * encoding is invalid (y >= p, no square root, x = 0 with sign bit).  d_ok may be NULL.
+ * Replaces ge25519_unpack (curve25519_ops.cu:470-531) with the checks it omits (defects D7, D8). */
+int bpk_point_unpack_device(void* d_points, uint8_t* d_ok, const void* d_in, size_t count, void* stream);
+/* d_points[i] = generator number first_index + i of the family `seed` (32 bytes, HOST pointer):
+ * SHA-256(seed || index_be32 [|| counter_be32]) decoded as a point, counter bumped until it decodes, times 8,
+ * never the identity, normalised.  Labels as complete_bulletproof_test.cu:33-41,79-88 (seed byte 1..4). */
+int bpk_gens_derive_device(void* d_points, const uint8_t seed[32], uint32_t first_index, size_t count, void* stream);
+
+/* test hook: out[i] = 2 a[i] (op 0), a[i] + b[i] (op 1; b NULL: a[i] + a[i]), 8 a[i] (op 2); extended points,
+ * outputs not normalised.  Lets the parity tests pin the group law itself against the CPU oracle. */
+int bpk_debug_ge_op_device(int op, const void* d_a, const void* d_b, void* d_out, size_t count, void* stream);
+/* test hook: field operations on compile-time constants; writes 6 field elements (8 words each):
+ * 1^2, 1*1, 1+1, 2^2, 1-2 (canonical), 2*(2d) (canonical).  Guards the inline-asm operand constraints. */
+int bpk_debug_const_operands_device(uint32_t* d_out48, void* stream);
+
 /* ---- range proofs: replaces cuda_range_proof_verify (cuda_bulletproof.h:61) on batches ---- */
 /* Flat proof record, uint64 words (n-bit proof, k = log2 n):
  *   V,A,S,T1,T2 (5 x 128 B) | taux,mu,t (3 x 32 B) | a,b,c,x (4 x 32 B) | L[0..k) (k x 128 B) | R[0..k) (k x 128 B) */
