@@ -527,6 +527,9 @@ __global__ void __launch_bounds__(128) msm_reduce_warp_kernel(const uint8_t* __r
 // run every point operation on a quad of lanes (ge_add_quad / ge_dbl_quad: 3 resp. 2 multiplication depths
 // instead of 9 / 8; measured 0.99 / 0.72 us against 2.21 / 1.67 us per dependent operation).
 // Logical thread = quad; all 32 lanes of a warp stay converged (full-mask shuffles inside the quad ops).
+// Measured and rejected: out-of-line (__noinline__) copies of the two quad operations to shrink these kernels
+// (120 -> 36 KB of SASS) — the argument traffic through local memory costs more than the cold instruction
+// fetches save: 2.32 vs 2.27 ms per 2^20 MSM, 0.92 vs 0.86 ms at 2^16 (same box, alternating runs).
 __global__ void __launch_bounds__(128) msm_reduce_level_quad_kernel(const uint8_t* __restrict__ Xin,
                                                                     const uint8_t* __restrict__ Yin, uint32_t n_in,
                                                                     uint32_t n_out, int W, int has_y, uint32_t in_stride,
