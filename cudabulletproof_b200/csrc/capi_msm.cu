@@ -145,22 +145,22 @@ int bpk_synth_scalars_device(void* d_scalars, size_t n, uint64_t seed, int bits,
 // (cuda_bulletproof_kernels.cu:77-115).  Here the device buffers are a grow-only cache (one per
 // process, guarded by a mutex) and there is one synchronisation.  The upload (160 B per point over PCIe)
 // costs more than the whole MSM, so inputs of 2^20 points and more are cut into chunks of kHostChunk
-// points: one stream copies chunk after chunk while up to kMsmKits earlier chunks are being multiplied,
-// each as an independent MSM with its own workspace and side streams.  The partial results are summed
-// and normalised by one last kernel.
+// points: one stream copies chunk after chunk while the compute stream sorts each arrived chunk and adds it
+// into the SAME bucket sums (msm_run flags kMsmCarryIn / kMsmNoTail); the bucket reduction and the window
+// combine run once, after the last chunk.
 namespace {
-// measured on B200 at n = 2^20 (tools/probe_e2e.py): chunks of 2^17 / 2^18 / 2^19 / one piece = 7.3 / 5.8 / 4.6 / 5.3 ms
-// (a mid-size MSM is latency-bound, ~1.4 ms; uploading 2^19 points takes 1.5 ms)
-constexpr size_t kHostChunk = (size_t)1 << 19;
+// (independent MSMs per chunk were measured first — 2^17 / 2^18 / 2^19 / one piece = 7.3 / 5.8 / 4.6 / 5.3 ms at
+// n = 2^20: a mid-size MSM is latency-bound, ~1.4 ms — hence the shared buckets)
+constexpr size_t kHostChunk = (size_t)1 << 17;
 constexpr size_t kHostChunkMin = (size_t)1 << 20;  // below this a single MSM (scalars first) is faster
 constexpr int kMaxChunks = 4096;
 struct HostPath {
     std::mutex mu;
-    uint8_t *d_s = nullptr, *d_p = nullptr, *d_r = nullptr, *d_partial = nullptr;
-    uint8_t* d_ws[kMsmKits] = {};
-    size_t cap_s = 0, cap_p = 0, cap_partial = 0, cap_ws[kMsmKits] = {};
-    cudaStream_t main = nullptr, copy = nullptr, lane[kMsmKits] = {};
-    cudaEvent_t ev_points = nullptr, ev_lane[kMsmKits] = {};
+    uint8_t *d_s = nullptr, *d_p = nullptr, *d_r = nullptr;
+    uint8_t* d_ws[1] = {};
+    size_t cap_s = 0, cap_p = 0, cap_ws[1] = {};
+    cudaStream_t main = nullptr, copy = nullptr;
+    cudaEvent_t ev_points = nullptr;
     std::vector<cudaEvent_t> ev_chunk;
     bool ok = false;
 };
@@ -187,10 +187,6 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
             (e = cudaEventCreateWithFlags(&hp.ev_points, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaMalloc(&hp.d_r, 256)) != cudaSuccess)
             return fail(BPK_ERR_CUDA, e);
-        for (int i = 0; i < kMsmKits; i++)
-            if ((e = cudaStreamCreateWithFlags(&hp.lane[i], cudaStreamNonBlocking)) != cudaSuccess ||
-                (e = cudaEventCreateWithFlags(&hp.ev_lane[i], cudaEventDisableTiming)) != cudaSuccess)
-                return fail(BPK_ERR_CUDA, e);
         hp.ok = true;
     }
     if (n) {
@@ -226,44 +222,37 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
             chunk = (n + nchunks - 1) / nchunks;
             nchunks = (n + chunk - 1) / chunk;
         }
+        // every chunk adds into the SAME buckets (window width of the whole input, one workspace laid out for
+        // a full chunk); only the last chunk runs the bucket reduction and the window combine
         MsmPlan p_full, p_last;
-        msm_make_plan(&p_full, chunk, 0);
-        const size_t last_n = n - (nchunks - 1) * chunk;
-        msm_make_plan(&p_last, last_n, 0);
-        const size_t ws_need = p_full.workspace_bytes > p_last.workspace_bytes ? p_full.workspace_bytes : p_last.workspace_bytes;
-        for (int i = 0; i < kMsmKits; i++)
-            if ((e = grow(&hp.d_ws[i], &hp.cap_ws[i], ws_need)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
-        if ((e = grow(&hp.d_partial, &hp.cap_partial, nchunks * 128)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+        msm_make_plan(&p_full, chunk, msm_pick_window(n));
+        p_last = p_full;
+        p_last.n = n - (nchunks - 1) * chunk;
+        if ((e = grow(&hp.d_ws[0], &hp.cap_ws[0], p_full.workspace_bytes)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
         while (hp.ev_chunk.size() < nchunks) {
             cudaEvent_t ev;
             if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
             hp.ev_chunk.push_back(ev);
         }
         for (size_t c = 0; c < nchunks; c++) {
-            const size_t lo = c * chunk, cnt = c + 1 == nchunks ? last_n : chunk;
-            const int lane = (int)(c % kMsmKits);
+            const bool last = c + 1 == nchunks;
+            const size_t lo = c * chunk, cnt = last ? p_last.n : chunk;
             if ((e = cudaMemcpyAsync(hp.d_s + lo * 32, h_s + lo * 32, cnt * 32, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
                 (e = cudaMemcpyAsync(hp.d_p + lo * 128, h_p + lo * 128, cnt * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
                 (e = cudaEventRecord(hp.ev_chunk[c], hp.copy)) != cudaSuccess ||
-                (e = cudaStreamWaitEvent(hp.lane[lane], hp.ev_chunk[c], 0)) != cudaSuccess)
+                (e = cudaStreamWaitEvent(hp.main, hp.ev_chunk[c], 0)) != cudaSuccess)
                 return fail(BPK_ERR_CUDA, e);
             int nl = 0;
-            int rc = msm_run(c + 1 == nchunks ? p_last : p_full, hp.d_s + lo * 32, hp.d_p + lo * 128, hp.d_partial + c * 128,
-                             hp.d_ws[lane], 0, hp.lane[lane], &nl, nullptr, lane);
+            int flags = (c > 0 ? kMsmCarryIn : 0) | (last ? 0 : kMsmNoTail);
+            int rc = msm_run(last ? p_last : p_full, hp.d_s + lo * 32, hp.d_p + lo * 128, hp.d_r, hp.d_ws[0], 1, hp.main, &nl,
+                             nullptr, 0, flags);
             launches += nl;
             if (rc) {
                 count_launches(launches);
                 return fail_cuda(rc);
             }
         }
-        for (int i = 0; i < kMsmKits; i++)
-            if ((e = cudaEventRecord(hp.ev_lane[i], hp.lane[i])) != cudaSuccess ||
-                (e = cudaStreamWaitEvent(hp.main, hp.ev_lane[i], 0)) != cudaSuccess)
-                return fail(BPK_ERR_CUDA, e);
-        point_sum_kernel<<<1, 32, 0, hp.main>>>(hp.d_partial, nchunks, 1, hp.d_r);
-        launches++;
         count_launches(launches);
-        if ((e = cudaGetLastError()) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
     }
     ge25519 tmp;
     e = cudaMemcpyAsync(&tmp, hp.d_r, 128, cudaMemcpyDeviceToHost, hp.main);

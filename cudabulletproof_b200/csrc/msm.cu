@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "ge25519.cuh"
 #include "msm.h"
 #include "common.h"
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(128, 4)
     msm_accumulate_kernel(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
                           const uint2* __restrict__ desc, const uint32_t* __restrict__ offsets,
                           const uint32_t* __restrict__ segoff, GroupMap gm, const uint32_t* __restrict__ order,
-                          const uint32_t* __restrict__ binstart, int group,
+                          const uint32_t* __restrict__ binstart, int group, int carry,
                           uint8_t* __restrict__ bucket_sums, uint8_t* __restrict__ seg_sums) {
     uint32_t lo = binstart[group * kSegBinsPerGroup], hi = binstart[(group + 1) * kSegBinsPerGroup];
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,8 +345,11 @@ __global__ void __launch_bounds__(128, 4)
     uint32_t seg = order[lo + t];
     uint2 d = desc[seg];
     uint32_t e = d.x, end = d.x + seg_length(d, offsets, gm), id = d.y;
+    const bool single = segoff[id + 1] - segoff[id] == 1;
     ge_p3 acc;
-    ge_p3_0(acc);
+    // carry: the bucket already holds the sum over earlier chunks of the input (chunked host path)
+    if (carry && single) ge_load(acc, bucket_sums + (size_t)id * 128);
+    else ge_p3_0(acc);
     if (e < end) {
         uint32_t ent = __ldg(entries + e);
         ge_niels q;
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(128, 4)
             if (e >= end) break;
         }
     }
-    bool single = segoff[id + 1] - segoff[id] == 1;
+    if (carry && single && d.x == end) return;  // nothing new for this bucket
     ge_store(single ? bucket_sums + (size_t)id * 128 : seg_sums + (size_t)seg * 128, acc);
 }
 // buckets cut into several segments: a thread adds up to kHeavySeq segment sums itself, larger buckets
@@ -371,7 +375,7 @@ static constexpr uint32_t kHeavySeq = 8;
 __global__ void __launch_bounds__(128) msm_heavy_small_kernel(const uint32_t* __restrict__ heavy,
                                                               const uint32_t* __restrict__ heavy_cnt, int group,
                                                               uint32_t heavy_base, const uint32_t* __restrict__ segoff,
-                                                              const uint8_t* __restrict__ seg_sums,
+                                                              const uint8_t* __restrict__ seg_sums, int carry,
                                                               uint8_t* __restrict__ bucket_sums) {
     uint32_t cnt = heavy_cnt[group];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
@@ -380,6 +384,11 @@ __global__ void __launch_bounds__(128) msm_heavy_small_kernel(const uint32_t* __
         if (s1 - s0 > kHeavySeq) continue;
         ge_p3 acc;
         ge_load(acc, seg_sums + (size_t)s0 * 128);
+        if (carry) {
+            ge_p3 old;
+            ge_load(old, bucket_sums + (size_t)id * 128);
+            ge_add(acc, acc, old);
+        }
         for (uint32_t q = s0 + 1; q < s1; q++) {
             ge_p3 x;
             ge_load(x, seg_sums + (size_t)q * 128);
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(128) msm_heavy_small_kernel(const uint32_t* __
 __global__ void __launch_bounds__(128) msm_heavy_fix_kernel(const uint32_t* __restrict__ heavy,
                                                             const uint32_t* __restrict__ heavy_cnt, int group,
                                                             uint32_t heavy_base, const uint32_t* __restrict__ segoff,
-                                                            const uint8_t* __restrict__ seg_sums,
+                                                            const uint8_t* __restrict__ seg_sums, int carry,
                                                             uint8_t* __restrict__ bucket_sums) {
     uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -408,7 +417,14 @@ __global__ void __launch_bounds__(128) msm_heavy_fix_kernel(const uint32_t* __re
             ge_add(acc, acc, x);
         }
         ge_warp_sum(acc);
-        if (lane == 0) ge_store(bucket_sums + (size_t)id * 128, acc);
+        if (lane == 0) {
+            if (carry) {
+                ge_p3 old;
+                ge_load(old, bucket_sums + (size_t)id * 128);
+                ge_add(acc, acc, old);
+            }
+            ge_store(bucket_sums + (size_t)id * 128, acc);
+        }
     }
 }
 
@@ -672,7 +688,14 @@ __global__ void __launch_bounds__(32) msm_horner_kernel(const uint8_t* __restric
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int msm_pick_window(size_t n) {
-    // minimise W*(n + 2*2^(c-1)*9/7) over c with W = ceil(256/c); c <= 16 keeps entries in 32 bits
+    // Measured on B200 (tools/probe_c.py, ms per MSM, c = 13 / 14 / 15 / 16):
+    //   2^15: 0.84 0.85 0.74 0.80   2^16: 0.87 0.92 0.79 0.84   2^17: 1.13 1.09 0.90 0.93
+    //   2^18: 1.91 1.46 1.08 1.09   2^19: 3.46 2.45 1.47 1.48   2^20: 6.64 4.35 2.51 2.22
+    // From 2^15 points the window-group pipeline is on and the call is bound by dependent chains, whose
+    // length falls with the number of windows: wide windows win long before the operation count says so.
+    if (n >= ((size_t)1 << 19)) return 16;
+    if (n >= ((size_t)1 << 15)) return 15;
+    // below: minimise W*(n + 2*2^(c-1)*9/7) over c with W = ceil(256/c); c <= 16 keeps entries in 32 bits
     double best = 1e300;
     int best_c = 4;
     for (int c = 4; c <= 16; c++) {
@@ -807,7 +830,7 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
 
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
-            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index) {
+            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index, int flags) {
     uint8_t* ws = (uint8_t*)d_ws;
     uint8_t* table = ws + p.off_table;
     uint32_t* counts = (uint32_t*)(ws + p.off_counts);
@@ -835,7 +858,10 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
-    StreamKit* kit = n >= (1u << 15) ? stream_kit(kit_index) : nullptr;
+    const int carry = (flags & kMsmCarryIn) ? 1 : 0;
+    const bool no_tail = (flags & kMsmNoTail) != 0;
+    // a chunk that only adds into the buckets has no tails to overlap: one group, everything on `st`
+    StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(kit_index) : nullptr;
     GroupMap gm;
     make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr);
 
@@ -904,8 +930,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         size_t seg_bound = (size_t)nwin * p.B + ((n * (size_t)nwin) >> gshift) + 1;
         if (g == 0) prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
         msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, offsets, segoff,
-                                                                                  gm, order, binstart, g, buckets,
-                                                                                  segsums);
+                                                                                  gm, order, binstart, g, carry,
+                                                                                  buckets, segsums);
         if (g == gm.ngroups - 1) {
             prof_end(BPK_PROF_MSM_ACCUMULATE, st);
             prof_begin(BPK_PROF_MSM_TAIL, st);
@@ -919,12 +945,13 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (heavy_bound > (size_t)nwin * p.B) heavy_bound = (size_t)nwin * p.B;
         unsigned sgrid_h = (unsigned)((heavy_bound + 127) / 128);
         msm_heavy_small_kernel<<<sgrid_h < 4736 ? sgrid_h : 4736, 128, 0, tail>>>(heavy, heavy_cnt, g, (uint32_t)w_lo * p.B,
-                                                                                  segoff, segsums, buckets);
+                                                                                  segoff, segsums, carry, buckets);
         CBP_LAUNCH_CHECK(); nl++;
         unsigned hgrid = (unsigned)((heavy_bound * 32 + 127) / 128);
         msm_heavy_fix_kernel<<<hgrid < 2368 ? hgrid : 2368, 128, 0, tail>>>(heavy, heavy_cnt, g, (uint32_t)w_lo * p.B, segoff,
-                                                                            segsums, buckets);
+                                                                            segsums, carry, buckets);
         CBP_LAUNCH_CHECK(); nl++;
+        if (no_tail) continue;  // the buckets now hold this chunk too; reduction happens after the last chunk
         // reduction levels for this group's windows
         const uint32_t n1 = (p.B + kReduceM - 1) / kReduceM;  // per-window slice of the ping-pong buffers
         const uint8_t* X = buckets + (size_t)w_lo * p.B * 128;

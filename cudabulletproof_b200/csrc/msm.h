@@ -27,7 +27,13 @@ void msm_make_plan(MsmPlan* p, size_t n, int c /* 0 = auto */);
 // kit_index < kMsmKits selects the set of internal side streams: MSMs that are in flight at the same time
 // on one device (the chunked host path) must use different sets and different workspaces.
 constexpr int kMsmKits = 3;
+// flags, for inputs that arrive in chunks (all chunks share one workspace and one plan, processed in stream
+// order): kMsmCarryIn — the bucket sums in the workspace already hold earlier chunks, add this one into them;
+// kMsmNoTail — stop once the buckets are updated (no reduction, no result).  The last chunk passes
+// kMsmCarryIn alone and produces the result for the whole input.
+constexpr int kMsmCarryIn = 1, kMsmNoTail = 2;
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
-            int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready, int kit_index = 0);
+            int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready, int kit_index = 0,
+            int flags = 0);
 
 }  // namespace cbp

@@ -95,7 +95,7 @@ def test_msm_empty_and_mismatch(capfd):
     assert "Vector lengths must match" in capfd.readouterr().err
 
 
-@pytest.mark.parametrize("window_bits", [4, 7, 11, 13, 16])
+@pytest.mark.parametrize("window_bits", [4, 7, 11, 13, 15, 16])
 def test_msm_all_window_sizes_agree(oracle, window_bits):
     import torch
     import cudabulletproof_b200 as cbp
@@ -181,3 +181,20 @@ def test_msm_host_pointer_chunked_upload(oracle):
     # and it agrees with the device-resident single MSM
     dev = cbp.Msm(n)(sc, pts).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, dev)
+
+
+def test_msm_host_pointer_chunked_equal_scalars(oracle):
+    """chunks add into shared buckets (carry-in): with all scalars equal every chunk hits the same, split
+    ("heavy") buckets, so the carry path of the split-bucket kernels is exercised"""
+    import cudabulletproof_b200 as cbp
+    n = (1 << 20) + 777
+    pts, ks = cbp.synth_points(n, seed=0xE2F)
+    k = 0x0F1E2D3C4B5A69788796A5B4C3D2E1F00123456789ABCDEFFEDCBA9876543210 % (2**253)
+    h_pts = pts.cpu().numpy().view(np.uint64).reshape(n, 16)
+    h_sc = np.tile(np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint64), (n, 1))
+    got = cbp.cuda_point_vector_multi_scalar_mul(h_sc, h_pts)
+    total = int(ks.cpu().numpy().astype(np.uint64).astype(object).sum()) % L
+    want = np.zeros(16, dtype=np.uint64)
+    oracle.ge25519_scalarmult_base(ob.ptr(want), ((k % L) * total % L).to_bytes(32, "little"))
+    oracle.ge25519_normalize(ob.ptr(want))
+    assert np.array_equal(got, want)

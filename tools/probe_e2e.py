@@ -11,7 +11,7 @@ h_p = torch.empty((n, 128), dtype=torch.uint8).pin_memory(); h_p.copy_(pts)
 h_s = torch.empty((n, 32), dtype=torch.uint8).pin_memory(); h_s.copy_(sc)
 hp = h_p.numpy().view(np.uint64).reshape(n, 16)
 hs = h_s.numpy().view(np.uint64).reshape(n, 4)
-for lg in (17, 18, 19, 20, 21):
+for lg in (17, 18):
     os.environ["CBP_HOST_CHUNK_LOG2"] = str(lg)
     for _ in range(3):
         cbp.cuda_point_vector_multi_scalar_mul(hs, hp)
