@@ -342,7 +342,14 @@ def run_cuda(args):
         gam = rng.integers(0, 2**63, size=(distinct, 4), dtype=np.uint64)
         gam[:, 3] &= np.uint64((1 << 59) - 1)
         seeds = np.arange(distinct, dtype=np.uint64) + np.uint64(100000 * rank)
+        base = cbp.range_prove_batch(gens, vals, gam, seeds)  # also warms the prover up
+        torch.cuda.synchronize()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
         base = cbp.range_prove_batch(gens, vals, gam, seeds)
+        pe1.record()
+        torch.cuda.synchronize()
+        prove_ms = pe0.elapsed_time(pe1)
         reps = (m + distinct - 1) // distinct
         proofs = base.repeat(reps, 1)[:m].contiguous()
         bad = rng.choice(m, size=max(1, m // 100), replace=False)  # 1 % tampered: one bit flipped
@@ -410,6 +417,9 @@ def run_cuda(args):
         return {"metric": "range_proof_verifies_per_sec", "value": world * m * vsteps / (ms * 1e-3), "unit": "verifies/s",
                 "ms_per_step": ms / vsteps, "steps": vsteps, "proofs_per_gpu": m, "distinct_proofs": distinct,
                 "tampered": len(bad), "decisions_correct": ok, "gpu_launches": int(launches), "roofline": roofline,
+                "prover": {"proofs_per_s": distinct / (prove_ms * 1e-3), "ms": prove_ms, "proofs": distinct,
+                           "note": "bpk_range_prove_batch_device, 64-bit proofs, byte-identical to the CPU oracle's "
+                                   "(host-to-device copy of values / blinding factors included)"},
                 "e2e": {"value": world * m * vsteps / (e2e_ms * 1e-3), "unit": "verifies/s",
                         "h2d_bytes_per_step": int(proofs.numel()), "d2h_bytes_per_step": m,
                         "api": "bpk_range_verify_batch_device on records staged from pinned host memory"},
@@ -418,8 +428,63 @@ def run_cuda(args):
                                        f"{distinct} distinct proofs; generator tables with {args.fixed_window_bits}-bit windows"},
                 "fixed_window_bits": args.fixed_window_bits}
 
+    # ---------------- the HBM-bound rows of SURVEY.md §8d (rank 0, one pass each, inputs larger than L2) ----------------
+    def bench_other_ops():
+        cnt = 1 << 22  # 128 MiB per array of field elements
+        a = cbp.synth_scalars(cnt, seed=0xF1E1D, bits=253, device=dev)
+        b = cbp.synth_scalars(cnt, seed=0xF1E1E, bits=253, device=dev)
+        o = torch.empty_like(a)
+        pts, _ = cbp.synth_points(1 << 20, seed=0xC0DEC, device=dev)
+        enc = torch.empty((1 << 20, 32), dtype=torch.uint8, device=dev)
+        back = torch.empty_like(pts)
+        okm = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+        wsb = C.c_size_t(0)
+        lib.bpk_sc_inner_product_workspace_bytes(cnt, C.byref(wsb))
+        ws = torch.empty(max(1, wsb.value), dtype=torch.uint8, device=dev)
+        ip = torch.empty(32, dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def timed(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        rows = {}
+
+        def hbm_row(name, fn, nbytes, units, imad_per_unit):
+            ms = timed(fn)
+            rows[name] = {"ms": ms, "GB/s": nbytes / (ms * 1e-3) / 1e9, "frac_hbm": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                          "units_per_s": units / (ms * 1e-3),
+                          "frac_int": units * imad_per_unit / (ms * 1e-3) / 1e12 / INT_PEAK_TIMAD, "units": units}
+
+        hbm_row("fe_batch_add", lambda: lib.bpk_fe_batch_device(0, o.data_ptr(), a.data_ptr(), b.data_ptr(), cnt, st), 96 * cnt, cnt, 0)
+        hbm_row("fe_batch_mul", lambda: lib.bpk_fe_batch_device(2, o.data_ptr(), a.data_ptr(), b.data_ptr(), cnt, st), 96 * cnt, cnt, 72)
+        hbm_row("fe_batch_square", lambda: lib.bpk_fe_batch_device(3, o.data_ptr(), a.data_ptr(), a.data_ptr(), cnt, st), 64 * cnt, cnt, 44)
+        hbm_row("fe_batch_invert", lambda: lib.bpk_fe_batch_invert_device(o.data_ptr(), a.data_ptr(), cnt, None, 0, st), 128 * cnt, cnt,
+                3 * 72)
+        hbm_row("sc_inner_product", lambda: lib.bpk_sc_inner_product_device(ip.data_ptr(), a.data_ptr(), b.data_ptr(), cnt,
+                                                                            ws.data_ptr(), ws.numel(), st), 64 * cnt, cnt, 64)
+        hbm_row("point_pack", lambda: lib.bpk_point_pack_device(enc.data_ptr(), pts.data_ptr(), 1 << 20, st), 224 * (1 << 20), 1 << 20,
+                5 * 72)
+        hbm_row("point_unpack", lambda: lib.bpk_point_unpack_device(back.data_ptr(), okm.data_ptr(), enc.data_ptr(), 1 << 20, st),
+                160 * (1 << 20), 1 << 20, 253 * 44 + 25 * 72)
+        return {"note": "one kernel pass each on arrays larger than L2; bytes are algorithmic (SURVEY.md section 8d), "
+                        f"HBM peak {hbm_peak:.0f} GB/s ({peak_src}), integer peak {INT_PEAK_TIMAD} T IMAD.WIDE/s", "rows": rows}
+
     msm_res = bench_msm() if args.workload in ("msm", "both") else None
     ver_res = bench_verify() if args.workload in ("verify", "both") else None
+    other = None
+    if rank == 0 and world == 1 and args.workload == "both":
+        try:
+            other = bench_other_ops()
+        except Exception as ex:  # never lose the headline numbers over the side table
+            other = {"error": repr(ex)}
 
     if rank == 0:
         cpu = None
@@ -449,6 +514,8 @@ def run_cuda(args):
                     "result_xy": msm_res["result_xy"]}
             if ver_res is not None:
                 line["secondary"] = ver_res
+            if other is not None:
+                line["other_ops"] = other
         else:
             line = dict(ver_res)
             line.update({"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",

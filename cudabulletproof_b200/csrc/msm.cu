@@ -788,6 +788,9 @@ StreamKit* stream_kit(int idx) {
 }
 }  // namespace
 
+// Measured and rejected: sorting the lower half of the windows on a side stream while the upper half is being
+// accumulated.  The exposed front end shrinks (0.50 -> 0.34 ms) but the accumulation, whose table gathers
+// share the L2 with the sort's atomics, slows down by the same amount (1.48 -> 1.69 ms): 2.29 ms either way.
 // windows are processed top-down in groups of halving size (.., 4, 2, 1, 1): while the lower groups are
 // still being accumulated, the upper groups are reduced and folded into the Horner chain on a second
 // stream, so only the last (single-window) group's reduction latency is exposed.
