@@ -19,6 +19,12 @@
 
 namespace cbp {
 
+// Out-of-line copies: the prover kernel is one long straight-line program per proof (31 scalar-multiplication
+// sites, 14 fixed-base sums); fully inlined it was 870 KB of SASS and bound by instruction fetch.
+static __device__ __noinline__ void sc_mul_nf(sc& r, const sc& a, const sc& b) { sc_mul(r, a, b); }
+static __device__ __noinline__ void ge_normalize_nf(ge_p3& p) { ge_normalize(p); }
+static __device__ __noinline__ void ge_add_nf(ge_p3& r, const ge_p3& p, const ge_p3& q) { ge_add(r, p, q); }
+
 static constexpr int kPThreads = 128;
 
 __device__ __forceinline__ uint64_t sm64_at(uint64_t seed, uint64_t idx) {
@@ -58,7 +64,7 @@ __device__ __forceinline__ void cta_sc_sum(sc& v, sc* sred) {
     __syncthreads();
 }
 // sum over all rows of digits * table, normalised, valid in thread 0 (and stored to out, 128 B)
-__device__ __forceinline__ void cta_fixed_msm(ge_p3& result, const FixTab& table, int nrows,
+static __device__ __noinline__ void cta_fixed_msm(ge_p3& result, const FixTab& table, int nrows,
                                               int8_t (*digits)[kFixRowBytes], ge_p3* red) {
     ge_p3 acc;
     ge_p3_0(acc);
@@ -67,7 +73,7 @@ __device__ __forceinline__ void cta_fixed_msm(ge_p3& result, const FixTab& table
         fixed_base_madd(acc, table, (uint32_t)row, win, digits[row]);
     }
     cta_point_sum(acc, red);
-    if (threadIdx.x == 0) ge_normalize(acc);
+    if (threadIdx.x == 0) ge_normalize_nf(acc);
     result = acc;
 }
 __device__ __forceinline__ void zero_row(int8_t* row) {
@@ -209,14 +215,14 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         sh_ypow[0] = y;
         sh_yinvpow[0] = yi;
         for (int m = 1; m <= k; m++) {
-            sc_mul(sh_ypow[m], sh_ypow[m - 1], sh_ypow[m - 1]);
-            sc_mul(sh_yinvpow[m], sh_yinvpow[m - 1], sh_yinvpow[m - 1]);
+            sc_mul_nf(sh_ypow[m], sh_ypow[m - 1], sh_ypow[m - 1]);
+            sc_mul_nf(sh_yinvpow[m], sh_yinvpow[m - 1], sh_yinvpow[m - 1]);
         }
     }
     __syncthreads();
     // ---- l(X) = l0 + l1 X, r(X) = r0 + r1 X and t0, t1, t2 ----
     sc z = sh_z, z2, l0, r0, r1, yi_pow, yinv_pow;
-    sc_mul(z2, z, z);
+    sc_mul_nf(z2, z, z);
     sc_set0(l0);
     sc_set0(r0);
     sc_set0(r1);
@@ -225,8 +231,8 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     if (t < (int)n) {
         for (int m = 0; m < k; m++) {
             if ((t >> m) & 1) {
-                sc_mul(yi_pow, yi_pow, sh_ypow[m]);
-                sc_mul(yinv_pow, yinv_pow, sh_yinvpow[m]);
+                sc_mul_nf(yi_pow, yi_pow, sh_ypow[m]);
+                sc_mul_nf(yinv_pow, yinv_pow, sh_yinvpow[m]);
             }
         }
         sc two_i, tmp;
@@ -234,19 +240,19 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         two_i.v[t >> 5] = 1u << (t & 31);
         sc_sub(l0, aL, z);
         sc_add(tmp, aR, z);
-        sc_mul(tmp, tmp, yi_pow);
-        sc_mul(two_i, z2, two_i);
+        sc_mul_nf(tmp, tmp, yi_pow);
+        sc_mul_nf(two_i, z2, two_i);
         sc_add(r0, tmp, two_i);
-        sc_mul(r1, yi_pow, sR);
+        sc_mul_nf(r1, yi_pow, sR);
     }
     sc t0, t1, t2, tmp, tmp2;
-    sc_mul(t0, l0, r0);
+    sc_mul_nf(t0, l0, r0);
     cta_sc_sum(t0, sred);
-    sc_mul(tmp, l0, r1);
-    sc_mul(tmp2, sL, r0);
+    sc_mul_nf(tmp, l0, r1);
+    sc_mul_nf(tmp2, sL, r0);
     sc_add(t1, tmp, tmp2);
     cta_sc_sum(t1, sred);
-    sc_mul(t2, sL, r1);
+    sc_mul_nf(t2, sL, r1);
     cta_sc_sum(t2, sred);
     // ---- T1 = t1 g + tau1 h, T2 = t2 g + tau2 h ----
     for (int r = t; r < nrows; r += kPThreads) zero_row(digits[r]);
@@ -282,23 +288,23 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     }
     __syncthreads();
     sc x = sh_x, x2, tt, taux, mu;
-    sc_mul(x2, x, x);
-    sc_mul(tmp, t1, x);
-    sc_mul(tmp2, t2, x2);
+    sc_mul_nf(x2, x, x);
+    sc_mul_nf(tmp, t1, x);
+    sc_mul_nf(tmp2, t2, x2);
     sc_add(tt, t0, tmp);
     sc_add(tt, tt, tmp2);
-    sc_mul(tmp, tau1, x);
-    sc_mul(tmp2, tau2, x2);
+    sc_mul_nf(tmp, tau1, x);
+    sc_mul_nf(tmp2, tau2, x2);
     sc_add(taux, tmp, tmp2);
-    sc_mul(tmp, z2, gamma);
+    sc_mul_nf(tmp, z2, gamma);
     sc_add(taux, taux, tmp);
-    sc_mul(tmp, rho, x);
+    sc_mul_nf(tmp, rho, x);
     sc_add(mu, alpha, tmp);
     if (t < (int)n) {
         sc a, b;
-        sc_mul(tmp, sL, x);
+        sc_mul_nf(tmp, sL, x);
         sc_add(a, l0, tmp);
-        sc_mul(tmp, r1, x);
+        sc_mul_nf(tmp, r1, x);
         sc_add(b, r0, tmp);
         sa[t] = a;
         sb[t] = b;
@@ -326,8 +332,8 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         sc_set0(cL);
         sc_set0(cR);
         if (t < np) {
-            sc_mul(cL, sa[t], sb[t + np]);
-            sc_mul(cR, sa[t + np], sb[t]);
+            sc_mul_nf(cL, sa[t], sb[t + np]);
+            sc_mul_nf(cR, sa[t + np], sb[t]);
         }
         cta_sc_sum(cL, sred);
         cta_sc_sum(cR, sred);
@@ -338,8 +344,8 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
                 sc_set0(cg);
                 sc_set0(ch);
                 bool g_on = side == 0 ? hi : !hi;  // L uses G_R and H_L; R uses G_L and H_R
-                if (g_on) sc_mul(cg, sa[side == 0 ? m - np : m + np], swG[t]);
-                else sc_mul(ch, sb[side == 0 ? m + np : m - np], swH[t]);
+                if (g_on) sc_mul_nf(cg, sa[side == 0 ? m - np : m + np], swG[t]);
+                else sc_mul_nf(ch, sb[side == 0 ? m + np : m - np], swH[t]);
                 fix_recode(digits[t], cg, table.wbits);
                 fix_recode(digits[n + t], ch, table.wbits);
             }
@@ -379,11 +385,11 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         __syncthreads();
         sc u = sh_u, ui = sh_uinv, na, nb;
         if (t < np) {  // a' = u a_L + u^-1 a_R ; b' = u^-1 b_L + u b_R
-            sc_mul(tmp, u, sa[t]);
-            sc_mul(tmp2, ui, sa[t + np]);
+            sc_mul_nf(tmp, u, sa[t]);
+            sc_mul_nf(tmp2, ui, sa[t + np]);
             sc_add(na, tmp, tmp2);
-            sc_mul(tmp, ui, sb[t]);
-            sc_mul(tmp2, u, sb[t + np]);
+            sc_mul_nf(tmp, ui, sb[t]);
+            sc_mul_nf(tmp2, u, sb[t + np]);
             sc_add(nb, tmp, tmp2);
         }
         __syncthreads();
@@ -393,8 +399,8 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         }
         if (t < (int)n) {  // G' = u^-1 G_L + u G_R ; H' = u H_L + u^-1 H_R as weight updates
             sc wg = swG[t], wh = swH[t];
-            sc_mul(wg, wg, hi ? u : ui);
-            sc_mul(wh, wh, hi ? ui : u);
+            sc_mul_nf(wg, wg, hi ? u : ui);
+            sc_mul_nf(wh, wh, hi ? ui : u);
             swG[t] = wg;
             swH[t] = wh;
         }
