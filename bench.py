@@ -466,8 +466,13 @@ def run_cuda(args):
         hbm_row("fe_batch_add", lambda: lib.bpk_fe_batch_device(0, o.data_ptr(), a.data_ptr(), b.data_ptr(), cnt, st), 96 * cnt, cnt, 0)
         hbm_row("fe_batch_mul", lambda: lib.bpk_fe_batch_device(2, o.data_ptr(), a.data_ptr(), b.data_ptr(), cnt, st), 96 * cnt, cnt, 72)
         hbm_row("fe_batch_square", lambda: lib.bpk_fe_batch_device(3, o.data_ptr(), a.data_ptr(), a.data_ptr(), cnt, st), 64 * cnt, cnt, 44)
-        hbm_row("fe_batch_invert", lambda: lib.bpk_fe_batch_invert_device(o.data_ptr(), a.data_ptr(), cnt, None, 0, st), 128 * cnt, cnt,
-                3 * 72)
+        iwb = C.c_size_t(0)
+        lib.bpk_fe_batch_invert_workspace_bytes(cnt, C.byref(iwb))
+        iws = torch.empty(max(1, iwb.value), dtype=torch.uint8, device=dev)
+        hbm_row("fe_batch_invert", lambda: lib.bpk_fe_batch_invert_device(o.data_ptr(), a.data_ptr(), cnt, iws.data_ptr(), iws.numel(), st),
+                128 * cnt, cnt, 3 * 72)
+        hbm_row("fe_batch_invert_single_kernel", lambda: lib.bpk_fe_batch_invert_device(o.data_ptr(), a.data_ptr(), cnt, None, 0, st),
+                128 * cnt, cnt, 3 * 72)
         hbm_row("sc_inner_product", lambda: lib.bpk_sc_inner_product_device(ip.data_ptr(), a.data_ptr(), b.data_ptr(), cnt,
                                                                             ws.data_ptr(), ws.numel(), st), 64 * cnt, cnt, 64)
         hbm_row("point_pack", lambda: lib.bpk_point_pack_device(enc.data_ptr(), pts.data_ptr(), 1 << 20, st), 224 * (1 << 20), 1 << 20,

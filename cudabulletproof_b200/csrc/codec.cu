@@ -14,7 +14,8 @@
 
 namespace cbp {
 
-int fe_batch_invert_strided(uint8_t* d_out, const uint8_t* d_in, size_t in_stride, size_t count, cudaStream_t st);
+int fe_batch_invert_strided(uint8_t* d_out, const uint8_t* d_in, size_t in_stride, size_t count, cudaStream_t st,
+                            uint8_t* d_ws, size_t ws_bytes);
 
 // out[i] holds 1/Z_i on entry (0 for Z = 0, as fe25519_invert gives) and the encoding on exit
 __global__ void __launch_bounds__(256) point_pack_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ pts,
@@ -190,7 +191,7 @@ int bpk_point_pack_device(void* d_out, const void* d_points, size_t count, void*
     if (!d_out || !d_points) return fail(BPK_ERR_ARG);
     cudaStream_t st = (cudaStream_t)stream;
     // 1/Z for the whole array with one field inversion per 4096 points, parked in the output buffer
-    int rc = fe_batch_invert_strided((uint8_t*)d_out, (const uint8_t*)d_points + 64, 128, count, st);
+    int rc = fe_batch_invert_strided((uint8_t*)d_out, (const uint8_t*)d_points + 64, 128, count, st, nullptr, 0);
     if (rc != BPK_OK) return rc;
     point_pack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((uint8_t*)d_out, (const uint8_t*)d_points, count);
     CBP_CHECK_LAUNCH();

@@ -106,3 +106,27 @@ def test_inner_product_length_mismatch_leaves_result_untouched(capfd):
     cbp.cuda_field_vector_inner_product(a, b, result=res)
     assert (res == 0xDEADBEEF).all()
     assert "Vector lengths must match" in capfd.readouterr().err
+
+
+@pytest.mark.parametrize("count", [1 << 16, (1 << 18) + 12345])
+def test_batch_invert_tree_path_matches_single_kernel_and_python(count):
+    """large arrays with a workspace take the multi-level Montgomery tree; it must give the same canonical
+    bytes as the single-kernel path (which is pinned to the oracle above), zeros included"""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    a = cbp.synth_scalars(count, seed=0x1A7 + count, bits=255)
+    a[7] = 0  # inv(0) = 0
+    a[count - 1] = 0
+    nb = C.c_size_t(0)
+    assert lib.bpk_fe_batch_invert_workspace_bytes(count, C.byref(nb)) == 0 and nb.value > 0
+    ws = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+    tree, single = torch.empty_like(a), torch.empty_like(a)
+    assert lib.bpk_fe_batch_invert_device(tree.data_ptr(), a.data_ptr(), count, ws.data_ptr(), ws.numel(), None) == 0
+    assert lib.bpk_fe_batch_invert_device(single.data_ptr(), a.data_ptr(), count, None, 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(tree, single)
+    h_a, h_o = a.cpu().numpy().view(np.uint64).reshape(count, 4), tree.cpu().numpy().view(np.uint64).reshape(count, 4)
+    for i in [0, 1, 7, 255, 256, 4095, 4096, count // 2, count - 2, count - 1]:
+        v = ob.fe_to_int(h_a[i]) % P
+        assert ob.fe_to_int(h_o[i]) == (pow(v, P - 2, P) if v else 0)
