@@ -262,7 +262,7 @@ __device__ __forceinline__ void ge_warp_sum(ge_p3& v) {  // result in lane 0
 // partially filled top window receives half of all points) and, because segments are then ordered by
 // length (counting sort, longest first, grouped by window group), the 32 segments of a warp run in
 // lockstep instead of waiting for the longest of 32 Poisson-distributed runs.
-static constexpr uint32_t kMinSegLen = 64;  // segment length = max(64, 2 * mean run length), a power of two
+// segment length = max(64, 2 * mean run length), a power of two (msm_make_plan)
 static constexpr int kSegBinsPerGroup = 65;  // length classes ceil(64 len / seglen), longest first
 static constexpr int kSegBins = 1024;  // >= kMaxGroups * kSegBinsPerGroup, = threads of the bin scan
 

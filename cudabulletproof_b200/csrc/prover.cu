@@ -22,10 +22,39 @@ namespace cbp {
 // Out-of-line copies: the prover kernel is one long straight-line program per proof (31 scalar-multiplication
 // sites, 14 fixed-base sums); fully inlined it was 870 KB of SASS and bound by instruction fetch.
 static __device__ __noinline__ void sc_mul_nf(sc& r, const sc& a, const sc& b) { sc_mul(r, a, b); }
-static __device__ __noinline__ void ge_normalize_nf(ge_p3& p) { ge_normalize(p); }
-static __device__ __noinline__ void ge_add_nf(ge_p3& r, const ge_p3& p, const ge_p3& q) { ge_add(r, p, q); }
+// normalise up to three points with ONE field inversion (Montgomery); same canonical results as ge_normalize
+static __device__ __noinline__ void ge_normalize_many(ge_p3* pts, int cnt) {
+    fe z01, z012, inv, zi[3];
+    if (cnt == 1) {
+        fe_invert(zi[0], pts[0].Z);
+    } else {
+        fe_mul(z01, pts[0].Z, pts[1].Z);
+        if (cnt == 3) fe_mul(z012, z01, pts[2].Z);
+        else z012 = z01;
+        fe_invert(inv, z012);
+        if (cnt == 3) {
+            fe_mul(zi[2], inv, z01);
+            fe_mul(inv, inv, pts[2].Z);
+        }
+        fe_mul(zi[1], inv, pts[0].Z);
+        fe_mul(zi[0], inv, pts[1].Z);
+    }
+    for (int i = 0; i < cnt; i++) {
+        fe x, y;
+        fe_mul(x, pts[i].X, zi[i]);
+        fe_mul(y, pts[i].Y, zi[i]);
+        fe_canon(x);
+        fe_canon(y);
+        pts[i].X = x;
+        pts[i].Y = y;
+        fe_set1(pts[i].Z);
+        fe_mul(pts[i].T, x, y);
+        fe_canon(pts[i].T);
+    }
+}
 
-static constexpr int kPThreads = 128;
+static constexpr int kPThreads = 64;  // = kMaxN: one thread per vector element; small CTAs keep more proofs per SM in
+                                      // flight, which is what hides the serial sections (hashes, inversions)
 
 __device__ __forceinline__ uint64_t sm64_at(uint64_t seed, uint64_t idx) {
     uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
@@ -63,7 +92,7 @@ __device__ __forceinline__ void cta_sc_sum(sc& v, sc* sred) {
     v = sred[0];
     __syncthreads();
 }
-// sum over all rows of digits * table, normalised, valid in thread 0 (and stored to out, 128 B)
+// sum over all rows of digits * table, NOT normalised, valid in thread 0
 static __device__ __noinline__ void cta_fixed_msm(ge_p3& result, const FixTab& table, int nrows,
                                               int8_t (*digits)[kFixRowBytes], ge_p3* red) {
     ge_p3 acc;
@@ -73,7 +102,6 @@ static __device__ __noinline__ void cta_fixed_msm(ge_p3& result, const FixTab& t
         fixed_base_madd(acc, table, (uint32_t)row, win, digits[row]);
     }
     cta_point_sum(acc, red);
-    if (threadIdx.x == 0) ge_normalize_nf(acc);
     result = acc;
 }
 __device__ __forceinline__ void zero_row(int8_t* row) {
@@ -85,16 +113,16 @@ __device__ __forceinline__ void hash_xy(Sha256& sh, const ge_p3& P) {  // P norm
     sh.update_words(P.Y.v);
 }
 
-__global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* __restrict__ gens,
+__global__ void __launch_bounds__(kPThreads, 8) range_prove_kernel(const uint8_t* __restrict__ gens,
                                                                 const uint64_t* __restrict__ values,
                                                                 const uint8_t* __restrict__ gammas,
                                                                 const uint64_t* __restrict__ seeds, uint32_t n, int k,
                                                                 uint8_t* __restrict__ proofs, size_t rec_bytes) {
-    __shared__ sc sa[kMaxN], sb[kMaxN], swG[kMaxN], swH[kMaxN], sl1[kMaxN], sr1[kMaxN];
+    __shared__ sc sa[kMaxN], sb[kMaxN], swG[kMaxN], swH[kMaxN];
     __shared__ sc sred[kPThreads];
     __shared__ __align__(16) int8_t digits[2 * kMaxN + 2][kFixRowBytes];
     __shared__ ge_p3 red[kPThreads];
-    __shared__ sc sh_y, sh_z, sh_x, sh_u, sh_uinv, sh_yinv;
+    __shared__ sc sh_z, sh_x, sh_u, sh_uinv;
     __shared__ sc sh_ypow[kMaxK + 1], sh_yinvpow[kMaxK + 1];
     __shared__ uint32_t sh_tr[8];
     __shared__ ge_p3 sh_pts[3];
@@ -152,10 +180,7 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     }
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
-    if (t == 0) {
-        ge_store(rec + kRecV, P);
-        sh_pts[0] = P;
-    }
+    if (t == 0) sh_pts[0] = P;
     __syncthreads();
     // ---- A = alpha h + <aL, G> + <aR, H> (:1267-1276) ----
     if (t < (int)n) {
@@ -168,10 +193,7 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     }
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
-    if (t == 0) {
-        ge_store(rec + kRecA, P);
-        sh_pts[1] = P;
-    }
+    if (t == 0) sh_pts[1] = P;
     __syncthreads();
     // ---- S = rho h + <sL, G> + <sR, H> (:1279-1288) ----
     if (t < (int)n) {
@@ -182,8 +204,11 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
     if (t == 0) {
-        ge_store(rec + kRecS, P);
         sh_pts[2] = P;
+        ge_normalize_many(sh_pts, 3);  // V, A, S with one inversion
+        ge_store(rec + kRecV, sh_pts[0]);
+        ge_store(rec + kRecA, sh_pts[1]);
+        ge_store(rec + kRecS, sh_pts[2]);
         // y, z challenges
         Sha256 sh;
         uint32_t yb[8], zb[8];
@@ -209,9 +234,7 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
         sc_reduce(y, ty);
         sc_reduce(z, tz);
         sc_invert(yi, y);
-        sh_y = y;
         sh_z = z;
-        sh_yinv = yi;
         sh_ypow[0] = y;
         sh_yinvpow[0] = yi;
         for (int m = 1; m <= k; m++) {
@@ -264,7 +287,6 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
     if (t == 0) {
-        ge_store(rec + kRecT1, P);
         sh_pts[0] = P;
         fix_recode(digits[row_g], t2, table.wbits);
         fix_recode(digits[row_h], tau2, table.wbits);
@@ -272,13 +294,16 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
     __syncthreads();
     cta_fixed_msm(P, table, nrows, digits, red);
     if (t == 0) {
-        ge_store(rec + kRecT2, P);
+        sh_pts[1] = P;
+        ge_normalize_many(sh_pts, 2);  // T1, T2 with one inversion
+        ge_store(rec + kRecT1, sh_pts[0]);
+        ge_store(rec + kRecT2, sh_pts[1]);
         Sha256 sh;
         uint32_t xb[8];
         sh.init();
         sh.update_str("BulletproofXChal", 16);
         hash_xy(sh, sh_pts[0]);
-        hash_xy(sh, P);
+        hash_xy(sh, sh_pts[1]);
         sh.update_str("xcha", 4);
         sh.final_challenge(xb);
         sc tx;
@@ -355,13 +380,13 @@ __global__ void __launch_bounds__(kPThreads) range_prove_kernel(const uint8_t* _
             }
             __syncthreads();
             cta_fixed_msm(P, table, nrows, digits, red);
-            if (t == 0) {
-                ge_store(rec + kRecL + (size_t)(side == 0 ? r : k + r) * 128, P);
-                sh_pts[side] = P;
-            }
+            if (t == 0) sh_pts[side] = P;
             __syncthreads();
         }
         if (t == 0) {
+            ge_normalize_many(sh_pts, 2);  // L_r, R_r with one inversion
+            ge_store(rec + kRecL + (size_t)r * 128, sh_pts[0]);
+            ge_store(rec + kRecL + (size_t)(k + r) * 128, sh_pts[1]);
             Sha256 sh;
             uint32_t ub[8];
             sh.init();
