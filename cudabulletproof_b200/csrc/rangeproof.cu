@@ -625,6 +625,7 @@ static int gens_wbits_of(const void* d_gens_ws) {
     auto it = g_gens_wbits.find(d_gens_ws);
     return it == g_gens_wbits.end() ? 0 : it->second;
 }
+int bpk_gens_window_bits(const void* d_gens_ws) { return gens_wbits_of(d_gens_ws); }
 
 int bpk_gens_init_device_ex(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
                             const void* d_h, size_t n, int window_bits, void* stream) {

@@ -218,8 +218,11 @@ def range_prove_batch(gens, values, gammas, seeds, stream=None):
     d_s = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(gens.device)
     d_g = torch.from_numpy(np.ascontiguousarray(gammas, dtype=np.uint64).view(np.uint8).reshape(-1)).to(gens.device)
     out = torch.zeros((m, gens.record_bytes), dtype=torch.uint8, device=gens.device)
+    nbytes = C.c_size_t(0)
+    _check(_lib().bpk_range_prove_workspace_bytes(gens.n, m, C.byref(nbytes)), "bpk_range_prove_workspace_bytes")
+    ws = _dev_u8(max(1, nbytes.value), gens.device)  # batches of 64+ proofs take the phase-split prover
     _check(_lib().bpk_range_prove_batch_device(gens.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(),
-                                               d_s.data_ptr(), gens.n, m, out.data_ptr(), None, 0,
+                                               d_s.data_ptr(), gens.n, m, out.data_ptr(), ws.data_ptr(), nbytes.value,
                                                _stream_ptr(stream)), "bpk_range_prove_batch_device")
     torch.cuda.current_stream().synchronize()
     return out

@@ -117,6 +117,8 @@ size_t bpk_proof_record_bytes(size_t n);
 int bpk_gens_workspace_bytes(size_t n, size_t* bytes);
 int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
                          const void* d_h, size_t n, void* stream);
+/* window width (8 or 16) of a table built in this process, 0 if d_gens_ws is unknown */
+int bpk_gens_window_bits(const void* d_gens_ws);
 int bpk_gens_workspace_bytes_ex(size_t n, int window_bits, size_t* bytes);
 int bpk_gens_init_device_ex(void* d_gens_ws, size_t ws_bytes, const void* d_G, const void* d_H, const void* d_g,
                             const void* d_h, size_t n, int window_bits, void* stream);

@@ -305,3 +305,44 @@ def test_ipa_n4096_config4(oracle):
     proof.a.elements[0].limbs[0] ^= 1
     assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
     oracle.inner_product_proof_free(C.byref(proof))
+
+
+@pytest.mark.parametrize("n,window_bits", [(16, 8), (64, 16), (32, 16)])
+def test_batched_prover_is_byte_identical(oracle, gens16, gens64, n, window_bits):
+    """Batches of 64+ proofs take the phase-split prover (batch inversions across proofs, one window per lane);
+    its records must equal the one-CTA-per-proof kernel's byte for byte (which is pinned to the oracle above),
+    and a few are compared with the oracle directly.  n = 16 includes an out-of-range value."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    g = gens16 if n == 16 else gens64 if n == 64 else Gens(oracle, 32)
+    dg = dev_gens(g, window_bits)
+    m = 150
+    rng = random.Random(0xBA7C4 + n)
+    vals = [rng.getrandbits(n) for _ in range(m)]
+    if n == 16:
+        vals[5] = 65536  # config 1: must not yield a valid proof
+    seeds = list(range(7000, 7000 + m))
+    gam = ob.ints_to_fe([gamma_for(s) for s in seeds])
+    got = cbp.range_prove_batch(dg, vals, gam, seeds)  # workspace -> batched path
+    # the same inputs through the single-kernel path (no workspace)
+    d_v = torch.from_numpy(np.asarray(vals, dtype=np.uint64).view(np.int64)).cuda()
+    d_s = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).cuda()
+    d_g = torch.from_numpy(np.ascontiguousarray(gam, dtype=np.uint64).view(np.uint8).reshape(-1)).cuda()
+    ref = torch.zeros_like(got)
+    assert lib.bpk_range_prove_batch_device(dg.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(), d_s.data_ptr(), n, m,
+                                            ref.data_ptr(), None, 0, None) == 0
+    torch.cuda.synchronize()
+    diff = (got != ref).any(dim=1).nonzero().flatten().tolist()
+    if diff:
+        i = diff[0]
+        off = int((got[i] != ref[i]).nonzero()[0])
+        raise AssertionError(f"{len(diff)} records differ; first: proof {i}, byte offset {off}")
+    h = got.cpu().numpy()
+    for i in (0, 77, m - 1):
+        proof, V = oracle_prove(oracle, g, vals[i], seeds[i])
+        want = flatten_proof(proof, n).view(np.uint8)
+        assert np.array_equal(h[i], want)
+        oracle.range_proof_free(C.byref(proof))
+    acc = cbp.RangeVerifier(dg, m)(got).cpu().numpy().astype(bool)
+    assert acc.tolist() == [not (n == 16 and i == 5) for i in range(m)]
