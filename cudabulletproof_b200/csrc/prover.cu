@@ -545,9 +545,12 @@ __global__ void __launch_bounds__(128, 4) pb_fixed_msm_kernel(const uint8_t* __r
     constexpr uint32_t E = 1u << (WBITS - 1);
     const uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) / LP;
     const int win = threadIdx.x & (LP - 1);
-    const uint32_t p = unit / (uint32_t)nslots;
-    const int slot = (int)(unit % (uint32_t)nslots);
-    const bool live = p < num && ps[p < num ? p : 0].valid;
+    // slot-major: the lanes of a warp then work on the SAME sum of different proofs, whose zero rows coincide
+    // (in an IPA round L uses half of the G rows and R the other half: proof-major order ran every row at
+    // half the lanes)
+    const int slot = (int)(unit / num);
+    const uint32_t p = unit % num;
+    const bool live = slot < nslots && ps[p].valid;
     if (!__any_sync(0xffffffffu, live)) return;
     const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
     const uint8_t* table = gens + gh->table_off + (size_t)win * E * 96;
