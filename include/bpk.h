@@ -131,7 +131,10 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
                                   void* stream);
 /* deterministic batch prover (generate_range_proof, bulletproof_range_proof.cu:1159-1714, restated):
  * proof i commits d_values[i] (< 2^n) with blinding and nonces drawn from the SplitMix64 stream
- * seeded by d_seeds[i] — the same stream oracle/ref_corrected.c draws, so proofs are bit-identical. */
+ * seeded by d_seeds[i] — the same stream oracle/ref_corrected.c draws, so proofs are bit-identical.
+ * The workspace is optional: with bpk_range_prove_workspace_bytes() bytes (28 KB per proof, capped at 2^14
+ * proofs) batches of 64+ proofs run as a phase-split pipeline with batch inversions across proofs; with NULL
+ * every proof is one CTA.  Same bytes either way. */
 int bpk_range_prove_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes);
 int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas /* 32 B each */,
                                  const uint64_t* d_seeds, size_t n, size_t num_proofs, void* d_proofs,
