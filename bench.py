@@ -479,6 +479,20 @@ def run_cuda(args):
                 5 * 72)
         hbm_row("point_unpack", lambda: lib.bpk_point_unpack_device(back.data_ptr(), okm.data_ptr(), enc.data_ptr(), 1 << 20, st),
                 160 * (1 << 20), 1 << 20, 253 * 44 + 25 * 72)
+        # BASELINE config 4: one inner-product argument over n = 4096 generators (12 rounds) proved on the device
+        n_ipa = 4096
+        ig, _ = cbp.synth_points(2 * n_ipa + 1, seed=0xA66E0040, device=dev)
+        ia = cbp.synth_scalars(n_ipa, seed=0xA66E0041, bits=252, device=dev)
+        ib = cbp.synth_scalars(n_ipa, seed=0xA66E0042, bits=252, device=dev)
+        cbp.ipa_prove(ig[:n_ipa], ig[n_ipa:2 * n_ipa], ig[2 * n_ipa], ia, ib)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cbp.ipa_prove(ig[:n_ipa], ig[n_ipa:2 * n_ipa], ig[2 * n_ipa], ia, ib)
+        ipa_ms = (time.perf_counter() - t0) / 3 * 1e3
+        rows["ipa_prove_n4096"] = {"ms": ipa_ms, "rounds": 12,
+                                   "note": "bpk_ipa_prove_device: per round 2 inner products, 2 Pippenger MSMs of 2n'+1 points, "
+                                           "challenge hash + inversion, a/b and G/H folds; wall time incl. workspace allocation"}
         return {"note": "one kernel pass each on arrays larger than L2; bytes are algorithmic (SURVEY.md section 8d), "
                         f"HBM peak {hbm_peak:.0f} GB/s ({peak_src}), integer peak {INT_PEAK_TIMAD} T IMAD.WIDE/s", "rows": rows}
 

@@ -78,6 +78,8 @@ SIGNATURES = {
     "bpk_gens_derive_device": (_i, [_vp, C.c_char_p, C.c_uint32, _sz, _vp]),
     "bpk_debug_ge_op_device": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bpk_debug_const_operands_device": (_i, [_vp, _vp]),
+    "bpk_ipa_prove_workspace_bytes": (_i, [_sz, C.POINTER(_sz)]),
+    "bpk_ipa_prove_device": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, C.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bpk_gens_window_bits": (_i, [_vp]),
     "bpk_gens_workspace_bytes_ex": (_i, [_sz, _i, C.POINTER(_sz)]),
     "bpk_gens_init_device_ex": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _i, _vp]),

@@ -99,7 +99,7 @@ uint64_t bpk_kernel_launches(void) { return g_launches.load(); }
 
 int bpk_msm_window_bits(size_t n) { return msm_pick_window(n); }
 int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes) {
-    if (!bytes || window_bits < 0 || window_bits > 16 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
+    if (!bytes || window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
         return fail(BPK_ERR_ARG);
     MsmPlan p;
     msm_make_plan(&p, n, window_bits);
@@ -109,7 +109,7 @@ int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes) {
 int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* d_result, void* d_workspace,
                    size_t workspace_bytes, int window_bits, int normalize, void* stream) {
     if (!d_result || (n && (!d_scalars || !d_points || !d_workspace))) return fail(BPK_ERR_ARG);
-    if (window_bits < 0 || window_bits > 16 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
+    if (window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
         return fail(BPK_ERR_ARG);
     MsmPlan p;
     msm_make_plan(&p, n, window_bits);

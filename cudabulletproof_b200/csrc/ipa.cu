@@ -89,6 +89,90 @@ __global__ void __launch_bounds__(64) ipa_fold_points_kernel(uint8_t* G_out, uin
     ge_store((is_h ? H_out : G_out) + j * 128, r);
 }
 
+// ---- inner-product argument, prover side, any power-of-two width (inner_product_prove, ------------------
+// bulletproof_vectors.cu:375-509 restated; BASELINE config 4 is n = 4096, 12 rounds) -------------------------
+// Per round: c_L, c_R (mod-l inner products), L and R as ONE Pippenger MSM each over 2 n' + 1 points
+// (a_L x G_R, b_R x H_L, c_L x Q), the round challenge and its inverse, then the a/b and G/H folds above.
+__global__ void ipa_prove_setup_kernel(uint8_t* __restrict__ a, uint8_t* __restrict__ b, uint8_t* __restrict__ g,
+                                       uint8_t* __restrict__ h, const uint8_t* __restrict__ a_in,
+                                       const uint8_t* __restrict__ b_in, const uint8_t* __restrict__ G,
+                                       const uint8_t* __restrict__ H, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc t, r;
+    sc_load(t, a_in + i * 32);
+    sc_reduce(r, t);
+    sc_store(a + i * 32, r);
+    sc_load(t, b_in + i * 32);
+    sc_reduce(r, t);
+    sc_store(b + i * 32, r);
+    const uint4* gs = reinterpret_cast<const uint4*>(G + i * 128);
+    const uint4* hs = reinterpret_cast<const uint4*>(H + i * 128);
+    uint4* gd = reinterpret_cast<uint4*>(g + i * 128);
+    uint4* hd = reinterpret_cast<uint4*>(h + i * 128);
+    for (int q = 0; q < 8; q++) {
+        gd[q] = gs[q];
+        hd[q] = hs[q];
+    }
+}
+// side 0: L = <a_L, G_R> + <b_R, H_L> + c_L Q ; side 1: R = <a_R, G_L> + <b_L, H_R> + c_R Q
+__global__ void ipa_prove_gather_kernel(int side, size_t np, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                        const uint8_t* __restrict__ g, const uint8_t* __restrict__ h,
+                                        const uint8_t* __restrict__ Q, const uint8_t* __restrict__ c_side,
+                                        uint8_t* __restrict__ scal, uint8_t* __restrict__ pts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > np) return;
+    auto copy32 = [](uint8_t* d, const uint8_t* s_) {
+        const uint4* sp = reinterpret_cast<const uint4*>(s_);
+        uint4* dp = reinterpret_cast<uint4*>(d);
+        dp[0] = sp[0];
+        dp[1] = sp[1];
+    };
+    auto copy128 = [](uint8_t* d, const uint8_t* s_) {
+        const uint4* sp = reinterpret_cast<const uint4*>(s_);
+        uint4* dp = reinterpret_cast<uint4*>(d);
+        for (int q = 0; q < 8; q++) dp[q] = sp[q];
+    };
+    if (i == np) {
+        copy32(scal + 2 * np * 32, c_side);
+        copy128(pts + 2 * np * 128, Q);
+        return;
+    }
+    copy32(scal + i * 32, a + (side ? np + i : i) * 32);
+    copy32(scal + (np + i) * 32, b + (side ? i : np + i) * 32);
+    copy128(pts + i * 128, g + (side ? i : np + i) * 128);
+    copy128(pts + (np + i) * 128, h + (side ? np + i : i) * 128);
+}
+__global__ void ipa_prove_challenge_kernel(int round, uint8_t* __restrict__ tr, const uint8_t* __restrict__ Lr,
+                                           const uint8_t* __restrict__ Rr, uint8_t* __restrict__ x_out,
+                                           uint8_t* __restrict__ u_out, uint8_t* __restrict__ uinv_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fe lx, rx;
+    fe_load(lx, Lr);  // L, R are normalised: X is the affine x
+    fe_load(rx, Rr);
+    fe_canon(lx);
+    fe_canon(rx);
+    sc t0;
+    sc_load(t0, tr);
+    Sha256 sh;
+    uint32_t ub[8];
+    sh.init();
+    sh.update_str("InnerProductChal", 16);
+    sh.update_words(t0.v);
+    sh.update_words(lx.v);
+    sh.update_words(rx.v);
+    sh.final_challenge(ub);
+    sc raw, u, ui;
+#pragma unroll
+    for (int i = 0; i < 8; i++) raw.v[i] = ub[i];
+    sc_store(tr, raw);
+    if (round == 0) sc_store(x_out, raw);  // the first raw challenge is stored in the proof (:471-474)
+    sc_reduce(u, raw);
+    sc_invert(ui, u);
+    sc_store(u_out, u);
+    sc_store(uinv_out, ui);
+}
+
 // ---- stand-alone IPA verification -------------------------------------------------------------------
 struct IpaChal {
     uint32_t valid;
@@ -231,6 +315,96 @@ int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, co
         (uint8_t*)d_G_out, (uint8_t*)d_H_out, (const uint8_t*)d_G, (const uint8_t*)d_H, n_half, (const uint8_t*)d_u,
         (const uint8_t*)d_u_inv);
     CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+
+static size_t ipa_align(size_t x) { return (x + 255) / 256 * 256; }
+struct IpaProveLayout {
+    size_t a, b, g, h, scal, pts, small, ipws, msmws, total;
+};
+static int ipa_prove_layout(size_t n, IpaProveLayout* L) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += ipa_align(bytes);
+        return o;
+    };
+    L->a = take(n * 32);
+    L->b = take(n * 32);
+    L->g = take(n * 128);
+    L->h = take(n * 128);
+    L->scal = take((n + 1) * 32);
+    L->pts = take((n + 1) * 128);
+    L->small = take(8 * 32);  // tr | u | uinv | cL | cR
+    size_t ipb = 0;
+    if (bpk_sc_inner_product_workspace_bytes(n / 2 ? n / 2 : 1, &ipb) != BPK_OK) return BPK_ERR_ARG;
+    L->ipws = take(ipb + 256);
+    MsmPlan p;
+    msm_make_plan(&p, n + 1, 0);
+    size_t msm_bytes = p.workspace_bytes;
+    for (size_t m = n; m >= 2; m >>= 1) {  // every round's plan must fit (window width varies with the size)
+        msm_make_plan(&p, m + 1, 0);
+        if (p.workspace_bytes > msm_bytes) msm_bytes = p.workspace_bytes;
+    }
+    L->msmws = take(msm_bytes);
+    L->total = off;
+    return BPK_OK;
+}
+int bpk_ipa_prove_workspace_bytes(size_t n, size_t* bytes) {
+    if (!bytes || n < 2 || (n & (n - 1)) || n > ((size_t)1 << 24)) return fail(BPK_ERR_ARG);
+    IpaProveLayout L;
+    if (ipa_prove_layout(n, &L) != BPK_OK) return fail(BPK_ERR_ARG);
+    *bytes = L.total;
+    return BPK_OK;
+}
+int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, const void* d_a, const void* d_b, size_t n,
+                         const uint8_t transcript0[32], void* d_L, void* d_R, void* d_a_out, void* d_b_out, void* d_x_out,
+                         void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (n < 2 || (n & (n - 1)) || n > ((size_t)1 << 24)) return fail(BPK_ERR_ARG);
+    if (!d_G || !d_H || !d_Q || !d_a || !d_b || !transcript0 || !d_L || !d_R || !d_a_out || !d_b_out || !d_x_out ||
+        !d_workspace)
+        return fail(BPK_ERR_ARG);
+    IpaProveLayout Ly;
+    if (ipa_prove_layout(n, &Ly) != BPK_OK) return fail(BPK_ERR_ARG);
+    if (workspace_bytes < Ly.total) return fail(BPK_ERR_WORKSPACE);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)d_workspace;
+    uint8_t *a = ws + Ly.a, *b = ws + Ly.b, *g = ws + Ly.g, *h = ws + Ly.h, *scal = ws + Ly.scal, *pts = ws + Ly.pts;
+    uint8_t *tr = ws + Ly.small, *u = tr + 32, *ui = tr + 64, *cL = tr + 96, *cR = tr + 128;
+    size_t ipb = 0;
+    bpk_sc_inner_product_workspace_bytes(n / 2, &ipb);
+    CBP_CUDA(cudaMemcpyAsync(tr, transcript0, 32, cudaMemcpyHostToDevice, st));
+    ipa_prove_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a, b, g, h, (const uint8_t*)d_a, (const uint8_t*)d_b,
+                                                                      (const uint8_t*)d_G, (const uint8_t*)d_H, n);
+    CBP_CHECK_LAUNCH();
+    int round = 0;
+    for (size_t np = n >> 1; np >= 1; np >>= 1, round++) {
+        int rc;
+        if ((rc = bpk_sc_inner_product_device(cL, a, b + np * 32, np, ws + Ly.ipws, ipb + 256, st)) != BPK_OK) return rc;
+        if ((rc = bpk_sc_inner_product_device(cR, a + np * 32, b, np, ws + Ly.ipws, ipb + 256, st)) != BPK_OK) return rc;
+        MsmPlan p;
+        msm_make_plan(&p, 2 * np + 1, 0);
+        for (int side = 0; side < 2; side++) {
+            ipa_prove_gather_kernel<<<(unsigned)((np + 1 + 127) / 128), 128, 0, st>>>(side, np, a, b, g, h, (const uint8_t*)d_Q,
+                                                                                    side ? cR : cL, scal, pts);
+            CBP_CHECK_LAUNCH();
+            int nl = 0;
+            uint8_t* out = (uint8_t*)(side ? d_R : d_L) + (size_t)round * 128;
+            int mrc = msm_run(p, scal, pts, out, ws + Ly.msmws, 1, st, &nl, nullptr);
+            count_launches(nl);
+            if (mrc) return fail_cuda(mrc);
+        }
+        ipa_prove_challenge_kernel<<<1, 32, 0, st>>>(round, tr, (const uint8_t*)d_L + (size_t)round * 128,
+                                                     (const uint8_t*)d_R + (size_t)round * 128, (uint8_t*)d_x_out, u, ui);
+        CBP_CHECK_LAUNCH();
+        ipa_fold_scalars_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(a, b, a, b, np, u, ui);
+        CBP_CHECK_LAUNCH();
+        // in place: thread j reads g[j], g[j + n'] and writes g[j] only
+        ipa_fold_points_kernel<<<(unsigned)((2 * np + 63) / 64), 64, 0, st>>>(g, h, g, h, np, u, ui);
+        CBP_CHECK_LAUNCH();
+    }
+    CBP_CUDA(cudaMemcpyAsync(d_a_out, a, 32, cudaMemcpyDeviceToDevice, st));
+    CBP_CUDA(cudaMemcpyAsync(d_b_out, b, 32, cudaMemcpyDeviceToDevice, st));
     return BPK_OK;
 }
 

@@ -699,6 +699,7 @@ int msm_pick_window(size_t n) {
     //   2^18: 1.91 1.46 1.08 1.09   2^19: 3.46 2.45 1.47 1.48   2^20: 6.64 4.35 2.51 2.22
     // From 2^15 points the window-group pipeline is on and the call is bound by dependent chains, whose
     // length falls with the number of windows: wide windows win long before the operation count says so.
+    if (n >= ((size_t)1 << 23)) return 17;  // 2^24: 26.5 ms at c = 17 against 27.5 ms at c = 16 (2^22: 7.13 both)
     if (n >= ((size_t)1 << 19)) return 16;
     if (n >= ((size_t)1 << 15)) return 15;
     // below: minimise W*(n + 2*2^(c-1)*9/7) over c with W = ceil(256/c); c <= 16 keeps entries in 32 bits

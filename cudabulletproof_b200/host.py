@@ -338,3 +338,26 @@ def derive_generators(seed, count, first_index=0, device="cuda", stream=None):
            "bpk_gens_derive_device")
     torch.cuda.current_stream().synchronize()
     return out
+
+
+def ipa_prove(G, H, Q, a, b, transcript0=bytes(32), stream=None):
+    """Inner-product argument over n = len(a) (a power of two) generators, on the device.
+    G, H: (n, 128) uint8 cuda tensors (or (n, 16) uint64 numpy); Q: one point; a, b: (n, 32) / (n, 4).
+    Returns (L, R, a_final, b_final, x_raw) as cuda uint8 tensors: L, R (log2 n, 128), the rest (32,)."""
+    import torch
+    dG, dH, dQ = _as_dev_u8(G, 128), _as_dev_u8(H, 128), _as_dev_u8(Q, 128)
+    da, db = _as_dev_u8(a, 32), _as_dev_u8(b, 32)
+    n = da.shape[0]
+    k = n.bit_length() - 1
+    nbytes = C.c_size_t(0)
+    _check(_lib().bpk_ipa_prove_workspace_bytes(n, C.byref(nbytes)), "bpk_ipa_prove_workspace_bytes")
+    ws = _dev_u8(nbytes.value, dG.device)
+    L = torch.zeros((k, 128), dtype=torch.uint8, device=dG.device)
+    R = torch.zeros((k, 128), dtype=torch.uint8, device=dG.device)
+    small = torch.zeros((3, 32), dtype=torch.uint8, device=dG.device)
+    _check(_lib().bpk_ipa_prove_device(dG.data_ptr(), dH.data_ptr(), dQ.data_ptr(), da.data_ptr(), db.data_ptr(), n,
+                                       bytes(transcript0), L.data_ptr(), R.data_ptr(), small[0].data_ptr(),
+                                       small[1].data_ptr(), small[2].data_ptr(), ws.data_ptr(), nbytes.value,
+                                       _stream_ptr(stream)), "bpk_ipa_prove_device")
+    torch.cuda.current_stream().synchronize()
+    return L, R, small[0], small[1], small[2]

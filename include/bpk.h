@@ -84,6 +84,16 @@ int bpk_ipa_fold_scalars_device(void* d_a_out, void* d_b_out, const void* d_a, c
 int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, const void* d_H, size_t n_half,
                                const void* d_u, const void* d_u_inv, void* stream);
 
+/* Inner-product argument, prover side, for any power-of-two n (inner_product_prove,
+ * bulletproof_vectors.cu:375-509): d_L / d_R receive log2 n normalised points each, d_a_out / d_b_out the final
+ * scalars (32 B), d_x_out the raw first-round challenge the reference stores in the proof (32 B).
+ * transcript0: 32 bytes (HOST pointer).  Bit-identical to the CPU oracle.  Per round: two mod-l inner products,
+ * L and R as one Pippenger MSM each over 2n'+1 points, the challenge hash and inversion, the a/b and G/H folds. */
+int bpk_ipa_prove_workspace_bytes(size_t n, size_t* bytes);
+int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, const void* d_a, const void* d_b, size_t n,
+                         const uint8_t transcript0[32], void* d_L, void* d_R, void* d_a_out, void* d_b_out, void* d_x_out,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- point codec and generator derivation (N2, N4) ---- */
 /* d_out[i] (32 B) = RFC 8032 encoding of d_points[i] (ge25519, any Z): y little-endian, bit 255 = lsb(x).
  * Replaces ge25519_pack (curve25519_ops.cu:449-468) on arrays; one field inversion per 4096 points. */

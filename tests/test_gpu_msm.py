@@ -95,7 +95,7 @@ def test_msm_empty_and_mismatch(capfd):
     assert "Vector lengths must match" in capfd.readouterr().err
 
 
-@pytest.mark.parametrize("window_bits", [4, 7, 11, 13, 15, 16])
+@pytest.mark.parametrize("window_bits", [4, 7, 11, 13, 15, 16, 17])
 def test_msm_all_window_sizes_agree(oracle, window_bits):
     import torch
     import cudabulletproof_b200 as cbp

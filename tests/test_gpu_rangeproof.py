@@ -298,6 +298,15 @@ def test_ipa_n4096_config4(oracle):
     oracle.inner_product_prove(C.byref(proof), C.byref(av), C.byref(bv), C.byref(Gv), C.byref(Hv), ob.ptr(Q), ob.ptr(c),
                                bytes(32))
     assert proof.L_len == 12
+    # the same 12-round argument proved on the device: every L_j, R_j, the final a, b and the stored challenge
+    dL, dR, fa, fb, fx = cbp.ipa_prove(G, H, Q, a, b)
+    wantL = np.stack([np.frombuffer(bytes(proof.L.elements[j]), dtype=np.uint64) for j in range(12)])
+    wantR = np.stack([np.frombuffer(bytes(proof.R.elements[j]), dtype=np.uint64) for j in range(12)])
+    assert np.array_equal(dL.cpu().numpy().view(np.uint64).reshape(12, 16), wantL)
+    assert np.array_equal(dR.cpu().numpy().view(np.uint64).reshape(12, 16), wantR)
+    assert fa.cpu().numpy().tobytes() == bytes(proof.a.elements[0])
+    assert fb.cpu().numpy().tobytes() == bytes(proof.b.elements[0])
+    assert fx.cpu().numpy().tobytes() == bytes(proof.x)
     assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is True
     proof.R.elements[7].X.limbs[0] ^= 1
     assert cbp.cuda_inner_product_verify(proof, P, G, H, Q) is False
@@ -346,3 +355,28 @@ def test_batched_prover_is_byte_identical(oracle, gens16, gens64, n, window_bits
         oracle.range_proof_free(C.byref(proof))
     acc = cbp.RangeVerifier(dg, m)(got).cpu().numpy().astype(bool)
     assert acc.tolist() == [not (n == 16 and i == 5) for i in range(m)]
+
+
+@pytest.mark.parametrize("n", [2, 8, 64])
+def test_device_ipa_prover_matches_oracle_small(oracle, gens64, n):
+    """bpk_ipa_prove_device against inner_product_prove (bulletproof_vectors.cu:375-509 restated) at small widths,
+    with a non-zero initial transcript"""
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(0x1BA + n)
+    G, H, Q = gens64.G[:n].copy(), gens64.H[:n].copy(), gens64.g.copy()
+    a = ob.ints_to_fe([rng.getrandbits(256) for _ in range(n)])  # unreduced inputs are reduced mod l first
+    b = ob.ints_to_fe([rng.getrandbits(256) for _ in range(n)])
+    tr0 = bytes(rng.getrandbits(8) for _ in range(32))
+    av, bv, Gv, Hv = ob.field_vector(a), ob.field_vector(b), ob.point_vector(G), ob.point_vector(H)
+    c = np.zeros(4, dtype=np.uint64)
+    oracle.field_vector_inner_product(ob.ptr(c), C.byref(av), C.byref(bv))
+    proof = ob.InnerProductProof()
+    oracle.inner_product_prove(C.byref(proof), C.byref(av), C.byref(bv), C.byref(Gv), C.byref(Hv), ob.ptr(Q), ob.ptr(c), tr0)
+    k = n.bit_length() - 1
+    dL, dR, fa, fb, fx = cbp.ipa_prove(G, H, Q, a, b, transcript0=tr0)
+    for j in range(k):
+        assert dL[j].cpu().numpy().tobytes() == bytes(proof.L.elements[j]), j
+        assert dR[j].cpu().numpy().tobytes() == bytes(proof.R.elements[j]), j
+    assert fa.cpu().numpy().tobytes() == bytes(proof.a.elements[0])
+    assert fb.cpu().numpy().tobytes() == bytes(proof.b.elements[0])
+    assert fx.cpu().numpy().tobytes() == bytes(proof.x)

@@ -3,13 +3,13 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cudabulletproof_b200 as cbp
-n = 1 << 20
+n = 1 << 24
 pts, _ = cbp.synth_points(n, seed=1)
 sc = cbp.synth_scalars(n, seed=2, bits=253)
-for lg in (12, 14, 15, 16, 17, 18, 19, 20):
+for lg in (19, 20, 21, 22, 24):
     m = 1 << lg
     row = []
-    for c in (0, 11, 12, 13, 14, 15, 16):
+    for c in (0, 15, 16, 17, 18):
         msm = cbp.Msm(m, window_bits=c) if c else cbp.Msm(m)
         for _ in range(3):
             msm(sc[:m], pts[:m])
