@@ -493,6 +493,29 @@ def run_cuda(args):
         rows["ipa_prove_n4096"] = {"ms": ipa_ms, "rounds": 12,
                                    "note": "bpk_ipa_prove_device: per round 2 inner products, 2 Pippenger MSMs of 2n'+1 points, "
                                            "challenge hash + inversion, a/b and G/H folds; wall time incl. workspace allocation"}
+        # BASELINE configs 0-1: ONE range proof, proved on the device and verified through the reference-facing
+        # host-pointer drop-in cuda_range_proof_verify (latency, not throughput)
+        lat = {}
+        for nb in (16, 64):
+            gp, _ = cbp.synth_points(2 * nb + 2, seed=0xB0070002 + nb, device=dev)
+            gsmall = cbp.Generators(gp[:nb], gp[nb:2 * nb], gp[2 * nb], gp[2 * nb + 1], device=dev)
+            one_gam = np.array([[7, 0, 0, 0]], dtype=np.uint64)
+            cbp.range_prove_batch(gsmall, [42], one_gam, [1])
+            t0 = time.perf_counter()
+            recd = cbp.range_prove_batch(gsmall, [42], one_gam, [1])
+            prove_ms1 = (time.perf_counter() - t0) * 1e3
+            hG = gp[:nb].cpu().numpy().view(np.uint64).reshape(nb, 16)
+            hH = gp[nb:2 * nb].cpu().numpy().view(np.uint64).reshape(nb, 16)
+            hg = gp[2 * nb].cpu().numpy().view(np.uint64)
+            hh = gp[2 * nb + 1].cpu().numpy().view(np.uint64)
+            proof, hV, keep = cbp.record_to_range_proof(recd[0].cpu().numpy(), nb)
+            okv = cbp.cuda_range_proof_verify(proof, hV, nb, hG, hH, hg, hh)  # builds and caches the generator tables
+            t0 = time.perf_counter()
+            for _ in range(5):
+                okv = cbp.cuda_range_proof_verify(proof, hV, nb, hG, hH, hg, hh) and okv
+            lat[f"range_proof_{nb}bit"] = {"prove_ms": prove_ms1, "verify_host_api_ms": (time.perf_counter() - t0) / 5 * 1e3,
+                                          "accepted": bool(okv)}
+        rows["single_proof_latency"] = lat
         return {"note": "one kernel pass each on arrays larger than L2; bytes are algorithmic (SURVEY.md section 8d), "
                         f"HBM peak {hbm_peak:.0f} GB/s ({peak_src}), integer peak {INT_PEAK_TIMAD} T IMAD.WIDE/s", "rows": rows}
 

@@ -361,3 +361,24 @@ def ipa_prove(G, H, Q, a, b, transcript0=bytes(32), stream=None):
                                        _stream_ptr(stream)), "bpk_ipa_prove_device")
     torch.cuda.current_stream().synchronize()
     return L, R, small[0], small[1], small[2]
+
+
+def record_to_range_proof(record, n):
+    """flat proof record (include/bpk.h layout, (record_bytes,) uint8) -> (ctypes RangeProof with the reference's
+    layout, V as (16,) uint64, keep-alive tuple for the arrays the struct points into)"""
+    from . import RangeProof
+    k = n.bit_length() - 1
+    w = np.ascontiguousarray(np.asarray(record).reshape(-1)).view(np.uint64)
+    proof = RangeProof()
+    C.memmove(C.byref(proof), w[0:92].tobytes(), 92 * 8)  # V, A, S, T1, T2, taux, mu, t
+    a, b = w[92:96].copy().reshape(1, 4), w[96:100].copy().reshape(1, 4)
+    Ls = w[108:108 + 16 * k].copy().reshape(k, 16)
+    Rs = w[108 + 16 * k:108 + 32 * k].copy().reshape(k, 16)
+    ip = proof.ip_proof
+    ip.n = n
+    ip.a, ip.b = _fv(a), _fv(b)
+    C.memmove(C.byref(ip.c), w[100:104].tobytes(), 32)
+    C.memmove(C.byref(ip.x), w[104:108].tobytes(), 32)
+    ip.L, ip.R = _pv(Ls), _pv(Rs)
+    ip.L_len = k
+    return proof, w[0:16].copy(), (a, b, Ls, Rs)
