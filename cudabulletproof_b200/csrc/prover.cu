@@ -1087,7 +1087,7 @@ int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values
     const size_t chunk = num_proofs < kPbChunk ? num_proofs : kPbChunk;
     static const bool legacy_env = getenv("CBP_PROVER_LEGACY") != nullptr;
     const int wbits = bpk_gens_window_bits(d_gens_ws);
-    if (legacy_env || num_proofs < kPbMinBatch || !d_workspace || workspace_bytes < pb_layout(chunk).total || !wbits) {
+    if (legacy_env || n < 2 || num_proofs < kPbMinBatch || !d_workspace || workspace_bytes < pb_layout(chunk).total || !wbits) {
         range_prove_kernel<<<(unsigned)num_proofs, kPThreads, 0, st>>>((const uint8_t*)d_gens_ws, d_values,
                                                                       (const uint8_t*)d_gammas, d_seeds, (uint32_t)n, k,
                                                                       (uint8_t*)d_proofs, rec);

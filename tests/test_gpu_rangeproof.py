@@ -316,7 +316,7 @@ def test_ipa_n4096_config4(oracle):
     oracle.inner_product_proof_free(C.byref(proof))
 
 
-@pytest.mark.parametrize("n,window_bits", [(16, 8), (64, 16), (32, 16)])
+@pytest.mark.parametrize("n,window_bits", [(16, 8), (64, 16), (32, 16), (8, 8), (2, 16), (1, 8)])
 def test_batched_prover_is_byte_identical(oracle, gens16, gens64, n, window_bits):
     """Batches of 64+ proofs take the phase-split prover (batch inversions across proofs, one window per lane);
     its records must equal the one-CTA-per-proof kernel's byte for byte (which is pinned to the oracle above),
@@ -324,7 +324,7 @@ def test_batched_prover_is_byte_identical(oracle, gens16, gens64, n, window_bits
     import torch
     import cudabulletproof_b200 as cbp
     lib = cbp.load()
-    g = gens16 if n == 16 else gens64 if n == 64 else Gens(oracle, 32)
+    g = gens16 if n == 16 else gens64 if n == 64 else Gens(oracle, n)
     dg = dev_gens(g, window_bits)
     m = 150
     rng = random.Random(0xBA7C4 + n)
