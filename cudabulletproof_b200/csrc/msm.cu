@@ -801,7 +801,7 @@ StreamKit* stream_kit(int idx) {
 // Measured and rejected: sorting the lower half of the windows on a side stream while the upper half is being
 // accumulated.  The exposed front end shrinks (0.50 -> 0.34 ms) but the accumulation, whose table gathers
 // share the L2 with the sort's atomics, slows down by the same amount (1.48 -> 1.69 ms): 2.29 ms either way.
-// windows are processed top-down in groups of halving size (.., 4, 2, 1, 1): while the lower groups are
+// windows are processed top-down in groups of halving size (.., 4, 2, 2): while the lower groups are
 // still being accumulated, the upper groups are reduced and folded into the Horner chain on a second
 // stream, so only the last (single-window) group's reduction latency is exposed.
 static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline) {
@@ -816,6 +816,10 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
         int remaining = W;
         while (remaining > 0) {
             int take = remaining > 1 ? remaining / 2 : 1;
+            // the last two windows go together (.., 4, 2, 2): a one-window accumulation is a single partial wave
+            // (48 % of the multiply pipe in ncu against 84 % for the 8-window group); measured 2.27 vs 2.30 ms at
+            // 2^20 and 1.43 vs 1.49 ms at 2^19.  Larger last groups lengthen the exposed tail by more than they save.
+            if (remaining <= 2) take = remaining;
             if (gm->ngroups == kMaxGroups - 1) take = remaining;
             gm->w_hi[gm->ngroups] = hi;
             gm->w_lo[gm->ngroups] = hi - take + 1;
