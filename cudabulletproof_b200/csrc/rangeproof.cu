@@ -746,7 +746,8 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         const uint8_t* pr = (const uint8_t*)d_proofs + done * rec;
         const uint8_t* ve = d_V ? (const uint8_t*)d_V + done * 128 : nullptr;
         // side stream: the per-proof point tables need only the records, so they are built while the
-        // latency-bound transcript / coefficient kernels run
+        // latency-bound transcript / coefficient kernels run.  (Also moving the window sums there, next to the
+        // coefficient and fixed-base kernels, was measured: 6.43 vs 6.56 ms — both sides want the same pipe.)
         cudaStream_t ss = side->stream;
         CBP_CUDA(cudaEventRecord(side->ev_fork, st));
         CBP_CUDA(cudaStreamWaitEvent(ss, side->ev_fork, 0));
