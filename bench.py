@@ -344,12 +344,14 @@ def run_cuda(args):
         seeds = np.arange(distinct, dtype=np.uint64) + np.uint64(100000 * rank)
         base = cbp.range_prove_batch(gens, vals, gam, seeds)  # also warms the prover up
         torch.cuda.synchronize()
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        base = cbp.range_prove_batch(gens, vals, gam, seeds)
-        pe1.record()
-        torch.cuda.synchronize()
-        prove_ms = pe0.elapsed_time(pe1)
+        prove_ms = float("inf")
+        for _ in range(3):  # best of three: the call allocates its 0.5 GB workspace, which the caching allocator
+            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)  # may or may not have
+            pe0.record()
+            base = cbp.range_prove_batch(gens, vals, gam, seeds)
+            pe1.record()
+            torch.cuda.synchronize()
+            prove_ms = min(prove_ms, pe0.elapsed_time(pe1))
         reps = (m + distinct - 1) // distinct
         proofs = base.repeat(reps, 1)[:m].contiguous()
         bad = rng.choice(m, size=max(1, m // 100), replace=False)  # 1 % tampered: one bit flipped
