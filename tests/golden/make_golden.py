@@ -5,6 +5,9 @@ msm_vectors.json   — small MSM instances with results computed by the independ
 proof_n16.json     — one 16-bit range proof (value 42, seed 1) as the flat record of include/bpk.h, produced
                      by the C oracle's prover; the device prover must reproduce these bytes and both verifiers
                      must accept them.
+codec_vectors.json — generator derivation (hash -> decode -> x8) and point encodings computed by the independent
+                     Python model (hashlib + big integers): pins the C oracle's oracle_hash_to_point /
+                     ge25519_pack / ge25519_unpack and the device codec.
 """
 import ctypes as C
 import json
@@ -46,6 +49,30 @@ def main():
         json.dump({"generator": "tests/golden/make_golden.py (oracle/ref_corrected.c prover, value 42, seed 1, "
                                 "gamma (0x1234567 + 7919) mod 2^252, generators tests/helpers.Gens(16))",
                    "n": 16, "value": 42, "seed": 1, "record_hex": rec.tobytes().hex()}, f, indent=1)
+    import hashlib
+    gens = []
+    for seed_byte in (1, 2, 3, 4):
+        seed = bytes([seed_byte]) + bytes(31)
+        for idx in range(3):
+            ctr = 0
+            while True:
+                msg = seed + idx.to_bytes(4, "big") + (ctr.to_bytes(4, "big") if ctr else b"")
+                h = hashlib.sha256(msg).digest()
+                yv = int.from_bytes(h, "little")
+                sign = yv >> 255
+                yv &= (1 << 255) - 1
+                x = pyref.recover_x(yv, sign) if yv < P else None
+                if x is not None:
+                    pt = pyref.pt_mul(8, (x, yv))
+                    if pt != (0, 1):
+                        break
+                ctr += 1
+            gens.append({"seed_byte": seed_byte, "index": idx, "counter": ctr, "affine": [hex(pt[0]), hex(pt[1])],
+                         "encoding": pyref.encode(pt).hex()})
+    invalid = [P.to_bytes(32, "little").hex(), (1 | 1 << 255).to_bytes(32, "little").hex(), (2).to_bytes(32, "little").hex()]
+    with open(os.path.join(HERE, "codec_vectors.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py (hashlib + oracle/pyref.py)", "generators": gens,
+                   "invalid_encodings": invalid}, f, indent=1)
     print("golden files written")
 
 
