@@ -11,12 +11,12 @@
 //   sum (a s_i + z) G_i + sum ((b s_i^-1 - z^2 2^i) y^-i - z) H_i + (mu + ab - t) h
 //                                                ==  A + x S + sum u_j^2 L_j + sum u_j^-2 R_j
 // as multi-scalar sums: the 2n+2 shared generators through precomputed fixed-base tables (8- or 16-bit
-// windows, no doublings), the 2 log n + 5 per-proof points with 4-bit windows.
+// windows, no doublings), the 2 log n + 5 per-proof points with signed 5-bit windows.
 //
 // Kernels per batch (see the block comment above verify_coeff_kernel for the middle ones):
 //   verify_transcript  1 thread / proof : on-curve checks, SHA-256 challenges, scalar inversions
 //   verify_coeff / verify_fixed / verify_vtab / verify_winsum : the two multi-scalar sums, by phase
-//   verify_finish      1 thread / (proof, identity): Horner over the 64 windows, equality test
+//   verify_finish      1 thread / (proof, identity): Horner over the 51 windows, equality test
 //   verify_combine     accept bits
 #include <stdio.h>
 #include <string.h>
@@ -327,8 +327,13 @@ __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __
 //   verify_coeff    thread / (proof, slot)        : coefficients -> signed digits (global memory)
 //   verify_fixed    WARP   / proof                 : 131 x 32 table additions, lane = window, shuffle tree
 //   verify_vtab     thread / (proof, point, m)     : multiples 1..8 of the 17 per-proof points
-//   verify_winsum   thread / (identity, proof, w)  : 4-bit window sums over the per-proof points
+//   verify_winsum   thread / (identity, proof, w)  : 5-bit window sums over the per-proof points
 static constexpr int kVarMax = 2 + 2 * kMaxK + 3;  // A, S, L_j, R_j | V, T1, T2
+// per-proof points: signed kVarBits-bit windows, multiples 1..2^(kVarBits-1) per point
+static constexpr int kVarBits = 5;
+static constexpr int kVarWin = (253 + kVarBits) / kVarBits;  // digits of a scalar < 2^253 (+ carry room)
+static constexpr int kVarEntries = 1 << (kVarBits - 1);
+static_assert(kVarWin <= 64 && kVarWin * kVarBits >= 254, "digit rows are 64 bytes");
 static constexpr int kCoeffThreads = 96;           // n + 3 + kVarMax <= 96 for n <= 64
 static constexpr int kRowsMax = 2 * kMaxN + 3;     // G_i, H_i, h(identity 2), g, h(identity 1)
 
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8
         else if (q == nvar2) sv = vs.z2;
         else if (q == nvar2 + 1) sv = vs.x;
         else sv = vs.x2;
-        sc_recode_signed<4>(vrow + (size_t)q * 64, sv, 64);
+        sc_recode_signed<kVarBits>(vrow + (size_t)q * 64, sv, kVarWin);
     }
     // s_t = prod_j u_j^(+-1) = s_0 * prod over the set bits m of t of u_(k-1-m)^2, and y^-t from the
     // y^-(2^m) ladder, by doubling the filled prefix: level m fills [2^m, 2^(m+1)) from [0, 2^m)
@@ -493,46 +498,43 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
     }
 }
 
-// multiples m = 1..8 of per-proof point q, as cached points; threads are grouped by m so that the
-// double-and-add pattern is uniform within a warp
+// multiples 1..kVarEntries of per-proof point q as cached points, one thread per (proof, point): a chain of
+// additions of P (the entries are needed in order anyway; an earlier version recomputed every multiple by
+// double-and-add in its own thread, 3x the work)
 __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, int k,
                                                           uint32_t num, uint8_t* __restrict__ vtab) {
     const int nvar = 2 + 2 * k + 3;
-    uint32_t per_m = num * (uint32_t)nvar;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= per_m * 8) return;
-    int mlt = (int)(id / per_m) + 1;
-    uint32_t rem = id % per_m, p = rem / (uint32_t)nvar;
-    int q = (int)(rem % (uint32_t)nvar);
+    if (id >= num * (uint32_t)nvar) return;
     // no dependency on the transcript (runs concurrently with it): records that later turn out invalid
     // just produce unused table entries
+    const uint32_t p = id / (uint32_t)nvar;
+    const int q = (int)(id % (uint32_t)nvar);
     ge_p3 P, acc;
     ge_load(P, proofs + (size_t)p * rec_bytes + var_point_offset(q, k));
     acc = P;
-    // m in [1,8]: binary method from the top bit
-    int top = 31 - __clz(mlt);
-    for (int bit = top - 1; bit >= 0; bit--) {
-        ge_dbl(acc, acc);
-        if ((mlt >> bit) & 1) ge_add(acc, acc, P);
+    uint8_t* dst = vtab + ((size_t)p * kVarMax + q) * kVarEntries * 128;
+#pragma unroll 1
+    for (int m = 0; m < kVarEntries; m++) {
+        ge_cached c;
+        ge_to_cached(c, acc);
+        fe_store(dst + m * 128, c.YplusX);
+        fe_store(dst + m * 128 + 32, c.YminusX);
+        fe_store(dst + m * 128 + 64, c.Z2);
+        fe_store(dst + m * 128 + 96, c.T2d);
+        if (m + 1 < kVarEntries) ge_add(acc, acc, P);
     }
-    ge_cached c;
-    ge_to_cached(c, acc);
-    uint8_t* dst = vtab + (((size_t)p * kVarMax + q) * 8 + (mlt - 1)) * 128;
-    fe_store(dst, c.YplusX);
-    fe_store(dst + 32, c.YminusX);
-    fe_store(dst + 64, c.Z2);
-    fe_store(dst + 96, c.T2d);
 }
-// window sums: threads [0, 64 num) identity 2 (A, S, L_j, R_j), [64 num, 128 num) identity 1 (V, T1, T2)
+// window sums: threads [0, kVarWin num) identity 2 (A, S, L_j, R_j), [kVarWin num, 2 kVarWin num) identity 1 (V, T1, T2)
 __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restrict__ vscal,
                                                             const int8_t* __restrict__ vdigits,
                                                             const uint8_t* __restrict__ vtab, int k, uint32_t num,
                                                             uint8_t* __restrict__ winsum) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= num * 128) return;
-    int which = id >= num * 64;  // 1: identity 1
-    uint32_t rem = which ? id - num * 64 : id, p = rem >> 6;
-    int w = rem & 63;
+    if (id >= num * 2 * kVarWin) return;
+    int which = id >= num * kVarWin;  // 1: identity 1
+    uint32_t rem = which ? id - num * kVarWin : id, p = rem / kVarWin;
+    int w = (int)(rem % kVarWin);
     if (!vscal[p].valid) return;
     const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
     int q0 = which ? nvar2 : 0, q1 = which ? nvar : nvar2;
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
         int d = vdigits[((size_t)p * kVarMax + q) * 64 + w];
         if (d != 0) {
             int mag = d < 0 ? -d : d;
-            const uint8_t* src = vtab + (((size_t)p * kVarMax + q) * 8 + (mag - 1)) * 128;
+            const uint8_t* src = vtab + (((size_t)p * kVarMax + q) * kVarEntries + (mag - 1)) * 128;
             ge_cached c;
             fe_load(c.YplusX, src);
             fe_load(c.YminusX, src + 32);
@@ -552,10 +554,10 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
             ge_add_cached(ws, ws, c, d < 0);
         }
     }
-    ge_store(winsum + (((size_t)p * 2 + (which ? 0 : 1)) * 64 + w) * 128, ws);
+    ge_store(winsum + (((size_t)p * 2 + (which ? 0 : 1)) * kVarWin + w) * 128, ws);
 }
 
-// Horner over the 64 window sums, then F == Var as projective points.  index 0: identity 1, 1: identity 2.
+// Horner over the kVarWin window sums, then F == Var as projective points.  index 0: identity 1, 1: identity 2.
 __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restrict__ vscal,
                                                            const uint8_t* __restrict__ fsum,
                                                            const uint8_t* __restrict__ winsum, uint32_t num,
@@ -568,11 +570,11 @@ __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restri
     }
     ge_p3 acc;
     ge_p3_0(acc);
-    const uint8_t* ws = winsum + (size_t)id * 64 * 128;
+    const uint8_t* ws = winsum + (size_t)id * kVarWin * 128;
 #pragma unroll 1
-    for (int w = 63; w >= 0; w--) {
+    for (int w = kVarWin - 1; w >= 0; w--) {
 #pragma unroll 1  // keep the loop body small: this kernel is latency-bound and was stalling on instruction fetch
-        for (int d = 0; d < 4; d++) ge_dbl(acc, acc);
+        for (int d = 0; d < kVarBits; d++) ge_dbl(acc, acc);
         ge_p3 x;
         ge_load(x, ws + (size_t)w * 128);
         ge_add(acc, acc, x);
@@ -682,11 +684,11 @@ static VerifyLayout verify_layout(size_t chunk) {
     };
     L.vscal = take(chunk * sizeof(VScal));
     L.fsum = take(chunk * 2 * 128);
-    L.winsum = take(chunk * 2 * 64 * 128);
+    L.winsum = take(chunk * 2 * kVarWin * 128);
     L.flags = take(chunk * 2);
     L.digits = take(chunk * kRowsMax * kFixRowBytes);
     L.vdigits = take(chunk * kVarMax * 64);
-    L.vtab = take(chunk * kVarMax * 8 * 128);
+    L.vtab = take(chunk * kVarMax * kVarEntries * 128);
     L.total = off;
     return L;
 }
@@ -753,7 +755,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         CBP_CUDA(cudaStreamWaitEvent(ss, side->ev_fork, 0));
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
-        verify_vtab_kernel<<<(cnt * nvar * 8 + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab);
+        verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab);
         CBP_CHECK_LAUNCH();
         CBP_CUDA(cudaEventRecord(side->ev_join, ss));
         verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits,
@@ -769,7 +771,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         prof_end(BPK_PROF_VERIFY_MSM, st);
         CBP_CHECK_LAUNCH();
         CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
-        verify_winsum_kernel<<<(cnt * 128 + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, cnt, winsum);
+        verify_winsum_kernel<<<(cnt * 2 * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, cnt, winsum);
         CBP_CHECK_LAUNCH();
         verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
         CBP_CHECK_LAUNCH();

@@ -95,7 +95,13 @@ __device__ __forceinline__ void sc_recode_signed(OUT* out, const sc& k, int ndig
     constexpr uint32_t half = 1u << (WBITS - 1);
     for (int j = 0; j < ndig; j++) {
         int bit = j * WBITS;
-        uint32_t d = bit < 256 ? (k.v[bit >> 5] >> (bit & 31)) & ((1u << WBITS) - 1u) : 0u;
+        uint32_t d = 0;
+        if (bit < 256) {  // windows may straddle a 32-bit word (WBITS = 5)
+            int word = bit >> 5, sh = bit & 31;
+            uint64_t v = k.v[word];
+            if (word + 1 < 8) v |= (uint64_t)k.v[word + 1] << 32;
+            d = (uint32_t)(v >> sh) & ((1u << WBITS) - 1u);
+        }
         d += carry;
         carry = 0;
         int v = (int)d;
