@@ -389,10 +389,10 @@ def run_cuda(args):
         rejected = int((acc == 0).sum().item())
         ok = rejected == len(bad) and bool((acc[torch.from_numpy(bad).to(dev)] == 0).all().item())
         # algorithmic IMAD (SURVEY.md §8d units).  Whole proof: 131 bases x nwin windows mixed additions (504)
-        # + 17 points x 64 windows x 8M (576) + 2 x (252 doublings (464) + 64 additions (648)) Horner.
+        # + 17 points x 51 signed 5-bit windows x 8M (576) + 2 x (255 doublings (464) + 51 additions (648)) Horner.
         # The timed kernel (verify_fixed_kernel, nwin lanes per proof) does the first term plus two
         # log2(nwin)-level shuffle trees of 9M additions.
-        imad_proof = (131 * nwin * 504 + 17 * 64 * 576 + 2 * (252 * 464 + 64 * 648)) * 1.0
+        imad_proof = (131 * nwin * 504 + 17 * 51 * 576 + 2 * (255 * 464 + 51 * 648)) * 1.0
         imad_kernel = 131 * nwin * 504 + 2 * (nwin.bit_length() - 1) * nwin * 648.0
         per_launch = imad_kernel * (m / chunks)
         roofline = {"bound": "int", "kernel": "verify_fixed_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
