@@ -93,6 +93,24 @@ __device__ __forceinline__ void ge_dbl(ge_p3& r, const ge_p3& p) {
     fe_mul(r.T, E, H);
 }
 
+// r = 2p without the T coordinate (4S + 3M): for runs of doublings, where only the last one feeds an addition
+__device__ __forceinline__ void ge_dbl_xyz(ge_p3& r, const ge_p3& p) {
+    fe XX, YY, ZZ2, S, E, F, G, H;
+    fe_sq(XX, p.X);
+    fe_sq(YY, p.Y);
+    fe_sq(ZZ2, p.Z);
+    fe_dbl(ZZ2, ZZ2);
+    fe_add(S, p.X, p.Y);
+    fe_sq(S, S);
+    fe_add(H, YY, XX);
+    fe_sub(G, YY, XX);
+    fe_sub(E, S, H);
+    fe_sub(F, ZZ2, G);
+    fe_mul(r.X, E, F);
+    fe_mul(r.Y, G, H);
+    fe_mul(r.Z, F, G);
+}
+
 // ---- quad-cooperative point operations --------------------------------------------------------------
 // A dependent chain of point operations run by ONE lane is bound by the latency of its 8-9 sequential
 // field multiplications (~600 cycles each in a lone warp).  Here four adjacent lanes (a "quad",

@@ -574,7 +574,8 @@ __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restri
 #pragma unroll 1
     for (int w = kVarWin - 1; w >= 0; w--) {
 #pragma unroll 1  // keep the loop body small: this kernel is latency-bound and was stalling on instruction fetch
-        for (int d = 0; d < kVarBits; d++) ge_dbl(acc, acc);
+        for (int d = 0; d < kVarBits - 1; d++) ge_dbl_xyz(acc, acc);  // T is only needed by the addition
+        ge_dbl(acc, acc);
         ge_p3 x;
         ge_load(x, ws + (size_t)w * 128);
         ge_add(acc, acc, x);
