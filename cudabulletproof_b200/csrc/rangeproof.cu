@@ -501,8 +501,11 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
 // multiples 1..kVarEntries of per-proof point q as cached points, one thread per (proof, point): a chain of
 // additions of P (the entries are needed in order anyway; an earlier version recomputed every multiple by
 // double-and-add in its own thread, 3x the work)
+// For one point per identity (S with scalar x, V with scalar z^2: every window digit is non-zero) the multiples
+// are also kept in extended form: the window sums START from that entry instead of adding it to the identity.
 __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, int k,
-                                                          uint32_t num, uint8_t* __restrict__ vtab) {
+                                                          uint32_t num, uint8_t* __restrict__ vtab,
+                                                          uint8_t* __restrict__ vseed) {
     const int nvar = 2 + 2 * k + 3;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * (uint32_t)nvar) return;
@@ -514,8 +517,12 @@ __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restr
     ge_load(P, proofs + (size_t)p * rec_bytes + var_point_offset(q, k));
     acc = P;
     uint8_t* dst = vtab + ((size_t)p * kVarMax + q) * kVarEntries * 128;
+    const int nvar2 = 2 + 2 * k;
+    const int seed_slot = q == 1 ? 1 : q == nvar2 ? 0 : -1;  // index as in the window sums: 0 identity 1, 1 identity 2
+    uint8_t* sdst = seed_slot >= 0 ? vseed + ((size_t)p * 2 + seed_slot) * kVarEntries * 128 : nullptr;
 #pragma unroll 1
     for (int m = 0; m < kVarEntries; m++) {
+        if (sdst) ge_store(sdst + m * 128, acc);
         ge_cached c;
         ge_to_cached(c, acc);
         fe_store(dst + m * 128, c.YplusX);
@@ -528,7 +535,8 @@ __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restr
 // window sums: threads [0, kVarWin num) identity 2 (A, S, L_j, R_j), [kVarWin num, 2 kVarWin num) identity 1 (V, T1, T2)
 __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restrict__ vscal,
                                                             const int8_t* __restrict__ vdigits,
-                                                            const uint8_t* __restrict__ vtab, int k, uint32_t num,
+                                                            const uint8_t* __restrict__ vtab,
+                                                            const uint8_t* __restrict__ vseed, int k, uint32_t num,
                                                             uint8_t* __restrict__ winsum) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * 2 * kVarWin) return;
@@ -540,8 +548,18 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
     int q0 = which ? nvar2 : 0, q1 = which ? nvar : nvar2;
     ge_p3 ws;
     ge_p3_0(ws);
+    const int qs = which ? nvar2 : 1;  // the seed point of this identity (V resp. S)
+    {
+        int d = vdigits[((size_t)p * kVarMax + qs) * 64 + w];
+        if (d != 0) {
+            int mag = d < 0 ? -d : d;
+            ge_load(ws, vseed + (((size_t)p * 2 + (which ? 0 : 1)) * kVarEntries + (mag - 1)) * 128);
+            if (d < 0) ge_neg(ws, ws);
+        }
+    }
 #pragma unroll 1
     for (int q = q0; q < q1; q++) {
+        if (q == qs) continue;
         int d = vdigits[((size_t)p * kVarMax + q) * 64 + w];
         if (d != 0) {
             int mag = d < 0 ? -d : d;
@@ -673,7 +691,7 @@ int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, cons
 }
 
 struct VerifyLayout {
-    size_t vscal, fsum, winsum, flags, digits, vdigits, vtab, total;
+    size_t vscal, fsum, winsum, flags, digits, vdigits, vtab, vseed, total;
 };
 static VerifyLayout verify_layout(size_t chunk) {
     VerifyLayout L;
@@ -690,6 +708,7 @@ static VerifyLayout verify_layout(size_t chunk) {
     L.digits = take(chunk * kRowsMax * kFixRowBytes);
     L.vdigits = take(chunk * kVarMax * 64);
     L.vtab = take(chunk * kVarMax * kVarEntries * 128);
+    L.vseed = take(chunk * 2 * kVarEntries * 128);
     L.total = off;
     return L;
 }
@@ -738,6 +757,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     uint8_t* ws = (uint8_t*)d_workspace;
     VScal* vscal = (VScal*)(ws + L.vscal);
     uint8_t *fsum = ws + L.fsum, *winsum = ws + L.winsum, *flags = ws + L.flags, *vtab = ws + L.vtab;
+    uint8_t* vseed = ws + L.vseed;
     int8_t *digits = (int8_t*)(ws + L.digits), *vdigits = (int8_t*)(ws + L.vdigits);
     const int nvar = 2 + 2 * k + 3;
     cudaStream_t st = (cudaStream_t)stream;
@@ -756,7 +776,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         CBP_CUDA(cudaStreamWaitEvent(ss, side->ev_fork, 0));
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
-        verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab);
+        verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab, vseed);
         CBP_CHECK_LAUNCH();
         CBP_CUDA(cudaEventRecord(side->ev_join, ss));
         verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits,
@@ -772,7 +792,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         prof_end(BPK_PROF_VERIFY_MSM, st);
         CBP_CHECK_LAUNCH();
         CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
-        verify_winsum_kernel<<<(cnt * 2 * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, cnt, winsum);
+        verify_winsum_kernel<<<(cnt * 2 * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, vseed, k, cnt, winsum);
         CBP_CHECK_LAUNCH();
         verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
         CBP_CHECK_LAUNCH();
