@@ -612,7 +612,7 @@ __global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_
     if (p < num) accept[p] = flags[2 * p] & flags[2 * p + 1];
 }
 
-static constexpr size_t kVerifyChunk = 16384;  // proofs per pass (~40 KiB of scratch per proof); large passes keep the thread-per-proof kernels busy
+static constexpr size_t kVerifyChunk = 16384;  // proofs per pass (~62 KiB of scratch per proof); large passes keep the thread-per-proof kernels busy
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace cbp
