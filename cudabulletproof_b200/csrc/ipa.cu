@@ -321,8 +321,26 @@ int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, co
 }
 
 static size_t ipa_align(size_t x) { return (x + 255) / 256 * 256; }
+struct IpaSide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool ok = false;
+};
+static IpaSide g_ipa_side[16];
+static IpaSide* ipa_side() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    IpaSide& v = g_ipa_side[dev];
+    if (!v.ok) {
+        if (cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&v.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&v.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        v.ok = true;
+    }
+    return &v;
+}
 struct IpaProveLayout {
-    size_t a, b, g, h, scal, pts, small, ipws, msmws, total;
+    size_t a, b, g, h, scal[2], pts[2], small, ipws, msmws[2], total;
 };
 static int ipa_prove_layout(size_t n, IpaProveLayout* L) {
     size_t off = 0;
@@ -335,8 +353,10 @@ static int ipa_prove_layout(size_t n, IpaProveLayout* L) {
     L->b = take(n * 32);
     L->g = take(n * 128);
     L->h = take(n * 128);
-    L->scal = take((n + 1) * 32);
-    L->pts = take((n + 1) * 128);
+    for (int side = 0; side < 2; side++) {  // L and R are multiplied concurrently: own inputs, own workspace
+        L->scal[side] = take((n + 1) * 32);
+        L->pts[side] = take((n + 1) * 128);
+    }
     L->small = take(8 * 32);  // tr | u | uinv | cL | cR
     size_t ipb = 0;
     if (bpk_sc_inner_product_workspace_bytes(n / 2 ? n / 2 : 1, &ipb) != BPK_OK) return BPK_ERR_ARG;
@@ -348,7 +368,8 @@ static int ipa_prove_layout(size_t n, IpaProveLayout* L) {
         msm_make_plan(&p, m + 1, 0);
         if (p.workspace_bytes > msm_bytes) msm_bytes = p.workspace_bytes;
     }
-    L->msmws = take(msm_bytes);
+    L->msmws[0] = take(msm_bytes);
+    L->msmws[1] = take(msm_bytes);
     L->total = off;
     return BPK_OK;
 }
@@ -371,7 +392,9 @@ int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, cons
     if (workspace_bytes < Ly.total) return fail(BPK_ERR_WORKSPACE);
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)d_workspace;
-    uint8_t *a = ws + Ly.a, *b = ws + Ly.b, *g = ws + Ly.g, *h = ws + Ly.h, *scal = ws + Ly.scal, *pts = ws + Ly.pts;
+    uint8_t *a = ws + Ly.a, *b = ws + Ly.b, *g = ws + Ly.g, *h = ws + Ly.h;
+    IpaSide* sd = ipa_side();
+    if (!sd) return fail(BPK_ERR_CUDA);
     uint8_t *tr = ws + Ly.small, *u = tr + 32, *ui = tr + 64, *cL = tr + 96, *cR = tr + 128;
     size_t ipb = 0;
     bpk_sc_inner_product_workspace_bytes(n / 2, &ipb);
@@ -386,16 +409,23 @@ int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, cons
         if ((rc = bpk_sc_inner_product_device(cR, a + np * 32, b, np, ws + Ly.ipws, ipb + 256, st)) != BPK_OK) return rc;
         MsmPlan p;
         msm_make_plan(&p, 2 * np + 1, 0);
+        // L on the caller's stream, R on a side stream with its own workspace and side-stream set
+        CBP_CUDA(cudaEventRecord(sd->ev_fork, st));
+        CBP_CUDA(cudaStreamWaitEvent(sd->stream, sd->ev_fork, 0));
         for (int side = 0; side < 2; side++) {
-            ipa_prove_gather_kernel<<<(unsigned)((np + 1 + 127) / 128), 128, 0, st>>>(side, np, a, b, g, h, (const uint8_t*)d_Q,
+            cudaStream_t ms = side ? sd->stream : st;
+            uint8_t *scal = ws + Ly.scal[side], *pts = ws + Ly.pts[side];
+            ipa_prove_gather_kernel<<<(unsigned)((np + 1 + 127) / 128), 128, 0, ms>>>(side, np, a, b, g, h, (const uint8_t*)d_Q,
                                                                                     side ? cR : cL, scal, pts);
             CBP_CHECK_LAUNCH();
             int nl = 0;
             uint8_t* out = (uint8_t*)(side ? d_R : d_L) + (size_t)round * 128;
-            int mrc = msm_run(p, scal, pts, out, ws + Ly.msmws, 1, st, &nl, nullptr);
+            int mrc = msm_run(p, scal, pts, out, ws + Ly.msmws[side], 1, ms, &nl, nullptr, side);
             count_launches(nl);
             if (mrc) return fail_cuda(mrc);
         }
+        CBP_CUDA(cudaEventRecord(sd->ev_join, sd->stream));
+        CBP_CUDA(cudaStreamWaitEvent(st, sd->ev_join, 0));
         ipa_prove_challenge_kernel<<<1, 32, 0, st>>>(round, tr, (const uint8_t*)d_L + (size_t)round * 128,
                                                      (const uint8_t*)d_R + (size_t)round * 128, (uint8_t*)d_x_out, u, ui);
         CBP_CHECK_LAUNCH();
