@@ -540,7 +540,7 @@ template <int WBITS>
 __global__ void __launch_bounds__(128, 4) pb_fixed_msm_kernel(const uint8_t* __restrict__ gens,
                                                               const PScal* __restrict__ ps,
                                                               const int8_t* __restrict__ digits, int nslots, int nrows,
-                                                              uint32_t num, uint8_t* __restrict__ out) {
+                                                              int3 first_row, uint32_t num, uint8_t* __restrict__ out) {
     constexpr int LP = 256 / WBITS;
     constexpr uint32_t E = 1u << (WBITS - 1);
     const uint32_t unit = (blockIdx.x * blockDim.x + threadIdx.x) / LP;
@@ -570,10 +570,12 @@ __global__ void __launch_bounds__(128, 4) pb_fixed_msm_kernel(const uint8_t* __r
     uint32_t mag;
     bool neg;
     ge_niels q;
-    digit_of(0, mag, neg);
-    if (mag) ge_niels_load(q, table + ((size_t)0 * LP * E + (mag - 1)) * 96);
+    // V, T1, T2 only have the g and h rows: their sums start there instead of walking 2n rows of zero digits
+    const int row0 = slot == 0 ? first_row.x : slot == 1 ? first_row.y : first_row.z;
+    digit_of(row0, mag, neg);
+    if (mag) ge_niels_load(q, table + ((size_t)row0 * LP * E + (mag - 1)) * 96);
 #pragma unroll 1
-    for (int row = 0; row < nrows; row++) {
+    for (int row = row0; row < nrows; row++) {
         uint32_t cmag = mag;
         bool cneg = neg;
         ge_niels cur = q;
@@ -848,14 +850,11 @@ __global__ void __launch_bounds__(kPThreads) pb_ipa_init_kernel(const uint64_t* 
 }
 
 // round r, part 1: cL, cR and the digits of L (slot 0) and R (slot 1) over the ORIGINAL generators
-__global__ void __launch_bounds__(kPThreads) pb_lr_digits_kernel(const uint8_t* __restrict__ gens, uint32_t n, int k, int r,
-                                                                 const PScal* __restrict__ ps, const sc* __restrict__ va,
-                                                                 const sc* __restrict__ vb, const sc* __restrict__ vwg,
-                                                                 const sc* __restrict__ vwh, int8_t* __restrict__ digits) {
-    __shared__ sc sred[kPThreads];
+__device__ __forceinline__ void pb_lr_digits_body(const uint8_t* __restrict__ gens, uint32_t n, int k, int r,
+                                                  const PScal* __restrict__ ps, const sc* va, const sc* vb, const sc* vwg,
+                                                  const sc* vwh, int8_t* __restrict__ digits, sc* sred) {
     const int t = threadIdx.x;
     const uint32_t p = blockIdx.x;
-    if (!ps[p].valid) return;
     const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
     const int row_g = 2 * (int)n, row_h = 2 * (int)n + 1;
     const sc* sa = va + (size_t)p * kMaxN;
@@ -888,6 +887,15 @@ __global__ void __launch_bounds__(kPThreads) pb_lr_digits_kernel(const uint8_t* 
             fix_recode(d + row_h * kFixRowBytes, side == 0 ? cL : cR, wbits);
         }
     }
+}
+
+__global__ void __launch_bounds__(kPThreads) pb_lr_digits_kernel(const uint8_t* __restrict__ gens, uint32_t n, int k, int r,
+                                                                 const PScal* __restrict__ ps, const sc* __restrict__ va,
+                                                                 const sc* __restrict__ vb, const sc* __restrict__ vwg,
+                                                                 const sc* __restrict__ vwh, int8_t* __restrict__ digits) {
+    __shared__ sc sred[kPThreads];
+    if (!ps[blockIdx.x].valid) return;
+    pb_lr_digits_body(gens, n, k, r, ps, va, vb, vwg, vwh, digits, sred);
 }
 
 // round r, part 2: L_r, R_r -> record; challenge u
@@ -929,14 +937,11 @@ __global__ void __launch_bounds__(64) pb_u_kernel(uint8_t* __restrict__ proofs, 
 }
 
 // round r, part 3: fold a, b; update the generator weights
-__global__ void __launch_bounds__(kPThreads) pb_fold_kernel(uint32_t n, int k, int r, uint8_t* __restrict__ proofs,
-                                                            size_t rec_bytes, const PScal* __restrict__ ps,
-                                                            const sc* __restrict__ inv_out, sc* __restrict__ va,
-                                                            sc* __restrict__ vb, sc* __restrict__ vwg,
-                                                            sc* __restrict__ vwh) {
+__device__ __forceinline__ void pb_fold_body(uint32_t n, int k, int r, uint8_t* __restrict__ proofs, size_t rec_bytes,
+                                             const PScal* __restrict__ ps, const sc* __restrict__ inv_out, sc* va, sc* vb,
+                                             sc* vwg, sc* vwh) {
     const int t = threadIdx.x;
     const uint32_t p = blockIdx.x;
-    if (!ps[p].valid) return;
     sc* sa = va + (size_t)p * kMaxN;
     sc* sb = vb + (size_t)p * kMaxN;
     const int nr = (int)n >> r, np = nr >> 1, bitpos = k - 1 - r;
@@ -966,6 +971,21 @@ __global__ void __launch_bounds__(kPThreads) pb_fold_kernel(uint32_t n, int k, i
         uint8_t* rec = proofs + (size_t)p * rec_bytes;
         sc_store(rec + kRecIpA, na);
         sc_store(rec + kRecIpB, nb);
+    }
+}
+
+// fold of round r, then (same CTA, vectors still in cache) the digits of round r + 1
+__global__ void __launch_bounds__(kPThreads) pb_fold_digits_kernel(const uint8_t* __restrict__ gens, uint32_t n, int k, int r,
+                                                                   uint8_t* __restrict__ proofs, size_t rec_bytes,
+                                                                   const PScal* __restrict__ ps,
+                                                                   const sc* __restrict__ inv_out, sc* va, sc* vb, sc* vwg,
+                                                                   sc* vwh, int8_t* __restrict__ digits) {
+    __shared__ sc sred[kPThreads];
+    if (!ps[blockIdx.x].valid) return;
+    pb_fold_body(n, k, r, proofs, rec_bytes, ps, inv_out, va, vb, vwg, vwh);
+    if (r + 1 < k) {
+        __syncthreads();  // the folded vectors were written by other threads of this CTA
+        pb_lr_digits_body(gens, n, k, r + 1, ps, va, vb, vwg, vwh, digits, sred);
     }
 }
 
@@ -1050,11 +1070,11 @@ int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values
         const uint64_t* seeds = d_seeds + done;
         const uint8_t* gam = (const uint8_t*)d_gammas + done * 32;
         uint8_t* proofs = (uint8_t*)d_proofs + done * rec;
-        auto fixed_msm = [&](int nslots) -> int {
+        auto fixed_msm = [&](int nslots, int3 first_row) -> int {
             const int lp = 256 / wbits;
             unsigned grid = (unsigned)(((size_t)cnt * nslots * lp + 127) / 128);
-            if (wbits == 8) pb_fixed_msm_kernel<8><<<grid, 128, 0, st>>>(gens, ps, digits, nslots, nrows, cnt, pts);
-            else pb_fixed_msm_kernel<16><<<grid, 128, 0, st>>>(gens, ps, digits, nslots, nrows, cnt, pts);
+            if (wbits == 8) pb_fixed_msm_kernel<8><<<grid, 128, 0, st>>>(gens, ps, digits, nslots, nrows, first_row, cnt, pts);
+            else pb_fixed_msm_kernel<16><<<grid, 128, 0, st>>>(gens, ps, digits, nslots, nrows, first_row, cnt, pts);
             CBP_CHECK_LAUNCH();
             // normalise every slot of every proof with ONE batch inversion (stale slots are harmless)
             int rc = fe_batch_invert_strided(zinv, pts + 64, 128, (size_t)cnt * 3, st, tree, (size_t)cnt * 3 * 16);
@@ -1072,23 +1092,27 @@ int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values
         CBP_CUDA(cudaMemsetAsync(pts, 0, (size_t)cnt * 3 * 128, st));  // defined contents for skipped (invalid) proofs
         pb_init_kernel<<<cnt, kPThreads, 0, st>>>(gens, vals, gam, seeds, (uint32_t)n, k, proofs, rec, ps, digits);
         CBP_CHECK_LAUNCH();
-        if ((rc = fixed_msm(3)) != BPK_OK) return rc;
+        const int gh = 2 * (int)n;  // first of the two rows g, h
+        if ((rc = fixed_msm(3, make_int3(gh, 0, 0))) != BPK_OK) return rc;  // V | A | S
         pb_yz_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(proofs, rec, pts, cnt, ps, inv_in);
         CBP_CHECK_LAUNCH();
         if ((rc = sc_invert_batch()) != BPK_OK) return rc;
         pb_poly_kernel<<<cnt, kPThreads, 0, st>>>(gens, vals, seeds, (uint32_t)n, k, ps, inv_out, digits, vl0, vr0, vr1, vwh);
         CBP_CHECK_LAUNCH();
-        if ((rc = fixed_msm(2)) != BPK_OK) return rc;
+        if ((rc = fixed_msm(2, make_int3(gh, gh, 0))) != BPK_OK) return rc;  // T1 | T2
         pb_ipa_init_kernel<<<cnt, kPThreads, 0, st>>>(seeds, (uint32_t)n, proofs, rec, pts, ps, vl0, vr0, vr1, va, vb, vwg);
         CBP_CHECK_LAUNCH();
-        for (int r = 0; r < k; r++) {
-            pb_lr_digits_kernel<<<cnt, kPThreads, 0, st>>>(gens, (uint32_t)n, k, r, ps, va, vb, vwg, vwh, digits);
+        if (k > 0) {
+            pb_lr_digits_kernel<<<cnt, kPThreads, 0, st>>>(gens, (uint32_t)n, k, 0, ps, va, vb, vwg, vwh, digits);
             CBP_CHECK_LAUNCH();
-            if ((rc = fixed_msm(2)) != BPK_OK) return rc;
+        }
+        for (int r = 0; r < k; r++) {
+            if ((rc = fixed_msm(2, make_int3(0, 0, 0))) != BPK_OK) return rc;  // L_r | R_r
             pb_u_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(proofs, rec, k, r, pts, cnt, ps, inv_in);
             CBP_CHECK_LAUNCH();
             if ((rc = sc_invert_batch()) != BPK_OK) return rc;
-            pb_fold_kernel<<<cnt, kPThreads, 0, st>>>((uint32_t)n, k, r, proofs, rec, ps, inv_out, va, vb, vwg, vwh);
+            pb_fold_digits_kernel<<<cnt, kPThreads, 0, st>>>(gens, (uint32_t)n, k, r, proofs, rec, ps, inv_out, va, vb, vwg,
+                                                             vwh, digits);
             CBP_CHECK_LAUNCH();
         }
     }
