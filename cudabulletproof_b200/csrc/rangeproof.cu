@@ -380,10 +380,13 @@ __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8
         sc_set1(one);
         y_sh[0] = one;
     }
-    __syncthreads();
+    // levels 0..4 live entirely in warp 0 (t < 32): a warp-level barrier orders them; only the step into the
+    // second warp and the final cross-warp reads need the CTA barrier
+    __syncwarp();
 #pragma unroll 1
     for (int m = 0; m < k; m++) {
         const int half = 1 << m;
+        if (half >= 32) __syncthreads();
         if (t >= half && t < 2 * half) {
             sc a = s_sh[t - half], b = y_sh[t - half];
             sc_mul_nf(a, a, vs.usq[k - 1 - m]);
@@ -391,8 +394,9 @@ __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8
             s_sh[t] = a;
             y_sh[t] = b;
         }
-        __syncthreads();
+        __syncwarp();
     }
+    __syncthreads();
     if (t < (int)n) {
         sc cg, ch, tmp, two_i;
         sc_mul_nf(cg, vs.a, s_sh[t]);
