@@ -816,10 +816,11 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
         int remaining = W;
         while (remaining > 0) {
             int take = remaining > 1 ? remaining / 2 : 1;
-            // the last two windows go together (.., 4, 2, 2): a one-window accumulation is a single partial wave
+            // no one-window groups (16 windows: 8, 4, 2, 2; 18: 9, 4, 2, 3): a one-window accumulation is a single partial wave
             // (48 % of the multiply pipe in ncu against 84 % for the 8-window group); measured 2.27 vs 2.30 ms at
             // 2^20 and 1.43 vs 1.49 ms at 2^19.  Larger last groups lengthen the exposed tail by more than they save.
-            if (remaining <= 2) take = remaining;
+            if (remaining <= 3) take = remaining;
+            else if (take < 2) take = 2;
             if (gm->ngroups == kMaxGroups - 1) take = remaining;
             gm->w_hi[gm->ngroups] = hi;
             gm->w_lo[gm->ngroups] = hi - take + 1;
