@@ -18,6 +18,7 @@
 //   6. msm_reduce_level running-sum reduction  sum_b b*B_b  per window, m buckets per thread, repeated
 //   7. msm_finish       Horner over windows, normalise to Z = 1
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -99,12 +100,28 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const uint8_t* __re
 // 0.39 ms (front end 0.66 instead of 0.49 ms).  Slicing heavy partitions needs a second reserve/scan round and
 // would save < 0.1 ms over the two atomic passes below.
 // signed digits d_w in [-(2^(c-1)-1), 2^(c-1)], sum d_w 2^(cw) = k; bucket index |d|-1.
-template <bool SCATTER>
+// Two passes over the scalars (digits are recomputed, never stored):
+//  PASS 0  counts every (window, bucket) pair.  With cap > 0, windows below w_exact are at the same time
+//          scattered into FIXED slots of `cap` entries per bucket (entries[id * cap + pos]; counts[] is the
+//          cursor), which spares them the second atomic pass: the digits of every window but the top one are
+//          uniform for any scalars that are not adversarial, so a slot of mean + 8 sigma never fills up.  A
+//          bucket that does outgrow its slot raises *overflow (its count stays exact).
+//  PASS 1  exact placement through the scanned cursors, for the windows >= w_exact (the top window of scalars
+//          below the group order populates 1/16 of its buckets at 16x the mean) — or for every window when
+//          *overflow is set (then the slots of pass 0 are ignored and the layout is the compact one).
+template <int PASS>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restrict__ scalars, size_t n, int c, int W,
-                                                         uint32_t B, uint32_t* __restrict__ counters,
-                                                         uint32_t* __restrict__ entries) {
+                                                         uint32_t B, uint32_t cap, int w_exact,
+                                                         uint32_t* __restrict__ counters,
+                                                         uint32_t* __restrict__ entries,
+                                                         uint32_t* __restrict__ overflow) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    int w_from = 0;  // PASS 1: first window this pass places
+    if (PASS == 1) {
+        w_from = *overflow ? 0 : w_exact;
+        if (w_from >= W) return;
+    }
     uint32_t k[8];
     load_scalar_canon(k, scalars + i * 32);
     uint32_t carry = 0;
@@ -127,14 +144,14 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
                     neg = 1;
                     carry = 1;
                 }
-                if (d != 0) {
+                if (d != 0 && w >= w_from) {
                     live[j] = true;
                     id[j] = (uint32_t)w * B + (d - 1);
                     val[j] = ((uint32_t)i << 1) | neg;
                 }
             }
         }
-        if (SCATTER) {
+        if (PASS == 1) {
             uint32_t pos[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -142,6 +159,17 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (live[j]) entries[pos[j]] = val[j];
+        } else if (w0 < w_exact) {  // at least one slotted window in this batch
+            uint32_t pos[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (live[j]) pos[j] = atomicAdd(&counters[id[j]], 1u);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (live[j] && w0 + j < w_exact) {
+                    if (pos[j] < cap) entries[id[j] * cap + pos[j]] = val[j];
+                    else *overflow = 1u;
+                }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -190,18 +218,23 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 __device__ __forceinline__ uint32_t seg_count(uint32_t c, int seg_shift) {
     return c ? (c + (1u << seg_shift) - 1u) >> seg_shift : 1u;
 }
+// SEG = false scans the entry counts of the buckets that are placed compactly: all of them, or — when the
+// first digit pass slotted the windows below w_exact and no slot overflowed — the ids from `slotted` on.
 template <bool SEG>
-__device__ __forceinline__ uint32_t scan_input(uint32_t c, uint32_t id, const GroupMap& gm) {
-    return SEG ? seg_count(c, gm.seg_shift_of_window[id >> gm.log2B]) : c;
+__device__ __forceinline__ uint32_t scan_input(uint32_t c, uint32_t id, const GroupMap& gm, uint32_t slotted) {
+    return SEG ? seg_count(c, gm.seg_shift_of_window[id >> gm.log2B]) : (id >= slotted ? c : 0u);
 }
 template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint32_t total,
-                                                                      GroupMap gm, uint32_t* __restrict__ tile_sums) {
+                                                                      GroupMap gm, uint32_t slotted_ids,
+                                                                      const uint32_t* __restrict__ overflow,
+                                                                      uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t smem[64];
+    const uint32_t slotted = (!SEG && slotted_ids && !*overflow) ? slotted_ids : 0u;
     uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPer, s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++)
-        if (base + j < total) s += scan_input<SEG>(in[base + j], base + j, gm);
+        if (base + j < total) s += scan_input<SEG>(in[base + j], base + j, gm, slotted);
     uint32_t bt;
     block_exclusive_scan(s, smem, bt);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = bt;
@@ -215,23 +248,34 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t* tile_sums, u
 }
 template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t total,
-                                                                  GroupMap gm, const uint32_t* __restrict__ tile_sums,
+                                                                  GroupMap gm, uint32_t slotted_ids, uint32_t cap,
+                                                                  const uint32_t* __restrict__ overflow,
+                                                                  const uint32_t* __restrict__ tile_sums,
                                                                   uint32_t* __restrict__ offsets,
                                                                   uint32_t* __restrict__ cursors) {
     __shared__ uint32_t smem[64];
+    const uint32_t slotted = (!SEG && slotted_ids && !*overflow) ? slotted_ids : 0u;
     uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPer;
     uint32_t v[kScanPer], s = 0;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++) {
-        v[j] = base + j < total ? scan_input<SEG>(in[base + j], base + j, gm) : 0;
+        v[j] = base + j < total ? scan_input<SEG>(in[base + j], base + j, gm, slotted) : 0;
         s += v[j];
     }
     uint32_t bt;
-    uint32_t ex = block_exclusive_scan(s, smem, bt) + tile_sums[blockIdx.x];
+    // the compact runs start behind the slot area
+    uint32_t ex = block_exclusive_scan(s, smem, bt) + tile_sums[blockIdx.x] + slotted * cap;
 #pragma unroll
     for (int j = 0; j < kScanPer; j++) {
-        if (base + j <= total) offsets[base + j] = ex;  // offsets[total] = grand total (sentinel)
-        if (cursors && base + j < total) cursors[base + j] = ex;
+        const uint32_t id = base + j;
+        if (!SEG && id < slotted) {  // already placed by the first digit pass: run = [id * cap, id * cap + count)
+            offsets[id] = id * cap;
+            cursors[id] = id * cap + in[id];
+        } else {
+            if (id <= total) offsets[id] = ex;  // offsets[total] = end of the compact area (sentinel)
+            // the placing pass advances the cursors: afterwards cursors[id] is the END of bucket id's run
+            if (cursors && id < total) cursors[id] = ex;
+        }
         ex += v[j];
     }
 }
@@ -283,8 +327,9 @@ __global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restri
         heavy[(uint32_t)gm.w_lo[g] * B + idx] = id;
     }
 }
-__device__ __forceinline__ uint32_t seg_length(uint2 d, const uint32_t* __restrict__ offsets, const GroupMap& gm) {
-    uint32_t rest = offsets[d.y + 1] - d.x, cap = 1u << gm.seg_shift_of_window[d.y >> gm.log2B];
+// `ends` = the cursors after the placing pass (end of each bucket's run; runs need not be adjacent)
+__device__ __forceinline__ uint32_t seg_length(uint2 d, const uint32_t* __restrict__ ends, const GroupMap& gm) {
+    uint32_t rest = ends[d.y] - d.x, cap = 1u << gm.seg_shift_of_window[d.y >> gm.log2B];
     return rest < cap ? rest : cap;
 }
 __device__ __forceinline__ uint32_t seg_bin(uint2 d, const uint32_t* __restrict__ offsets, const GroupMap& gm) {
@@ -746,9 +791,29 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->off_segoff = take(((size_t)p->nbuckets + 1) * 4);
     p->off_desc = take(p->max_segs * 8);
     p->off_order = take(p->max_segs * 4);
-    p->off_bins = take((2 * kSegBins + 1 + kMaxGroups) * 4);  // hist/cursors | binstart (+1) | heavy counters
+    p->off_bins = take((2 * kSegBins + 2 + kMaxGroups) * 4);  // hist/cursors | binstart (+1) | heavy counters | slot overflow flag
     p->off_heavy = take((size_t)p->nbuckets * 4);
-    p->off_entries = take(n * (size_t)p->W * 4 + 4);
+    // Fixed slots for the first digit pass (msm_digits_kernel<0>): every window but the top one, mean + 8 sigma
+    // (+8) entries per bucket, a multiple of 8 so that a slot starts on a sector boundary.  From 2^19 points
+    // (CBP_MSM_SLOTS=0/1 forces); measured two-pass / slotted: 2^18 1.06 / 1.11 ms, 2^19 1.43 / 1.41,
+    // 2^20 2.27 / 2.20, 2^22 7.02 / 6.76.
+    p->cap = 0;
+    p->w_exact = 0;
+    bool slots = n >= ((size_t)1 << 19);
+    if (const char* ev = getenv("CBP_MSM_SLOTS")) slots = ev[0] == '1';
+    size_t entry_words = n * (size_t)p->W;
+    if (slots && p->W > 1) {
+        double mean = (double)n / (double)p->B;
+        size_t cap = (size_t)(mean + 8.0 * sqrt(mean) + 8.0);
+        cap = (cap + 7) & ~(size_t)7;
+        size_t slot_words = (size_t)(p->W - 1) * p->B * cap;
+        if (slot_words + n * (size_t)p->W < ((size_t)1 << 32)) {  // entry offsets are 32-bit
+            p->cap = (uint32_t)cap;
+            p->w_exact = p->W - 1;
+            if (slot_words + n > entry_words) entry_words = slot_words + n;
+        }
+    }
+    p->off_entries = take(entry_words * 4 + 4);
     p->off_buckets = take((size_t)p->nbuckets * 128);
     p->off_segsums = take(p->max_segs * 128);
     uint32_t n1 = (p->B + kReduceM - 1) / kReduceM;
@@ -861,6 +926,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     uint32_t* bins = (uint32_t*)(ws + p.off_bins);
     uint32_t* binstart = bins + kSegBins;
     uint32_t* heavy_cnt = binstart + kSegBins + 1;
+    uint32_t* overflow = heavy_cnt + kMaxGroups;
     uint32_t* heavy = (uint32_t*)(ws + p.off_heavy);
     uint32_t* entries = (uint32_t*)(ws + p.off_entries);
     uint8_t* buckets = ws + p.off_buckets;
@@ -886,7 +952,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 1 + kMaxGroups) * 4, st);
+    e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 2 + kMaxGroups) * 4, st);
     if (e != cudaSuccess) return (int)e;
     {
         // the affine table depends only on the points: build it on a side stream while the scalar-only
@@ -907,33 +973,39 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     }
     prof_begin(BPK_PROF_MSM_FRONT, st);
     unsigned dgrid = (unsigned)((n + 255) / 256);
-    msm_digits_kernel<false><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, counts, nullptr);
+    const uint32_t slotted_ids = (uint32_t)p.w_exact * p.B;  // buckets placed by the first pass (0: none)
+    msm_digits_kernel<0><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, counts,
+                                                entries, overflow);
     CBP_LAUNCH_CHECK(); nl++;
     uint32_t ntiles = (p.nbuckets + 1 + kScanTile - 1) / kScanTile;  // +1: the sentinel slot
-    scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles);
+    scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, overflow, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles, offsets, cursors);
+    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, p.cap, overflow, tiles,
+                                                              offsets, cursors);
     CBP_LAUNCH_CHECK(); nl++;
-    msm_digits_kernel<true><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, cursors, entries);
+    msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
+                                                entries, overflow);
     CBP_LAUNCH_CHECK(); nl++;
+    const uint32_t* ends = cursors;  // after the placing pass: end of every bucket's run
     // segments
-    scan_tile_sums_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles);
+    scan_tile_sums_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, 0u, overflow, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, tiles, segoff, nullptr);
+    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, 0u, 0u, overflow, tiles, segoff,
+                                                             nullptr);
     CBP_LAUNCH_CHECK(); nl++;
     const uint32_t* nsegs_p = segoff + p.nbuckets;
     unsigned bgrid = (p.nbuckets + 255) / 256, sgrid = (unsigned)((p.max_segs + 255) / 256);
     seg_build_kernel<<<bgrid, 256, 0, st>>>(counts, offsets, segoff, p.nbuckets, p.B, gm, desc, heavy, heavy_cnt);
     CBP_LAUNCH_CHECK(); nl++;
-    seg_hist_kernel<<<sgrid < 1184 ? sgrid : 1184, 256, 0, st>>>(desc, offsets, nsegs_p, gm, bins);
+    seg_hist_kernel<<<sgrid < 1184 ? sgrid : 1184, 256, 0, st>>>(desc, ends, nsegs_p, gm, bins);
     CBP_LAUNCH_CHECK(); nl++;
     seg_bin_scan_kernel<<<1, kSegBins, 0, st>>>(bins, binstart);
     CBP_LAUNCH_CHECK(); nl++;
-    seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, offsets, nsegs_p, gm, bins, order);
+    seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, ends, nsegs_p, gm, bins, order);
     CBP_LAUNCH_CHECK(); nl++;
 
     prof_end(BPK_PROF_MSM_FRONT, st);
@@ -947,7 +1019,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         const int gshift = gm.seg_shift_of_window[w_lo];
         size_t seg_bound = (size_t)nwin * p.B + ((n * (size_t)nwin) >> gshift) + 1;
         if (g == 0) prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
-        msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, offsets, segoff,
+        msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, ends, segoff,
                                                                                   gm, order, binstart, g, carry,
                                                                                   buckets, segsums);
         if (g == gm.ngroups - 1) {

@@ -12,6 +12,8 @@ struct MsmPlan {
     int W;              // number of windows = ceil(256 / c)
     uint32_t B;         // buckets per window = 2^(c-1)
     uint32_t nbuckets;  // W * B
+    uint32_t cap;       // entries per fixed bucket slot of the first digit pass (0: every window takes both passes)
+    int w_exact;        // windows below this one are slotted, the others placed exactly by the second pass
     int seg_shift;      // log2 of the accumulation segment length
     size_t max_segs;    // upper bound on accumulation segments (buckets + entries / segment length)
     size_t off_table, off_counts, off_offsets, off_cursors, off_tiles, off_segoff, off_desc, off_order, off_bins, off_heavy,

@@ -198,3 +198,62 @@ def test_msm_host_pointer_chunked_equal_scalars(oracle):
     oracle.ge25519_scalarmult_base(ob.ptr(want), ((k % L) * total % L).to_bytes(32, "little"))
     oracle.ge25519_normalize(ob.ptr(want))
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("slots", ["0", "1"])
+@pytest.mark.parametrize("window_bits", [7, 11])
+def test_msm_slotted_front_end_small(oracle, monkeypatch, slots, window_bits):
+    """The first digit pass places every window but the top one into fixed bucket slots (msm.cu,
+    msm_digits_kernel<0>; default from 2^19 points, forced here).  Random scalars stay inside the slots;
+    repeated scalars overflow them and take the exact two-pass placement: same bytes either way."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    monkeypatch.setenv("CBP_MSM_SLOTS", slots)
+    rng = random.Random(900 + window_bits)
+    n = 600
+    pts = np.stack([ob.affine_to_ge(*p) for p in curve_points(rng, n)])
+    d_p = torch.from_numpy(pts.view(np.uint8).reshape(n, 128)).cuda()
+    k = rng.getrandbits(255)
+    cases = {
+        "random": [rng.getrandbits(256) for _ in range(n)],
+        "mod_l": [rng.getrandbits(256) % L for _ in range(n)],
+        "equal (every slot of the run overflows)": [k] * n,
+        "half equal": [k if i % 2 else rng.getrandbits(253) for i in range(n)],
+        "one overflowing low window": [(rng.getrandbits(240) << 16) | 0x1234 for _ in range(n)],
+    }
+    msm = cbp.Msm(n, window_bits=window_bits)
+    for name, ints in cases.items():
+        sc = ob.ints_to_fe(ints)
+        d_s = torch.from_numpy(sc.view(np.uint8).reshape(n, 32)).cuda()
+        got = msm(d_s, d_p).cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, oracle_msm(oracle, sc, pts)), name
+
+
+def test_msm_slotted_equals_two_pass_at_size(oracle, monkeypatch):
+    """2^18 points, both forced: the slotted and the two-pass front end give identical bytes, for
+    252-bit random scalars and for an adversarial input that overflows the slots."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    n = 1 << 18
+    pts, ks = cbp.synth_points(n, seed=0x51075)
+    sc = cbp.synth_scalars(n, seed=0x51076, bits=252)
+    adv = sc.clone()
+    adv[: n // 2] = adv[0]  # half of the scalars equal: 2^17 entries in one bucket per window
+    out = {}
+    for slots in ("1", "0"):
+        monkeypatch.setenv("CBP_MSM_SLOTS", slots)
+        msm = cbp.Msm(n)
+        out[slots] = (msm(sc, pts).cpu().numpy().copy(), msm(adv, pts).cpu().numpy().copy())
+        torch.cuda.synchronize()
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])
+    # anchor on the oracle: sum s_i k_i * B
+    ks_h = ks.cpu().numpy().astype(np.uint64)
+    sc_h = sc.cpu().numpy().view(np.uint64).reshape(n, 4)
+    acc = 0
+    for i in range(n):
+        acc += (int(sc_h[i, 0]) | int(sc_h[i, 1]) << 64 | int(sc_h[i, 2]) << 128 | int(sc_h[i, 3]) << 192) * int(ks_h[i])
+    want = np.zeros(16, dtype=np.uint64)
+    oracle.ge25519_scalarmult_base(ob.ptr(want), (acc % L).to_bytes(32, "little"))
+    oracle.ge25519_normalize(ob.ptr(want))
+    assert np.array_equal(out["1"][0].view(np.uint64), want)
