@@ -708,6 +708,105 @@ __global__ void __launch_bounds__(128) msm_reduce_warp_quad_kernel(const uint8_t
     }
 }
 
+// ---- 6c. low-latency reduction for the exposed tail ----------------------------------------------------
+// The running-sum levels above are work-efficient but ~110 dependent point operations deep (21 in level 0,
+// ~31 in each of the three warp levels), and for the LAST window group (and for small MSMs throughout) that
+// depth is the exposed tail of the call.  Here the bucket index j (weight j + 1) is split as j = hi * 2^lbits + lo:
+//     sum_j (j+1) X_j = 2^lbits * sum_hi hi R_hi + sum_lo lo C_lo + T,
+// R_hi / C_lo the row / column sums of the (hi, lo) grid (msm_reduce2d_sums_kernel: one CTA per row or column,
+// strided quad sums + shuffle tree), T the grand total.  The two short weighted sums are taken bit by bit,
+//     sum_i i Z_i = sum_k 2^k S_k,   S_k = sum of the Z_i whose index has bit k set,
+// one CTA per bit (msm_reduce2d_bits_kernel, every S_k a plain tree sum again; T by one more CTA), which leaves
+// ONE point Q_p per bit position p of the bucket weight: a Horner chain of c - 2 doublings and c - 1 additions
+// on a quad (msm_reduce2d_horner_kernel).  About 2x the additions of the running-sum scheme, at a depth of
+// ~12 + ~12 + 2c quad operations.
+// These kernels are a few dozen dependent additions executed ONCE: cold instruction fetch is a large part of
+// their time, so the sums share one loop with exactly one inlined copy of the (quad-cooperative) addition.
+//
+// Sum of the points src[(first + i * stride)], i in [0, count) with (i & mask) == mask (mask = 0 or one bit), by
+// one CTA of 128 threads = 32 quads: strided quad sums, shuffle tree over the 8 quads of a warp, the 4 warp
+// results through shared memory.  Result in every lane of quad 0 of warp 0.
+__device__ __forceinline__ void block_quad_point_sum(ge_p3& acc, const uint8_t* __restrict__ src, uint32_t first,
+                                                     uint32_t stride, uint32_t count, uint32_t mask,
+                                                     uint8_t (*sh)[128]) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, quad = threadIdx.x >> 2;  // quad 0..31
+    const uint32_t nsel = mask ? count >> 1 : count;  // selected elements, enumerated by t
+    const uint32_t low = mask ? mask - 1u : 0u;
+    const int nseq = (int)((nsel + 31u) / 32u);
+    ge_p3_0(acc);
+#pragma unroll 1
+    for (int step = 0; step < nseq + 5; step++) {
+        ge_p3 x;
+        if (step < nseq) {
+            const uint32_t t = quad + 32u * (uint32_t)step;
+            ge_p3_0(x);
+            if (t < nsel) {
+                const uint32_t i = mask ? (((t & ~low) << 1) | mask | (t & low)) : t;
+                ge_load(x, src + (size_t)(first + i * stride) * 128);
+            }
+        } else {
+            if (step == nseq + 3) {  // the four warp sums meet in warp 0 (the other warps idle along)
+                if (lane == 0) ge_store(sh[warp], acc);
+                __syncthreads();
+                ge_load(acc, sh[(lane >> 2) & 3]);
+            }
+            const int s2 = step - nseq;  // quad distances 4, 2, 1 within the warp, then 2, 1 over the warp sums
+            ge_shfl_down(x, acc, s2 < 3 ? (16 >> s2) : (8 >> (s2 - 3)));
+        }
+        ge_add_quad(acc, acc, x);
+    }
+}
+// one CTA per (window, row or column)
+__global__ void __launch_bounds__(128) msm_reduce2d_sums_kernel(const uint8_t* __restrict__ X, uint32_t B, int lbits,
+                                                                uint32_t out_stride, uint8_t* __restrict__ sums) {
+    __shared__ __align__(16) uint8_t sh[4][128];
+    const uint32_t Lo = 1u << lbits, H = B >> lbits, per = H + Lo;
+    const uint32_t w = blockIdx.x / per, r = blockIdx.x % per;
+    const uint8_t* xb = X + (size_t)w * B * 128;
+    ge_p3 acc;
+    const bool row = r < H;  // row r: lo = 0 .. Lo-1; column r - H: hi = 0 .. H-1
+    block_quad_point_sum(acc, xb, row ? r * Lo : r - H, row ? 1u : Lo, row ? Lo : H, 0u, sh);
+    if (threadIdx.x == 0) ge_store(sums + ((size_t)w * out_stride + r) * 128, acc);
+}
+// one CTA per (window, bit of the bucket index) and one per window for the total T = sum of all rows;
+// output Q[w][p], p = bit position (column bits first), Q[w][nb] = T
+__global__ void __launch_bounds__(128) msm_reduce2d_bits_kernel(const uint8_t* __restrict__ sums, uint32_t in_stride,
+                                                                uint32_t B, int lbits, int hbits,
+                                                                uint8_t* __restrict__ Q) {
+    __shared__ __align__(16) uint8_t sh[4][128];
+    const int nb = lbits + hbits;
+    const uint32_t w = blockIdx.x / (uint32_t)(nb + 1);
+    const int role = (int)(blockIdx.x % (uint32_t)(nb + 1));
+    const uint32_t Lo = 1u << lbits, H = B >> lbits;
+    const uint8_t* rows = sums + (size_t)w * in_stride * 128;
+    const uint8_t* cols = rows + (size_t)H * 128;
+    ge_p3 acc;
+    const bool col = role < lbits;
+    const uint32_t mask = col ? 1u << role : (role < nb ? 1u << (role - lbits) : 0u);
+    block_quad_point_sum(acc, col ? cols : rows, 0u, 1u, col ? Lo : H, mask, sh);
+    if (threadIdx.x == 0) ge_store(Q + ((size_t)w * 32 + role) * 128, acc);
+}
+// one warp per window: Horner over the bit positions on a quad, acc = 2 acc + Q_p, finally + T
+__global__ void __launch_bounds__(32) msm_reduce2d_horner_kernel(const uint8_t* __restrict__ Q, int nb,
+                                                                 uint8_t* __restrict__ winX,
+                                                                 uint8_t* __restrict__ winY) {
+    const uint32_t w = blockIdx.x;
+    const uint8_t* q = Q + (size_t)w * 32 * 128;
+    ge_p3 acc, x;
+    ge_load(acc, q + (size_t)(nb - 1) * 128);
+#pragma unroll 1
+    for (int pbit = nb - 2; pbit >= -1; pbit--) {
+        if (pbit >= 0) ge_dbl_quad(acc, acc);
+        ge_load(x, q + (size_t)(pbit >= 0 ? pbit : nb) * 128);
+        ge_add_quad(acc, acc, x);
+    }
+    if (threadIdx.x == 0) {
+        ge_store(winX + (size_t)w * 128, acc);
+        ge_p3_0(x);
+        ge_store(winY + (size_t)w * 128, x);
+    }
+}
+
 // ---- 7. window combine + normalise --------------------------------------------------------------
 // Horner chain over the windows, top down, kept in `state` between calls so that the chain for the
 // upper windows runs (on a second stream) while the lower windows are still being accumulated:
@@ -1048,7 +1147,23 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         const uint8_t* Y = X;
         uint32_t n_in = p.B, in_stride = p.B;
         int has_y = 0, pp = 0, level = 0;
-        do {
+        // exposed tails (last group of the pipeline, small MSMs): the shallow 2-D reduction (6c)
+        static const bool no2d = getenv("CBP_MSM_NO2D") != nullptr;
+        if ((kit == nullptr || nwin <= 2) && p.c >= 9 && !no2d) {
+            const int lbits = (p.c - 1) / 2, hbits = p.c - 1 - lbits;
+            const uint32_t per = (p.B >> lbits) + (1u << lbits);  // <= n1 for c >= 9
+            uint8_t* sums = ws + p.off_redX[0] + (size_t)w_lo * n1 * 128;
+            uint8_t* Q = ws + p.off_redY[0] + (size_t)w_lo * n1 * 128;  // 32 slots per window (n1 >= 32)
+            msm_reduce2d_sums_kernel<<<per * (uint32_t)nwin, 128, 0, tail>>>(X, p.B, lbits, n1, sums);
+            CBP_LAUNCH_CHECK(); nl++;
+            msm_reduce2d_bits_kernel<<<(unsigned)(nwin * p.c), 128, 0, tail>>>(sums, n1, p.B, lbits, hbits, Q);
+            CBP_LAUNCH_CHECK(); nl++;
+            msm_reduce2d_horner_kernel<<<nwin, 32, 0, tail>>>(Q, p.c - 1, winX + (size_t)w_lo * 128,
+                                                              winY + (size_t)w_lo * 128);
+            CBP_LAUNCH_CHECK(); nl++;
+            n_in = 1;
+        }
+        while (n_in > 1) {
             bool seq = level == 0;  // level 0 is work-efficient (thread-sequential), upper levels warp-cooperative
             // small groups are latency-exposed: quad-cooperative kernels; large groups overlap with later
             // accumulations and use the work-efficient one-lane-per-chunk kernels
@@ -1091,7 +1206,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
             has_y = 1;
             pp ^= 1;
             level++;
-        } while (n_in > 1);
+        }
         cudaStream_t hs = tail;
         if (kit) {
             hs = kit->aux;
