@@ -713,8 +713,8 @@ __global__ void __launch_bounds__(128) msm_reduce_warp_quad_kernel(const uint8_t
 // ~31 in each of the three warp levels), and for the LAST window group (and for small MSMs throughout) that
 // depth is the exposed tail of the call.  Here the bucket index j (weight j + 1) is split as j = hi * 2^lbits + lo:
 //     sum_j (j+1) X_j = 2^lbits * sum_hi hi R_hi + sum_lo lo C_lo + T,
-// R_hi / C_lo the row / column sums of the (hi, lo) grid (msm_reduce2d_sums_kernel: one CTA per row or column,
-// strided quad sums + shuffle tree), T the grand total.  The two short weighted sums are taken bit by bit,
+// R_hi / C_lo the row / column sums of the (hi, lo) grid (msm_reduce2d_partial_kernel + msm_reduce2d_sums_kernel),
+// T the grand total.  The two short weighted sums are taken bit by bit,
 //     sum_i i Z_i = sum_k 2^k S_k,   S_k = sum of the Z_i whose index has bit k set,
 // one CTA per bit (msm_reduce2d_bits_kernel, every S_k a plain tree sum again; T by one more CTA), which leaves
 // ONE point Q_p per bit position p of the bucket weight: a Horner chain of c - 2 doublings and c - 1 additions
@@ -726,26 +726,30 @@ __global__ void __launch_bounds__(128) msm_reduce_warp_quad_kernel(const uint8_t
 // Sum of the points src[(first + i * stride)], i in [0, count) with (i & mask) == mask (mask = 0 or one bit), by
 // one CTA of 128 threads = 32 quads: strided quad sums, shuffle tree over the 8 quads of a warp, the 4 warp
 // results through shared memory.  Result in every lane of quad 0 of warp 0.
+// NWARP = 1: the same by one warp (8 quads), no shared memory; result in quad 0 of that warp.
+template <int NWARP>
 __device__ __forceinline__ void block_quad_point_sum(ge_p3& acc, const uint8_t* __restrict__ src, uint32_t first,
                                                      uint32_t stride, uint32_t count, uint32_t mask,
                                                      uint8_t (*sh)[128]) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, quad = threadIdx.x >> 2;  // quad 0..31
+    constexpr uint32_t NQ = 8u * NWARP;  // quads that share the sum
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t quad = NWARP == 1 ? lane >> 2 : threadIdx.x >> 2;
     const uint32_t nsel = mask ? count >> 1 : count;  // selected elements, enumerated by t
     const uint32_t low = mask ? mask - 1u : 0u;
-    const int nseq = (int)((nsel + 31u) / 32u);
+    const int nseq = (int)((nsel + NQ - 1u) / NQ);
     ge_p3_0(acc);
 #pragma unroll 1
-    for (int step = 0; step < nseq + 5; step++) {
+    for (int step = 0; step < nseq + (NWARP == 1 ? 3 : 5); step++) {
         ge_p3 x;
         if (step < nseq) {
-            const uint32_t t = quad + 32u * (uint32_t)step;
+            const uint32_t t = quad + NQ * (uint32_t)step;
             ge_p3_0(x);
             if (t < nsel) {
                 const uint32_t i = mask ? (((t & ~low) << 1) | mask | (t & low)) : t;
                 ge_load(x, src + (size_t)(first + i * stride) * 128);
             }
         } else {
-            if (step == nseq + 3) {  // the four warp sums meet in warp 0 (the other warps idle along)
+            if (NWARP > 1 && step == nseq + 3) {  // the four warp sums meet in warp 0 (the other warps idle along)
                 if (lane == 0) ge_store(sh[warp], acc);
                 __syncthreads();
                 ge_load(acc, sh[(lane >> 2) & 3]);
@@ -756,17 +760,45 @@ __device__ __forceinline__ void block_quad_point_sum(ge_p3& acc, const uint8_t* 
         ge_add_quad(acc, acc, x);
     }
 }
-// one CTA per (window, row or column)
-__global__ void __launch_bounds__(128) msm_reduce2d_sums_kernel(const uint8_t* __restrict__ X, uint32_t B, int lbits,
-                                                                uint32_t out_stride, uint8_t* __restrict__ sums) {
-    __shared__ __align__(16) uint8_t sh[4][128];
-    const uint32_t Lo = 1u << lbits, H = B >> lbits, per = H + Lo;
-    const uint32_t w = blockIdx.x / per, r = blockIdx.x % per;
+// Row and column sums in two steps.  (A single step — one CTA per row or column, strided quad sums and a
+// shuffle tree — is issue-bound: a quad addition costs ~1000 warp instructions for 8 additions, a thread-level
+// one ~2000 for 32; measured 54 us for two windows of 2^15 buckets.)
+// (1) work-efficient, thread-level: every thread adds 8 consecutive buckets of a row (PR) resp. of a column (PC)
+__global__ void __launch_bounds__(128) msm_reduce2d_partial_kernel(const uint8_t* __restrict__ X, uint32_t B, int lbits,
+                                                                   int nwin, uint32_t out_stride,
+                                                                   uint8_t* __restrict__ PR, uint8_t* __restrict__ PC) {
+    const uint32_t n8 = B >> 3, Lo = 1u << lbits;
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= 2u * n8 * (uint32_t)nwin) return;
+    const uint32_t w = g / (2u * n8), r = g % (2u * n8);
+    const bool row = r < n8;
+    const uint32_t t = row ? r : r - n8;
+    // row chunk t: buckets 8t .. 8t+7;  column chunk t = hi8 * Lo + lo: buckets (8 hi8 + j) * Lo + lo
+    const uint32_t first = row ? t * 8u : ((t >> lbits) * 8u << lbits) + (t & (Lo - 1u));
+    const uint32_t stride = row ? 1u : Lo;
     const uint8_t* xb = X + (size_t)w * B * 128;
+    ge_p3 acc, x;
+    ge_load(acc, xb + (size_t)first * 128);
+#pragma unroll 1
+    for (uint32_t j = 1; j < 8; j++) {
+        ge_load(x, xb + (size_t)(first + j * stride) * 128);
+        ge_add(acc, acc, x);
+    }
+    ge_store((row ? PR : PC) + ((size_t)w * out_stride + t) * 128, acc);
+}
+// (2) one warp per (window, row or column): the Lo/8 resp. H/8 partial sums, on quads
+__global__ void __launch_bounds__(128) msm_reduce2d_sums_kernel(const uint8_t* __restrict__ PR,
+                                                                const uint8_t* __restrict__ PC, uint32_t B, int lbits,
+                                                                int nwin, uint32_t stride, uint8_t* __restrict__ sums) {
+    const uint32_t Lo = 1u << lbits, H = B >> lbits, per = H + Lo;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= per * (uint32_t)nwin) return;  // whole warp
+    const uint32_t w = gw / per, r = gw % per;
     ge_p3 acc;
-    const bool row = r < H;  // row r: lo = 0 .. Lo-1; column r - H: hi = 0 .. H-1
-    block_quad_point_sum(acc, xb, row ? r * Lo : r - H, row ? 1u : Lo, row ? Lo : H, 0u, sh);
-    if (threadIdx.x == 0) ge_store(sums + ((size_t)w * out_stride + r) * 128, acc);
+    const bool row = r < H;  // row r: its Lo/8 chunks are adjacent; column r - H: chunk hi8 at hi8 * Lo + lo
+    const uint8_t* src = (row ? PR : PC) + (size_t)w * stride * 128;
+    block_quad_point_sum<1>(acc, src, row ? r * (Lo >> 3) : r - H, row ? 1u : Lo, row ? Lo >> 3 : H >> 3, 0u, nullptr);
+    if ((threadIdx.x & 31) == 0) ge_store(sums + ((size_t)w * stride + r) * 128, acc);
 }
 // one CTA per (window, bit of the bucket index) and one per window for the total T = sum of all rows;
 // output Q[w][p], p = bit position (column bits first), Q[w][nb] = T
@@ -783,7 +815,7 @@ __global__ void __launch_bounds__(128) msm_reduce2d_bits_kernel(const uint8_t* _
     ge_p3 acc;
     const bool col = role < lbits;
     const uint32_t mask = col ? 1u << role : (role < nb ? 1u << (role - lbits) : 0u);
-    block_quad_point_sum(acc, col ? cols : rows, 0u, 1u, col ? Lo : H, mask, sh);
+    block_quad_point_sum<4>(acc, col ? cols : rows, 0u, 1u, col ? Lo : H, mask, sh);
     if (threadIdx.x == 0) ge_store(Q + ((size_t)w * 32 + role) * 128, acc);
 }
 // one warp per window: Horner over the bit positions on a quad, acc = 2 acc + Q_p, finally + T
@@ -968,7 +1000,7 @@ StreamKit* stream_kit(int idx) {
 // windows are processed top-down in groups of halving size (.., 4, 2, 2): while the lower groups are
 // still being accumulated, the upper groups are reduced and folded into the Horner chain on a second
 // stream, so only the last (single-window) group's reduction latency is exposed.
-static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline) {
+static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline, int last_max) {
     gm->ngroups = 0;
     gm->log2B = c - 1;
     int hi = W - 1;
@@ -982,8 +1014,8 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
             int take = remaining > 1 ? remaining / 2 : 1;
             // no one-window groups (16 windows: 8, 4, 2, 2; 18: 9, 4, 2, 3): a one-window accumulation is a single partial wave
             // (48 % of the multiply pipe in ncu against 84 % for the 8-window group); measured 2.27 vs 2.30 ms at
-            // 2^20 and 1.43 vs 1.49 ms at 2^19.  Larger last groups lengthen the exposed tail by more than they save.
-            if (remaining <= 3) take = remaining;
+            // 2^20 and 1.43 vs 1.49 ms at 2^19.  Larger last groups lengthen the exposed tail (last_max: see msm_run).
+            if (remaining <= last_max) take = remaining;
             else if (take < 2) take = 2;
             if (gm->ngroups == kMaxGroups - 1) take = remaining;
             gm->w_hi[gm->ngroups] = hi;
@@ -999,6 +1031,8 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
         // SMs full (the extra partial sums are folded by msm_heavy_small_kernel)
         int shift = seg_shift;
         if (pipeline && gm->ngroups > 1) {
+            // (re-measured with the slotted front end, segment shift -1 / -2 / -3 for the 2-window groups and
+            // 0 / -1 / -2 for the 4-window group: 2.19 - 2.20 ms at 2^20 for -1..-2 / 0..-1, worse beyond)
             if (nwin <= 1) shift -= 2;
             else if (nwin <= 3) shift -= 1;
         }
@@ -1046,7 +1080,9 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     // a chunk that only adds into the buckets has no tails to overlap: one group, everything on `st`
     StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(kit_index) : nullptr;
     GroupMap gm;
-    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr);
+    // the last group's reduction is exposed; with the shallow 2-D reduction a 4-window last group (16 windows:
+    // 8, 4, 4) pays from 2^20 points (8,4,2,2 / 8,4,4: 2^19 1.43 / 1.44 ms, 2^20 2.19 / 2.16, 2^22 6.70 / 6.57)
+    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 20) ? 4 : 3);
 
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
@@ -1149,12 +1185,18 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         int has_y = 0, pp = 0, level = 0;
         // exposed tails (last group of the pipeline, small MSMs): the shallow 2-D reduction (6c)
         static const bool no2d = getenv("CBP_MSM_NO2D") != nullptr;
-        if ((kit == nullptr || nwin <= 2) && p.c >= 9 && !no2d) {
+        if ((kit == nullptr || nwin <= 2 || g == gm.ngroups - 1) && p.c >= 9 && !no2d) {
             const int lbits = (p.c - 1) / 2, hbits = p.c - 1 - lbits;
             const uint32_t per = (p.B >> lbits) + (1u << lbits);  // <= n1 for c >= 9
             uint8_t* sums = ws + p.off_redX[0] + (size_t)w_lo * n1 * 128;
             uint8_t* Q = ws + p.off_redY[0] + (size_t)w_lo * n1 * 128;  // 32 slots per window (n1 >= 32)
-            msm_reduce2d_sums_kernel<<<per * (uint32_t)nwin, 128, 0, tail>>>(X, p.B, lbits, n1, sums);
+            uint8_t* PR = ws + p.off_redX[1] + (size_t)w_lo * n1 * 128;  // B/8 = n1 chunk sums per window each
+            uint8_t* PC = ws + p.off_redY[1] + (size_t)w_lo * n1 * 128;
+            const uint32_t pthreads = 2u * (p.B >> 3) * (uint32_t)nwin;
+            msm_reduce2d_partial_kernel<<<(pthreads + 127) / 128, 128, 0, tail>>>(X, p.B, lbits, nwin, n1, PR, PC);
+            CBP_LAUNCH_CHECK(); nl++;
+            msm_reduce2d_sums_kernel<<<(per * (uint32_t)nwin * 32u + 127) / 128, 128, 0, tail>>>(PR, PC, p.B, lbits, nwin,
+                                                                                                 n1, sums);
             CBP_LAUNCH_CHECK(); nl++;
             msm_reduce2d_bits_kernel<<<(unsigned)(nwin * p.c), 128, 0, tail>>>(sums, n1, p.B, lbits, hbits, Q);
             CBP_LAUNCH_CHECK(); nl++;
