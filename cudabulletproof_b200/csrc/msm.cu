@@ -1185,7 +1185,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         int has_y = 0, pp = 0, level = 0;
         // exposed tails (last group of the pipeline, small MSMs): the shallow 2-D reduction (6c)
         static const bool no2d = getenv("CBP_MSM_NO2D") != nullptr;
-        if ((kit == nullptr || nwin <= 2 || g == gm.ngroups - 1) && p.c >= 9 && !no2d) {
+        static const int from2d = getenv("CBP_2D_FROM") ? atoi(getenv("CBP_2D_FROM")) : 99;
+        if ((kit == nullptr || nwin <= 2 || g == gm.ngroups - 1 || g >= from2d) && p.c >= 9 && !no2d) {
             const int lbits = (p.c - 1) / 2, hbits = p.c - 1 - lbits;
             const uint32_t per = (p.B >> lbits) + (1u << lbits);  // <= n1 for c >= 9
             uint8_t* sums = ws + p.off_redX[0] + (size_t)w_lo * n1 * 128;
