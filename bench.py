@@ -293,11 +293,11 @@ def run_cuda(args):
         roofline = {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": imad_acc / (acc_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": imad_acc / (acc_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
                     "traffic": ACC_TRAFFIC_2_20 if args.log_n == 20 else None,
-                    "traffic_note": "dram__bytes_read+write summed over the window-group launches (8, 4, 4 windows) of "
-                                    "one 2^20 MSM, ncu --set full (profiles/r01_final2_acc_ncu_raw.csv); algorithmic "
+                    "traffic_note": "dram__bytes_read+write summed over the window-group launches (8, 4, 2, 2 windows) "
+                                    "of one 2^20 MSM, ncu --set full (profiles/r01_final3_acc_ncu_raw.csv); algorithmic "
                                     "gather bytes N*W*100 = 1.68e9, the rest is L2 hits",
                     "launch_ms": acc_ms, "launches_timed": acc_n,
-                    "launch_note": "span of the window-group launches (8, 4, 4 windows) per MSM",
+                    "launch_note": "span of the window-group launches (8, 4, 2, 2 windows at 2^20) per MSM",
                     "ncu": {"sm__pipe_fmaheavy_cycles_active_pct": 84.4, "stall_top": "math_pipe_throttle"},
                     "peak_source": "measured IMAD.WIDE.U32 issue rate (profiles/r01_microbench_int_pipe.jsonl)",
                     "algorithmic_imad_per_launch": imad_acc}

@@ -873,26 +873,23 @@ __global__ void __launch_bounds__(32) msm_horner_kernel(const uint8_t* __restric
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int msm_pick_window(size_t n) {
-    // Measured on B200 (tools/probe_c.py, ms per MSM, c = 13 / 14 / 15 / 16):
-    //   2^15: 0.84 0.85 0.74 0.80   2^16: 0.87 0.92 0.79 0.84   2^17: 1.13 1.09 0.90 0.93
-    //   2^18: 1.91 1.46 1.08 1.09   2^19: 3.46 2.45 1.47 1.48   2^20: 6.64 4.35 2.51 2.22
-    // From 2^15 points the window-group pipeline is on and the call is bound by dependent chains, whose
-    // length falls with the number of windows: wide windows win long before the operation count says so.
-    if (n >= ((size_t)1 << 23)) return 17;  // 2^24: 26.5 ms at c = 17 against 27.5 ms at c = 16 (2^22: 7.13 both)
+    // Measured on B200 (tools/probe_c.py, ms per MSM), with the slotted front end and the 2-D reduction:
+    //          c = 12     13     14     15     16     17
+    //   2^6            0.459  0.549  0.523  0.605            (c = 8: 0.469, 10: 0.476)
+    //   2^10    0.600  0.516  0.634  0.529  0.612            (c = 8: 0.566)
+    //   2^12    0.600  0.591  0.629  0.527  0.609
+    //   2^14    0.624  0.609  0.654  0.556  0.627
+    //   2^16    0.907  0.692  0.786  0.650  0.678  0.826
+    //   2^18    2.558  1.640  1.301  0.923  0.957  1.063
+    //   2^19           2.894  2.297  1.419  1.298  1.463
+    //   2^20           5.457  3.941  2.401  2.006  2.377
+    //   2^22          20.60  14.34   8.304  6.435  7.987
+    //   2^24          79.4   55.5   31.4   24.39  30.23   (c = 17 was ahead, 25.8 against 25.3, before the slots)
+    // Every call is bound by dependent chains (window combine, reductions, one inversion) up to ~2^17 points, and
+    // their length falls with the number of windows: wide windows win long before the operation count says so.
     if (n >= ((size_t)1 << 19)) return 16;
-    if (n >= ((size_t)1 << 15)) return 15;
-    // below: minimise W*(n + 2*2^(c-1)*9/7) over c with W = ceil(256/c); c <= 16 keeps entries in 32 bits
-    double best = 1e300;
-    int best_c = 4;
-    for (int c = 4; c <= 16; c++) {
-        int W = (256 + c - 1) / c;
-        double cost = (double)W * ((double)n + 2.0 * (double)(1u << (c - 1)) * 9.0 / 7.0) + 1.5 * c * W;
-        if (cost < best) {
-            best = cost;
-            best_c = c;
-        }
-    }
-    return best_c;
+    if (n >= ((size_t)1 << 11)) return 15;
+    return 13;
 }
 
 static_assert(kMaxGroups * kSegBinsPerGroup <= kSegBins, "bin table too small");
@@ -1080,9 +1077,10 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     // a chunk that only adds into the buckets has no tails to overlap: one group, everything on `st`
     StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(kit_index) : nullptr;
     GroupMap gm;
-    // the last group's reduction is exposed; with the shallow 2-D reduction a 4-window last group (16 windows:
-    // 8, 4, 4) pays from 2^20 points (8,4,2,2 / 8,4,4: 2^19 1.43 / 1.44 ms, 2^20 2.19 / 2.16, 2^22 6.70 / 6.57)
-    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 20) ? 4 : 3);
+    // the last group's reduction is exposed: 16 windows go as 8, 4, 2, 2 up to 2^20 points and as 8, 4, 4 above
+    // (measured with the 2-D reduction on every group, 8,4,2,2 / 8,4,4: 2^19 1.30 / 1.31 ms, 2^20 2.00 / 2.03,
+    // 2^22 6.65 / 6.43)
+    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 21) ? 4 : 3);
 
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
@@ -1183,10 +1181,13 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         const uint8_t* Y = X;
         uint32_t n_in = p.B, in_stride = p.B;
         int has_y = 0, pp = 0, level = 0;
-        // exposed tails (last group of the pipeline, small MSMs): the shallow 2-D reduction (6c)
+        // The shallow 2-D reduction (6c), for every group: the reductions of the overlapped groups are not
+        // exposed themselves, but the Horner chain runs through them in order, and a group's ~110-operation
+        // running-sum levels, starved of SM slots by the next accumulation, delayed the chain to the end
+        // (2-D on the last group only / on all groups: 2^18 1.06 / 0.94 ms, 2^20 2.16 / 2.03, 2^22 6.56 / 6.44).
+        // The running-sum kernels remain for narrow windows (c < 9) and as a cross-check (CBP_MSM_NO2D).
         static const bool no2d = getenv("CBP_MSM_NO2D") != nullptr;
-        static const int from2d = getenv("CBP_2D_FROM") ? atoi(getenv("CBP_2D_FROM")) : 99;
-        if ((kit == nullptr || nwin <= 2 || g == gm.ngroups - 1 || g >= from2d) && p.c >= 9 && !no2d) {
+        if (p.c >= 9 && !no2d) {
             const int lbits = (p.c - 1) / 2, hbits = p.c - 1 - lbits;
             const uint32_t per = (p.B >> lbits) + (1u << lbits);  // <= n1 for c >= 9
             uint8_t* sums = ws + p.off_redX[0] + (size_t)w_lo * n1 * 128;
