@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 LOG_N_DEFAULT = 20
 VERIFY_PROOFS_DEFAULT = 1 << 14
 INT_PEAK_TIMAD = 9.0  # measured IMAD.WIDE.U32 issue rate on this pool's B200 (profiles/r01_microbench_int_pipe.jsonl)
-ACC_TRAFFIC_2_20 = 1.2325e9  # DRAM bytes of the accumulation launches of one 2^20 MSM (ncu --set full, see traffic_note)
+ACC_TRAFFIC_2_20 = 1.207e9  # DRAM bytes of the accumulation launches of one 2^20 MSM (ncu --set full, see traffic_note)
 
 
 def measured_peaks():
@@ -298,7 +298,7 @@ def run_cuda(args):
                                     "gather bytes N*W*100 = 1.68e9, the rest is L2 hits",
                     "launch_ms": acc_ms, "launches_timed": acc_n,
                     "launch_note": "span of the window-group launches (8, 4, 2, 2 windows at 2^20) per MSM",
-                    "ncu": {"sm__pipe_fmaheavy_cycles_active_pct": 84.4, "stall_top": "math_pipe_throttle"},
+                    "ncu": {"sm__pipe_fmaheavy_cycles_active_pct": 84.2, "stall_top": "math_pipe_throttle"},
                     "peak_source": "measured IMAD.WIDE.U32 issue rate (profiles/r01_microbench_int_pipe.jsonl)",
                     "algorithmic_imad_per_launch": imad_acc}
         roofline_hbm = {"bound": "hbm", "kernel": "msm_precompute_kernel", "achieved": n * 224.0 / (pre_ms * 1e-3) / 1e9,

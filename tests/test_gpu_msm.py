@@ -257,3 +257,36 @@ def test_msm_slotted_equals_two_pass_at_size(oracle, monkeypatch):
     oracle.ge25519_scalarmult_base(ob.ptr(want), (acc % L).to_bytes(32, "little"))
     oracle.ge25519_normalize(ob.ptr(want))
     assert np.array_equal(out["1"][0].view(np.uint64), want)
+
+
+def test_msm_running_sum_reduction_cross_check(oracle):
+    """The bucket reduction has two implementations: the shallow 2-D one (default for c >= 9) and the
+    work-efficient running-sum levels (narrow windows; CBP_MSM_NO2D=1 forces them, read once per process).
+    Both must give the oracle's bytes — single group (n < 2^15) and the window-group pipeline (2^16)."""
+    import os
+    import subprocess
+    import sys
+    import cudabulletproof_b200 as cbp
+    script = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r); import cudabulletproof_b200 as cbp\n"
+        "for n, seed in ((3000, 5), (1 << 16, 6)):\n"
+        "    pts, _ = cbp.synth_points(n, seed=seed); sc = cbp.synth_scalars(n, seed=seed + 100, bits=253)\n"
+        "    print(cbp.Msm(n)(sc, pts).cpu().numpy().tobytes().hex())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, CBP_MSM_NO2D="1")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    forced = out.stdout.split()
+    for (n, seed), hexed in zip(((3000, 5), (1 << 16, 6)), forced):
+        pts, ks = cbp.synth_points(n, seed=seed)
+        sc = cbp.synth_scalars(n, seed=seed + 100, bits=253)
+        got = cbp.Msm(n)(sc, pts).cpu().numpy()
+        assert got.tobytes().hex() == hexed
+        ks_h = ks.cpu().numpy().astype(np.uint64)
+        sc_h = sc.cpu().numpy().view(np.uint64).reshape(n, 4)
+        acc = 0
+        for i in range(n):
+            acc += (int(sc_h[i, 0]) | int(sc_h[i, 1]) << 64 | int(sc_h[i, 2]) << 128 | int(sc_h[i, 3]) << 192) * int(ks_h[i])
+        want = np.zeros(16, dtype=np.uint64)
+        oracle.ge25519_scalarmult_base(ob.ptr(want), (acc % L).to_bytes(32, "little"))
+        oracle.ge25519_normalize(ob.ptr(want))
+        assert np.array_equal(got.view(np.uint64), want)
