@@ -106,22 +106,31 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const uint8_t* __re
 //          cursor), which spares them the second atomic pass: the digits of every window but the top one are
 //          uniform for any scalars that are not adversarial, so a slot of mean + 8 sigma never fills up.  A
 //          bucket that does outgrow its slot raises *overflow (its count stays exact).
-//  PASS 1  exact placement through the scanned cursors, for the windows >= w_exact (the top window of scalars
-//          below the group order populates 1/16 of its buckets at 16x the mean) — or for every window when
-//          *overflow is set (then the slots of pass 0 are ignored and the layout is the compact one).
+//          The top window (w_exact = W - 1; scalars below the group order populate 1/16 of its buckets at 16x
+//          the mean, so it gets no slots) is only counted, but the value the atomic returns — the entry's rank
+//          inside its bucket — is kept per point (toprank: bucket | sign << 31, rank).
+//  PASS 1  exact placement into compact runs.  With slots: the top window, at offsets[bucket] + rank, without
+//          atomics or a second look at the scalar (0.04 -> 0.01 ms at 2^20: its 4096 populated buckets made the
+//          atomics contend) — and, only when *overflow is set, the slotted windows again through the scanned
+//          cursors (the slots of pass 0 are then ignored).  Without slots (cap = 0): every window.
 template <int PASS>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restrict__ scalars, size_t n, int c, int W,
                                                          uint32_t B, uint32_t cap, int w_exact,
                                                          uint32_t* __restrict__ counters,
                                                          uint32_t* __restrict__ entries,
-                                                         uint32_t* __restrict__ overflow) {
+                                                         uint32_t* __restrict__ overflow,
+                                                         const uint32_t* __restrict__ offsets,
+                                                         uint2* __restrict__ toprank) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int w_from = 0;  // PASS 1: first window this pass places
-    if (PASS == 1) {
-        w_from = *overflow ? 0 : w_exact;
-        if (w_from >= W) return;
+    int w_to = W;  // windows [0, w_to) go through the loop below
+    if (PASS == 1 && toprank) {
+        const uint2 r = toprank[i];
+        if (r.x != 0xffffffffu) entries[offsets[r.x & 0x7fffffffu] + r.y] = ((uint32_t)i << 1) | (r.x >> 31);
+        if (!*overflow) return;
+        w_to = w_exact;
     }
+    uint2 top = make_uint2(0xffffffffu, 0u);
     uint32_t k[8];
     load_scalar_canon(k, scalars + i * 32);
     uint32_t carry = 0;
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
                     neg = 1;
                     carry = 1;
                 }
-                if (d != 0 && w >= w_from) {
+                if (d != 0 && w < w_to) {
                     live[j] = true;
                     id[j] = (uint32_t)w * B + (d - 1);
                     val[j] = ((uint32_t)i << 1) | neg;
@@ -159,15 +168,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (live[j]) entries[pos[j]] = val[j];
-        } else if (w0 < w_exact) {  // at least one slotted window in this batch
+        } else if (toprank) {  // slots: the atomics' return values place (slotted windows) or rank (top window)
             uint32_t pos[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (live[j]) pos[j] = atomicAdd(&counters[id[j]], 1u);
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if (live[j] && w0 + j < w_exact) {
-                    if (pos[j] < cap) entries[id[j] * cap + pos[j]] = val[j];
+                if (live[j]) {
+                    if (w0 + j >= w_exact) top = make_uint2(id[j] | (val[j] << 31), pos[j]);
+                    else if (pos[j] < cap) entries[id[j] * cap + pos[j]] = val[j];
                     else *overflow = 1u;
                 }
         } else {
@@ -176,6 +186,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint8_t* __restri
                 if (live[j]) atomicAdd(&counters[id[j]], 1u);
         }
     }
+    if (PASS == 0 && toprank) toprank[i] = top;
 }
 
 static constexpr int kMaxGroups = 8;
@@ -249,6 +260,7 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t* tile_sums, u
 template <bool SEG>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t total,
                                                                   GroupMap gm, uint32_t slotted_ids, uint32_t cap,
+                                                                  uint32_t ranked_from,
                                                                   const uint32_t* __restrict__ overflow,
                                                                   const uint32_t* __restrict__ tile_sums,
                                                                   uint32_t* __restrict__ offsets,
@@ -274,7 +286,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
         } else {
             if (id <= total) offsets[id] = ex;  // offsets[total] = end of the compact area (sentinel)
             // the placing pass advances the cursors: afterwards cursors[id] is the END of bucket id's run
-            if (cursors && id < total) cursors[id] = ex;
+            // (buckets from ranked_from on are placed by rank, without cursors: the end is written here)
+            if (cursors && id < total) cursors[id] = ex + (id >= ranked_from ? v[j] : 0u);
         }
         ex += v[j];
     }
@@ -942,6 +955,7 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
         }
     }
     p->off_entries = take(entry_words * 4 + 4);
+    p->off_toprank = take(p->cap ? n * 8 : 0);
     p->off_buckets = take((size_t)p->nbuckets * 128);
     p->off_segsums = take(p->max_segs * 128);
     uint32_t n1 = (p->B + kReduceM - 1) / kReduceM;
@@ -1107,19 +1121,21 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     prof_begin(BPK_PROF_MSM_FRONT, st);
     unsigned dgrid = (unsigned)((n + 255) / 256);
     const uint32_t slotted_ids = (uint32_t)p.w_exact * p.B;  // buckets placed by the first pass (0: none)
+    uint2* toprank = p.cap ? (uint2*)(ws + p.off_toprank) : nullptr;
     msm_digits_kernel<0><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, counts,
-                                                entries, overflow);
+                                                entries, overflow, offsets, toprank);
     CBP_LAUNCH_CHECK(); nl++;
     uint32_t ntiles = (p.nbuckets + 1 + kScanTile - 1) / kScanTile;  // +1: the sentinel slot
     scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, overflow, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, p.cap, overflow, tiles,
-                                                              offsets, cursors);
+    scan_apply_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, p.cap,
+                                                              p.cap ? slotted_ids : 0xffffffffu, overflow, tiles, offsets,
+                                                              cursors);
     CBP_LAUNCH_CHECK(); nl++;
     msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
-                                                entries, overflow);
+                                                entries, overflow, offsets, toprank);
     CBP_LAUNCH_CHECK(); nl++;
     const uint32_t* ends = cursors;  // after the placing pass: end of every bucket's run
     // segments
@@ -1127,8 +1143,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
     CBP_LAUNCH_CHECK(); nl++;
-    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, 0u, 0u, overflow, tiles, segoff,
-                                                             nullptr);
+    scan_apply_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, 0u, 0u, 0xffffffffu, overflow, tiles,
+                                                             segoff, nullptr);
     CBP_LAUNCH_CHECK(); nl++;
     const uint32_t* nsegs_p = segoff + p.nbuckets;
     unsigned bgrid = (p.nbuckets + 255) / 256, sgrid = (unsigned)((p.max_segs + 255) / 256);
