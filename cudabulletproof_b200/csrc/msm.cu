@@ -1021,8 +1021,25 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
         gm->ngroups = 1;
     } else {
         int remaining = W;
+        // CBP_GROUPS="10,4,2": explicit group sizes, top down, for measurements.  With the 2-D reduction on every
+        // group (ms at 2^20 / 2^22): 8,4,2,2 1.97 / 6.58; 8,4,4 2.03 / 6.36; 10,4,2 2.01 / 6.42; 9,4,3 2.01 / 6.40;
+        // 10,3,3 2.02 / 6.47; 11,3,2 2.02 / 6.44; 12,4 2.02 / 6.38; 10,6 2.02 / 6.41.
+        const char* genv = getenv("CBP_GROUPS");
         while (remaining > 0) {
             int take = remaining > 1 ? remaining / 2 : 1;
+            if (genv && *genv) {
+                int v = atoi(genv);
+                while (*genv && *genv != ',') genv++;
+                if (*genv == ',') genv++;
+                if (v >= 1 && v <= remaining && gm->ngroups < kMaxGroups - 1) {
+                    gm->w_hi[gm->ngroups] = hi;
+                    gm->w_lo[gm->ngroups] = hi - v + 1;
+                    gm->ngroups++;
+                    hi -= v;
+                    remaining -= v;
+                    continue;
+                }
+            }
             // no one-window groups (16 windows: 8, 4, 2, 2; 18: 9, 4, 2, 3): a one-window accumulation is a single partial wave
             // (48 % of the multiply pipe in ncu against 84 % for the 8-window group); measured 2.27 vs 2.30 ms at
             // 2^20 and 1.43 vs 1.49 ms at 2^19.  Larger last groups lengthen the exposed tail (last_max: see msm_run).
