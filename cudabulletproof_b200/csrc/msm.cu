@@ -9,14 +9,18 @@
 // integer used is k = canonical(fe25519_tobytes(s)) = s mod p, all 255 bits, no reduction mod l —
 // so the result is exact for every point of the curve, including points with a torsion component.
 //
-// Pipeline (all on one stream, no host synchronisation):
-//   1. msm_precompute   AoS ge25519 -> 96-byte affine (y+x, y-x, 2dxy) table   [HBM streaming]
-//   2. msm_count        signed c-bit digit recoding + per-(window,bucket) histogram
-//   3. scan             exclusive prefix sum over W*B counters
-//   4. msm_scatter      second recoding pass, writes (point index, sign) into its bucket run
-//   5. msm_accumulate   one thread per bucket: gathers its run, 7M mixed additions  [IMAD-bound, ~90% of time]
-//   6. msm_reduce_level running-sum reduction  sum_b b*B_b  per window, m buckets per thread, repeated
-//   7. msm_finish       Horner over windows, normalise to Z = 1
+// Pipeline (no host synchronisation; from 2^15 points the windows go top-down in groups whose reductions and
+// Horner steps run on side streams under the next group's accumulation):
+//   1. msm_precompute   AoS ge25519 -> 96-byte affine (y+x, y-x, 2dxy) table   [HBM streaming, side stream]
+//   2. msm_digits<0>    signed c-bit digit recoding + per-(window,bucket) counts; from 2^19 points the same pass
+//                       places every window but the top one into fixed bucket slots and keeps the top window's ranks
+//   3. scan             exclusive prefix sum over the counters of the compactly placed buckets
+//   4. msm_digits<1>    exact placement: the top window by rank (or every window: small inputs, slot overflow)
+//   4b. seg_*           runs cut into segments, segments ordered by (window group, length)
+//   5. msm_accumulate   one thread per segment: gathers its run, 7M mixed additions  [IMAD-bound, ~2/3 of the time]
+//   6. msm_reduce2d_*   sum_b b*B_b per window: row / column sums, per-bit subset sums, bit Horner (c >= 9);
+//      msm_reduce_*     work-efficient running-sum levels (narrow windows; cross-check)
+//   7. msm_horner       Horner over the windows (chain state kept between groups), normalise to Z = 1
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
