@@ -55,9 +55,11 @@ SIGNATURES = {
     "bpk_last_cuda_error": (_i, []),
     "bpk_clear_last_error": (_i, []),
     "bpk_kernel_launches": (_u64, []),
+    "bpk_debug_set_option": (_i, [_i, C.c_longlong]),
     "bpk_profile_enable": (_i, [_i]),
     "bpk_profile_reset": (_i, []),
     "bpk_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),
+    "bpk_measure_int_peak": (_i, [C.c_double, C.POINTER(C.c_double), _i]),
     "bpk_msm_workspace_bytes": (_i, [_sz, _i, C.POINTER(_sz)]),
     "bpk_msm_window_bits": (_i, [_sz]),
     "bpk_msm_device": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp]),
@@ -78,6 +80,7 @@ SIGNATURES = {
     "bpk_gens_derive_device": (_i, [_vp, C.c_char_p, C.c_uint32, _sz, _vp]),
     "bpk_debug_ge_op_device": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bpk_debug_const_operands_device": (_i, [_vp, _vp]),
+    "bpk_debug_projectivize_device": (_i, [_vp, _sz, _u64, _vp, C.c_uint32, _vp]),
     "bpk_ipa_prove_workspace_bytes": (_i, [_sz, C.POINTER(_sz)]),
     "bpk_ipa_prove_device": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, C.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bpk_gens_window_bits": (_i, [_vp]),
@@ -87,6 +90,7 @@ SIGNATURES = {
     "bpk_range_verify_batch_device": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
     "bpk_range_prove_workspace_bytes": (_i, [_sz, _sz, C.POINTER(_sz)]),
     "bpk_range_prove_batch_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
+    "bpk_range_prove_batch_keyed_device": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _sz, _vp]),
     "bpk_synth_points_device": (_i, [_vp, _vp, _sz, _u64, _vp]),
     "bpk_synth_scalars_device": (_i, [_vp, _sz, _u64, _i, _vp]),
     # include/cuda_bulletproof.h

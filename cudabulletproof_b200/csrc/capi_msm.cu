@@ -14,6 +14,44 @@ std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_last_error{0};
 std::atomic<int> g_last_cuda_error{0};
 
+int current_device_index() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        fail(BPK_ERR_CUDA, e != cudaSuccess ? e : cudaErrorInvalidDevice);
+        return -1;
+    }
+    return dev;
+}
+std::recursive_mutex& device_mutex(int dev) {
+    static std::recursive_mutex mu[kMaxDevices];
+    return mu[dev];
+}
+Options& options() {
+    static Options opt;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto num = [](const char* name, int dflt) {
+            const char* v = getenv(name);
+            return v && *v ? atoi(v) : dflt;
+        };
+        opt.msm_slots = num("CBP_MSM_SLOTS", -1);
+        opt.msm_no2d = getenv("CBP_MSM_NO2D") ? 1 : 0;
+        opt.host_chunk_log2 = num("CBP_HOST_CHUNK_LOG2", 0);
+        opt.prover_legacy = getenv("CBP_PROVER_LEGACY") ? 1 : 0;
+        opt.msm_small_max = num("CBP_MSM_SMALL_MAX", -1);
+        if (const char* g = getenv("CBP_GROUPS")) {
+            while (*g && opt.ngroups < 8) {
+                int v = atoi(g);
+                if (v >= 1) opt.groups[opt.ngroups++] = v;
+                while (*g && *g != ',') g++;
+                if (*g == ',') g++;
+            }
+        }
+    });
+    return opt;
+}
+
 // sum of `count` extended points by one warp (lane-strided partial sums, shuffle tree)
 __global__ void point_sum_kernel(const uint8_t* __restrict__ pts, size_t count, int normalize,
                                  uint8_t* __restrict__ out) {
@@ -69,6 +107,35 @@ __global__ void __launch_bounds__(128) synth_points_kernel(uint8_t* __restrict__
     ge_store(pts + i * 128, r);
     if (ks) ks[i] = k;
 }
+// test hook: re-randomise the projective representation (X, Y, Z, T) -> (zX, zY, zZ, zT) with a per-point z != 0,
+// after adding the point *torsion to every torsion_stride-th point.  The group element is unchanged by z, so
+// full-size MSM tests can leave the Z = 1 fast path of msm_precompute_kernel without a new expected value.
+__global__ void __launch_bounds__(128) projectivize_kernel(uint8_t* __restrict__ pts, size_t n, uint64_t seed,
+                                                           const uint8_t* __restrict__ torsion,
+                                                           uint32_t torsion_stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_p3 p;
+    ge_load(p, pts + i * 128);
+    if (torsion && torsion_stride && i % torsion_stride == 0) {
+        ge_p3 t;
+        ge_load(t, torsion);
+        ge_add(p, p, t);
+    }
+    fe z;
+    uint64_t s = splitmix64(seed ^ splitmix64(i * 2 + 1));
+    for (int j = 0; j < 4; j++) {
+        s = splitmix64(s + j);
+        z.v[2 * j] = (uint32_t)s;
+        z.v[2 * j + 1] = (uint32_t)(s >> 32);
+    }
+    if (fe_iszero(z)) fe_set1(z);  // z = 0 (mod p) would destroy the point
+    fe_mul(p.X, p.X, z);
+    fe_mul(p.Y, p.Y, z);
+    fe_mul(p.Z, p.Z, z);
+    fe_mul(p.T, p.T, z);
+    ge_store(pts + i * 128, p);
+}
 __global__ void synth_scalars_kernel(uint64_t* __restrict__ out, size_t n, uint64_t seed, int bits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -96,10 +163,37 @@ int bpk_clear_last_error(void) {
     return g_last_error.exchange(0);
 }
 uint64_t bpk_kernel_launches(void) { return g_launches.load(); }
+int bpk_debug_set_option(int option, long long value) {
+    Options& o = options();
+    switch (option) {
+        case BPK_OPT_MSM_SLOTS: o.msm_slots = (int)value; break;
+        case BPK_OPT_MSM_NO2D: o.msm_no2d = value != 0; break;
+        case BPK_OPT_HOST_CHUNK_LOG2: o.host_chunk_log2 = (int)value; break;
+        case BPK_OPT_PROVER_LEGACY: o.prover_legacy = value != 0; break;
+        case BPK_OPT_MSM_SMALL_MAX: o.msm_small_max = (int)value; break;
+        case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic
+            o.ngroups = 0;
+            for (int sh = 28; sh >= 0; sh -= 4) {
+                int v = (int)((value >> sh) & 15);
+                if (v && o.ngroups < 8) o.groups[o.ngroups++] = v;
+            }
+            break;
+        default: return fail(BPK_ERR_ARG);
+    }
+    return BPK_OK;
+}
 
 int bpk_msm_window_bits(size_t n) { return msm_pick_window(n); }
+// entry indices are (point index << 1 | sign) and all offsets 32-bit prefix sums over the n * W entries:
+// n < 2^31 and n * ceil(256 / c) < 2^32 (n up to 2^27 at c = 16; larger inputs: split the call, the partial results
+// add up with bpk_point_sum_device)
+static bool msm_size_ok(size_t n, int window_bits) {
+    if (n >= (1ull << 31)) return false;
+    const int c = window_bits > 0 ? window_bits : msm_pick_window(n);
+    return n * (size_t)((256 + c - 1) / c) < (1ull << 32);
+}
 int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes) {
-    if (!bytes || window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
+    if (!bytes || window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || !msm_size_ok(n, window_bits))
         return fail(BPK_ERR_ARG);
     MsmPlan p;
     msm_make_plan(&p, n, window_bits);
@@ -109,7 +203,7 @@ int bpk_msm_workspace_bytes(size_t n, int window_bits, size_t* bytes) {
 int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* d_result, void* d_workspace,
                    size_t workspace_bytes, int window_bits, int normalize, void* stream) {
     if (!d_result || (n && (!d_scalars || !d_points || !d_workspace))) return fail(BPK_ERR_ARG);
-    if (window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || n >= (1ull << 31))
+    if (window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || !msm_size_ok(n, window_bits))
         return fail(BPK_ERR_ARG);
     MsmPlan p;
     msm_make_plan(&p, n, window_bits);
@@ -129,6 +223,15 @@ int bpk_synth_points_device(void* d_points, uint64_t* d_k, size_t n, uint64_t se
     if (n && !d_points) return fail(BPK_ERR_ARG);
     if (!n) return BPK_OK;
     synth_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint8_t*)d_points, d_k, n, seed);
+    CBP_CHECK_LAUNCH();
+    return BPK_OK;
+}
+int bpk_debug_projectivize_device(void* d_points, size_t n, uint64_t seed, const void* d_torsion,
+                                   uint32_t torsion_stride, void* stream) {
+    if (n && !d_points) return fail(BPK_ERR_ARG);
+    if (!n) return BPK_OK;
+    projectivize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (uint8_t*)d_points, n, seed, (const uint8_t*)d_torsion, torsion_stride);
     CBP_CHECK_LAUNCH();
     return BPK_OK;
 }
@@ -155,7 +258,6 @@ constexpr size_t kHostChunk = (size_t)1 << 17;
 constexpr size_t kHostChunkMin = (size_t)1 << 20;  // below this a single MSM (scalars first) is faster
 constexpr int kMaxChunks = 4096;
 struct HostPath {
-    std::mutex mu;
     uint8_t *d_s = nullptr, *d_p = nullptr, *d_r = nullptr;
     uint8_t* d_ws[1] = {};
     size_t cap_s = 0, cap_p = 0, cap_ws[1] = {};
@@ -164,7 +266,7 @@ struct HostPath {
     std::vector<cudaEvent_t> ev_chunk;
     bool ok = false;
 };
-HostPath g_hp;
+HostPath g_hp[kMaxDevices];  // one per device, used under that device's lock
 cudaError_t grow(uint8_t** p, size_t* cap, size_t need) {
     if (need <= *cap) return cudaSuccess;
     if (*p) cudaFree(*p);
@@ -178,8 +280,9 @@ cudaError_t grow(uint8_t** p, size_t* cap, size_t need) {
 
 static int msm_host(ge25519* result, const FieldVector* scalars, const PointVector* points) {
     size_t n = scalars->length;
-    std::lock_guard<std::mutex> lock(g_hp.mu);
-    HostPath& hp = g_hp;
+    DeviceLock dlock;
+    if (!dlock.ok()) return BPK_ERR_CUDA;
+    HostPath& hp = g_hp[dlock.dev];
     cudaError_t e;
     if (!hp.ok) {
         if ((e = cudaStreamCreateWithFlags(&hp.main, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -212,10 +315,7 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
         if (rc) return fail_cuda(rc);
     } else {
         size_t chunk = kHostChunk;
-        if (const char* ev = getenv("CBP_HOST_CHUNK_LOG2")) {  // tuning knob
-            int lg = atoi(ev);
-            if (lg >= 15 && lg <= 26) chunk = (size_t)1 << lg;
-        }
+        if (const int lg = options().host_chunk_log2; lg >= 15 && lg <= 26) chunk = (size_t)1 << lg;  // tuning knob
         size_t nchunks = (n + chunk - 1) / chunk;
         if (nchunks > (size_t)kMaxChunks) {  // keep the event pool bounded for enormous inputs
             nchunks = kMaxChunks;

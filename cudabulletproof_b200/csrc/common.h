@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <mutex>
 #include "../../include/bpk.h"
 
 namespace cbp {
@@ -17,6 +18,39 @@ inline int fail(int code, cudaError_t ce = cudaSuccess) {
 }
 inline int fail_cuda(int ce) { return ce == 0 ? BPK_OK : fail(BPK_ERR_CUDA, (cudaError_t)ce); }
 inline void count_launches(int n) { g_launches.fetch_add((uint64_t)n); }
+
+// ---- per-device host state ------------------------------------------------------------------------
+// Every piece of cached host-side state (side streams and events, upload buffers, generator tables) is keyed by
+// the CUDA device that is current when an entry point is called, and every enqueue that touches shared side
+// streams or events holds that device's lock: two host threads may call any entry points concurrently, on any
+// streams, and a thread may switch devices between calls.  cudaStreamWaitEvent binds to the event's most recent
+// record at the time of the call, so serialising the ENQUEUE (not the execution) is enough.
+constexpr int kMaxDevices = 64;
+int current_device_index();             // cudaGetDevice(), or -1 (error recorded) when out of range
+std::recursive_mutex& device_mutex(int dev);
+struct DeviceLock {
+    int dev;
+    std::unique_lock<std::recursive_mutex> lock;
+    DeviceLock() : dev(current_device_index()) {
+        if (dev >= 0) lock = std::unique_lock<std::recursive_mutex>(device_mutex(dev));
+    }
+    bool ok() const { return dev >= 0; }
+};
+
+// ---- measurement / test switches --------------------------------------------------------------------
+// Read ONCE per process from the environment (first use), changeable afterwards only through
+// bpk_debug_set_option(): nothing on a call path looks at the environment.
+struct Options {
+    int msm_slots = -1;       // CBP_MSM_SLOTS: -1 auto (slotted first digit pass from 2^19 points), 0 off, 1 on
+    int msm_no2d = 0;         // CBP_MSM_NO2D: 1 = running-sum bucket reduction everywhere (cross-check)
+    int host_chunk_log2 = 0;  // CBP_HOST_CHUNK_LOG2: chunk size of the host-pointer upload pipeline, 0 = default
+    int prover_legacy = 0;    // CBP_PROVER_LEGACY: one-CTA-per-proof prover for every batch size
+    int ngroups = 0;          // CBP_GROUPS="8,4,4": explicit window groups of the MSM pipeline, top down
+    int groups[8] = {};
+    int msm_small_max = -1;   // CBP_MSM_SMALL_MAX: largest n taken by the single-launch small-n MSM (-1 default)
+};
+Options& options();
+
 // optional per-kernel timing: no-ops unless bpk_profile_enable(1)
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);

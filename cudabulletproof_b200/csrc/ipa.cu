@@ -326,10 +326,10 @@ struct IpaSide {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool ok = false;
 };
-static IpaSide g_ipa_side[16];
-static IpaSide* ipa_side() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+static IpaSide g_ipa_side[kMaxDevices];
+// caller holds the device lock
+static IpaSide* ipa_side(int dev) {
+    if (dev < 0 || dev >= kMaxDevices) return nullptr;
     IpaSide& v = g_ipa_side[dev];
     if (!v.ok) {
         if (cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
@@ -393,7 +393,9 @@ int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, cons
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* ws = (uint8_t*)d_workspace;
     uint8_t *a = ws + Ly.a, *b = ws + Ly.b, *g = ws + Ly.g, *h = ws + Ly.h;
-    IpaSide* sd = ipa_side();
+    DeviceLock dlock;  // side stream / events shared per device
+    if (!dlock.ok()) return BPK_ERR_CUDA;
+    IpaSide* sd = ipa_side(dlock.dev);
     if (!sd) return fail(BPK_ERR_CUDA);
     uint8_t *tr = ws + Ly.small, *u = tr + 32, *ui = tr + 64, *cL = tr + 96, *cR = tr + 128;
     size_t ipb = 0;
@@ -441,6 +443,44 @@ int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, cons
 }
 
 // ---- host-pointer drop-ins ----------------------------------------------------------------------------
+// The reference's wrappers malloc / copy / synchronise / free on every call (cuda_bulletproof_kernels.cu:77-115).
+// Here every device keeps one grow-only device buffer, one pinned staging buffer, one stream and the generator
+// tables of the last generator set: a call is one upload, the kernels, one byte back, no allocation.
+namespace {
+struct HostVerify {
+    cudaStream_t st = nullptr;
+    uint8_t* d_buf = nullptr;
+    size_t d_cap = 0;
+    uint8_t* h_pin = nullptr;
+    size_t h_cap = 0;
+    // generator tables are cached across calls: the reference signature passes G, H, g, h every time
+    uint8_t* gens_dev = nullptr;
+    uint8_t* gens_key = nullptr;
+    size_t gens_key_bytes = 0, gens_n = 0;
+};
+HostVerify g_hv[kMaxDevices];
+
+// caller holds the device lock
+bool hv_reserve(HostVerify& hv, size_t dev_bytes, size_t pin_bytes) {
+    cudaError_t e = cudaSuccess;
+    if (!hv.st) e = cudaStreamCreateWithFlags(&hv.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess && dev_bytes > hv.d_cap) {
+        if (hv.d_buf) cudaFree(hv.d_buf);
+        hv.d_buf = nullptr;
+        hv.d_cap = 0;
+        if ((e = cudaMalloc(&hv.d_buf, dev_bytes)) == cudaSuccess) hv.d_cap = dev_bytes;
+    }
+    if (e == cudaSuccess && pin_bytes > hv.h_cap) {
+        if (hv.h_pin) cudaFreeHost(hv.h_pin);
+        hv.h_pin = nullptr;
+        hv.h_cap = 0;
+        if ((e = cudaMallocHost(&hv.h_pin, pin_bytes)) == cudaSuccess) hv.h_cap = pin_bytes;
+    }
+    if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
+    return e == cudaSuccess;
+}
+}  // namespace
+
 static bool ipa_verify_host(const InnerProductProof* proof, const ge25519* P, const PointVector* G,
                             const PointVector* H, const ge25519* Q, const uint8_t tr0[32]) {
     size_t n = proof->n;
@@ -453,33 +493,33 @@ static bool ipa_verify_host(const InnerProductProof* proof, const ge25519* P, co
     size_t total = 2 * n + 2 * (size_t)k + 2;
     MsmPlan plan;
     msm_make_plan(&plan, total, 0);
-    size_t off_G = 0, off_H = off_G + n * 128, off_Q = off_H + n * 128, off_P = off_Q + 128, off_L = off_P + 128,
-           off_R = off_L + (size_t)k * 128 + 128, off_s = off_R + (size_t)k * 128 + 128, off_ch = off_s + 128,
-           off_sc = off_ch + ((sizeof(IpaChal) + 255) / 256) * 256, off_pt = off_sc + total * 32,
-           off_res = off_pt + total * 128, off_ws = off_res + 256, bytes = off_ws + plan.workspace_bytes;
-    uint8_t* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, bytes);
-    if (e != cudaSuccess) {
-        fail(BPK_ERR_CUDA, e);
-        return false;
+    // one contiguous upload: G | H | Q | P | L | R | a, b, x, transcript
+    const size_t off_G = 0, off_H = off_G + n * 128, off_Q = off_H + n * 128, off_P = off_Q + 128, off_L = off_P + 128,
+                 off_R = off_L + (size_t)k * 128, off_s = off_R + (size_t)k * 128, up_bytes = off_s + 128;
+    const size_t off_ch = ipa_align(up_bytes), off_sc = off_ch + ipa_align(sizeof(IpaChal)), off_pt = off_sc + ipa_align(total * 32),
+                 off_res = off_pt + total * 128, off_ws = off_res + 256, bytes = off_ws + plan.workspace_bytes;
+    DeviceLock dlock;
+    if (!dlock.ok()) return false;
+    HostVerify& hv = g_hv[dlock.dev];
+    if (!hv_reserve(hv, bytes, up_bytes)) return false;
+    uint8_t *d = hv.d_buf, *hp = hv.h_pin;
+    memcpy(hp + off_G, G->elements, n * 128);
+    memcpy(hp + off_H, H->elements, n * 128);
+    memcpy(hp + off_Q, Q, 128);
+    memcpy(hp + off_P, P, 128);
+    if (k) {
+        memcpy(hp + off_L, proof->L.elements, (size_t)k * 128);
+        memcpy(hp + off_R, proof->R.elements, (size_t)k * 128);
     }
+    memcpy(hp + off_s, proof->a.elements, 32);
+    memcpy(hp + off_s + 32, proof->b.elements, 32);
+    memcpy(hp + off_s + 64, &proof->x, 32);
+    memcpy(hp + off_s + 96, tr0, 32);
+    cudaStream_t st = hv.st;
+    cudaError_t e;
     bool ok = false;
-    uint8_t small[128];
-    cudaStream_t st = 0;
     do {
-        if ((e = cudaMemcpyAsync(d + off_G, G->elements, n * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(d + off_H, H->elements, n * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(d + off_Q, Q, 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(d + off_P, P, 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if (k) {
-            if ((e = cudaMemcpyAsync(d + off_L, proof->L.elements, (size_t)k * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-            if ((e = cudaMemcpyAsync(d + off_R, proof->R.elements, (size_t)k * 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        }
-        memcpy(small, proof->a.elements, 32);
-        memcpy(small + 32, proof->b.elements, 32);
-        memcpy(small + 64, &proof->x, 32);
-        memcpy(small + 96, tr0, 32);
-        if ((e = cudaMemcpyAsync(d + off_s, small, 128, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d, hp, up_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         IpaChal* ch = (IpaChal*)(d + off_ch);
         ipa_verify_challenges_kernel<<<1, 32, 0, st>>>(d + off_L, d + off_R, k, d + off_s, d + off_s + 32, d + off_s + 64,
                                                        d + off_s + 96, ch);
@@ -499,13 +539,11 @@ static bool ipa_verify_host(const InnerProductProof* proof, const ge25519* P, co
         ipa_verify_decide_kernel<<<1, 32, 0, st>>>(ch, d + off_res, d + off_res + 128);
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         count_launches(1);
-        uint8_t acc = 0;
-        if ((e = cudaMemcpyAsync(&acc, d + off_res + 128, 1, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(hp, d + off_res + 128, 1, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
-        ok = acc != 0;
+        ok = hp[0] != 0;
     } while (0);
     if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
-    cudaFree(d);
     return ok;
 }
 
@@ -515,57 +553,48 @@ bool cuda_inner_product_verify(const InnerProductProof* proof, const ge25519* P,
     return ipa_verify_host(proof, P, G, H, Q, zero);
 }
 
-// generator tables are cached across calls: the reference signature passes G, H, g, h every time
-static std::mutex g_gens_mu;
-static uint8_t* g_gens_dev = nullptr;
-static uint8_t* g_gens_key = nullptr;
-static size_t g_gens_key_bytes = 0, g_gens_n = 0;
-
-static const uint8_t* gens_for(size_t n, const PointVector* G, const PointVector* H, const ge25519* g, const ge25519* h) {
+// caller holds the device lock
+static const uint8_t* gens_for(HostVerify& hv, size_t n, const PointVector* G, const PointVector* H, const ge25519* g,
+                               const ge25519* h) {
     size_t key_bytes = (2 * n + 2) * 128;
+    if (hv.gens_dev && hv.gens_n == n && hv.gens_key_bytes == key_bytes && memcmp(G->elements, hv.gens_key, n * 128) == 0 &&
+        memcmp(H->elements, hv.gens_key + n * 128, n * 128) == 0 && memcmp(g, hv.gens_key + 2 * n * 128, 128) == 0 &&
+        memcmp(h, hv.gens_key + 2 * n * 128 + 128, 128) == 0)
+        return hv.gens_dev;
+    if (hv.gens_dev) {
+        cudaStreamSynchronize(hv.st);  // no call is in flight (the lock is held), but be explicit
+        cudaFree(hv.gens_dev);
+    }
+    free(hv.gens_key);
+    hv.gens_dev = nullptr;
+    hv.gens_key = nullptr;
     uint8_t* key = (uint8_t*)malloc(key_bytes);
+    if (!key) return nullptr;
     memcpy(key, G->elements, n * 128);
     memcpy(key + n * 128, H->elements, n * 128);
     memcpy(key + 2 * n * 128, g, 128);
     memcpy(key + 2 * n * 128 + 128, h, 128);
-    if (g_gens_dev && g_gens_n == n && g_gens_key_bytes == key_bytes && memcmp(key, g_gens_key, key_bytes) == 0) {
-        free(key);
-        return g_gens_dev;
-    }
-    if (g_gens_dev) cudaFree(g_gens_dev);
-    free(g_gens_key);
-    g_gens_dev = nullptr;
-    g_gens_key = nullptr;
     size_t ws = 0;
-    if (bpk_gens_workspace_bytes(n, &ws) != BPK_OK) {
-        free(key);
-        return nullptr;
+    uint8_t *d_in = nullptr, *tab = nullptr;
+    cudaError_t e = cudaSuccess;
+    int rc = bpk_gens_workspace_bytes(n, &ws);
+    if (rc == BPK_OK && (e = cudaMalloc(&tab, ws)) == cudaSuccess && (e = cudaMalloc(&d_in, key_bytes)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(d_in, key, key_bytes, cudaMemcpyHostToDevice, hv.st)) == cudaSuccess) {
+        rc = bpk_gens_init_device(tab, ws, d_in, d_in + n * 128, d_in + 2 * n * 128, d_in + 2 * n * 128 + 128, n, hv.st);
+        e = cudaStreamSynchronize(hv.st);
     }
-    uint8_t* d_in = nullptr;
-    cudaError_t e;
-    if ((e = cudaMalloc(&g_gens_dev, ws)) != cudaSuccess || (e = cudaMalloc(&d_in, key_bytes)) != cudaSuccess ||
-        (e = cudaMemcpy(d_in, key, key_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        fail(BPK_ERR_CUDA, e);
-        cudaFree(g_gens_dev);
-        cudaFree(d_in);
-        g_gens_dev = nullptr;
-        free(key);
-        return nullptr;
-    }
-    int rc = bpk_gens_init_device(g_gens_dev, ws, d_in, d_in + n * 128, d_in + 2 * n * 128, d_in + 2 * n * 128 + 128, n, 0);
-    e = cudaDeviceSynchronize();
-    cudaFree(d_in);
+    if (d_in) cudaFree(d_in);
     if (rc != BPK_OK || e != cudaSuccess) {
         if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
-        cudaFree(g_gens_dev);
-        g_gens_dev = nullptr;
+        if (tab) cudaFree(tab);
         free(key);
         return nullptr;
     }
-    g_gens_key = key;
-    g_gens_key_bytes = key_bytes;
-    g_gens_n = n;
-    return g_gens_dev;
+    hv.gens_dev = tab;
+    hv.gens_key = key;
+    hv.gens_key_bytes = key_bytes;
+    hv.gens_n = n;
+    return hv.gens_dev;
 }
 
 bool cuda_range_proof_verify(const RangeProof* proof, const ge25519* V, size_t n, const PointVector* G,
@@ -578,12 +607,18 @@ bool cuda_range_proof_verify(const RangeProof* proof, const ge25519* V, size_t n
     const InnerProductProof* ip = &proof->ip_proof;
     if (ip->L_len != (size_t)k || ip->L.length != (size_t)k || ip->R.length != (size_t)k) return false;
     if (ip->a.length < 1 || ip->b.length < 1) return false;
-    std::lock_guard<std::mutex> lock(g_gens_mu);
-    const uint8_t* gens = gens_for(n, G, H, g, h);
-    if (!gens) return false;
     size_t rec = proof_record_bytes(k), ws = 0;
-    bpk_range_verify_workspace_bytes(n, 1, &ws);
-    uint8_t* hrec = (uint8_t*)calloc(1, rec);
+    if (bpk_range_verify_workspace_bytes(n, 1, &ws) != BPK_OK) return false;
+    // device buffer: record | V | accept | workspace; staging buffer: record | V
+    const size_t off_V = ipa_align(rec), off_acc = off_V + 256, off_ws = off_acc + 256;
+    DeviceLock dlock;
+    if (!dlock.ok()) return false;
+    HostVerify& hv = g_hv[dlock.dev];
+    if (!hv_reserve(hv, off_ws + ws, off_V + 128)) return false;
+    const uint8_t* gens = gens_for(hv, n, G, H, g, h);
+    if (!gens) return false;
+    uint8_t *hrec = hv.h_pin, *d = hv.d_buf;
+    memset(hrec, 0, off_V + 128);
     memcpy(hrec + kRecV, &proof->V, 5 * 128 + 3 * 32);
     memcpy(hrec + kRecIpA, ip->a.elements, 32);
     memcpy(hrec + kRecIpB, ip->b.elements, 32);
@@ -593,27 +628,16 @@ bool cuda_range_proof_verify(const RangeProof* proof, const ge25519* V, size_t n
         memcpy(hrec + kRecL, ip->L.elements, (size_t)k * 128);
         memcpy(hrec + kRecL + (size_t)k * 128, ip->R.elements, (size_t)k * 128);
     }
-    uint8_t* d = nullptr;
+    memcpy(hrec + off_V, V, 128);
+    cudaError_t e = cudaMemcpyAsync(d, hrec, off_V + 128, cudaMemcpyHostToDevice, hv.st);
     bool ok = false;
-    cudaError_t e = cudaMalloc(&d, rec + 128 + 256 + ws);
     if (e == cudaSuccess) {
-        uint8_t* d_V = d + ((rec + 255) / 256) * 256;
-        uint8_t* d_acc = d_V + 128;
-        uint8_t* d_ws = d_acc + 128;
-        e = cudaMalloc(&d_ws, ws);  // separate allocation keeps alignment simple
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d, hrec, rec, cudaMemcpyHostToDevice, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_V, V, 128, cudaMemcpyHostToDevice, 0);
-        if (e == cudaSuccess) {
-            int rc = bpk_range_verify_batch_device(gens, d, d_V, n, 1, d_acc, d_ws, ws, 0);
-            uint8_t acc = 0;
-            if (rc == BPK_OK) e = cudaMemcpy(&acc, d_acc, 1, cudaMemcpyDeviceToHost);
-            ok = rc == BPK_OK && e == cudaSuccess && acc != 0;
-        }
-        cudaFree(d_ws);
+        int rc = bpk_range_verify_batch_device(gens, d, d + off_V, n, 1, d + off_acc, d + off_ws, ws, hv.st);
+        if (rc == BPK_OK) e = cudaMemcpyAsync(hrec, d + off_acc, 1, cudaMemcpyDeviceToHost, hv.st);
+        if (rc == BPK_OK && e == cudaSuccess) e = cudaStreamSynchronize(hv.st);
+        ok = rc == BPK_OK && e == cudaSuccess && hrec[0] != 0;
     }
     if (e != cudaSuccess) fail(BPK_ERR_CUDA, e);
-    cudaFree(d);
-    free(hrec);
     return ok;
 }
 

@@ -945,7 +945,7 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->cap = 0;
     p->w_exact = 0;
     bool slots = n >= ((size_t)1 << 19);
-    if (const char* ev = getenv("CBP_MSM_SLOTS")) slots = ev[0] == '1';
+    if (options().msm_slots >= 0) slots = options().msm_slots != 0;  // measurement / test switch
     size_t entry_words = n * (size_t)p->W;
     if (slots && p->W > 1) {
         double mean = (double)n / (double)p->B;
@@ -989,10 +989,10 @@ struct StreamKit {
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     bool ok = false;
 };
-StreamKit g_kits[16][kMsmKits];
-StreamKit* stream_kit(int idx) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || idx < 0 || idx >= kMsmKits) return nullptr;
+StreamKit g_kits[kMaxDevices][kMsmKits];
+// caller holds the device lock
+StreamKit* stream_kit(int dev, int idx) {
+    if (dev < 0 || dev >= kMaxDevices || idx < 0 || idx >= kMsmKits) return nullptr;
     StreamKit& k = g_kits[dev][idx];
     if (!k.ok) {
         if (cudaStreamCreateWithFlags(&k.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
@@ -1025,16 +1025,15 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
         gm->ngroups = 1;
     } else {
         int remaining = W;
-        // CBP_GROUPS="10,4,2": explicit group sizes, top down, for measurements.  With the 2-D reduction on every
+        // explicit group sizes (options().groups, top down) for measurements.  With the 2-D reduction on every
         // group (ms at 2^20 / 2^22): 8,4,2,2 1.97 / 6.58; 8,4,4 2.03 / 6.36; 10,4,2 2.01 / 6.42; 9,4,3 2.01 / 6.40;
         // 10,3,3 2.02 / 6.47; 11,3,2 2.02 / 6.44; 12,4 2.02 / 6.38; 10,6 2.02 / 6.41.
-        const char* genv = getenv("CBP_GROUPS");
+        const Options& opt = options();
+        int gi = 0;
         while (remaining > 0) {
             int take = remaining > 1 ? remaining / 2 : 1;
-            if (genv && *genv) {
-                int v = atoi(genv);
-                while (*genv && *genv != ',') genv++;
-                if (*genv == ',') genv++;
+            if (gi < opt.ngroups) {
+                int v = opt.groups[gi++];
                 if (v >= 1 && v <= remaining && gm->ngroups < kMaxGroups - 1) {
                     gm->w_hi[gm->ngroups] = hi;
                     gm->w_lo[gm->ngroups] = hi - v + 1;
@@ -1107,10 +1106,15 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
+    // bucket offsets, cursors and entry indices are 32-bit (index << 1 | sign; prefix sums over n * W entries)
+    if (n >= ((size_t)1 << 31) || n * (size_t)p.W >= ((size_t)1 << 32)) return (int)cudaErrorInvalidValue;
     const int carry = (flags & kMsmCarryIn) ? 1 : 0;
     const bool no_tail = (flags & kMsmNoTail) != 0;
+    // the side streams and events of a kit are shared by every call on this device: serialise the enqueue
+    DeviceLock dlock;
+    if (!dlock.ok()) return (int)cudaErrorInvalidDevice;
     // a chunk that only adds into the buckets has no tails to overlap: one group, everything on `st`
-    StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(kit_index) : nullptr;
+    StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(dlock.dev, kit_index) : nullptr;
     GroupMap gm;
     // the last group's reduction is exposed: 16 windows go as 8, 4, 2, 2 up to 2^20 points and as 8, 4, 4 above
     // (measured with the 2-D reduction on every group, 8,4,2,2 / 8,4,4: 2^19 1.30 / 1.31 ms, 2^20 2.00 / 2.03,
@@ -1223,8 +1227,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         // running-sum levels, starved of SM slots by the next accumulation, delayed the chain to the end
         // (2-D on the last group only / on all groups: 2^18 1.06 / 0.94 ms, 2^20 2.16 / 2.03, 2^22 6.56 / 6.44).
         // The running-sum kernels remain for narrow windows (c < 9) and as a cross-check (CBP_MSM_NO2D).
-        static const bool no2d = getenv("CBP_MSM_NO2D") != nullptr;
-        if (p.c >= 9 && !no2d) {
+        if (p.c >= 9 && !options().msm_no2d) {
             const int lbits = (p.c - 1) / 2, hbits = p.c - 1 - lbits;
             const uint32_t per = (p.B >> lbits) + (1u << lbits);  // <= n1 for c >= 9
             uint8_t* sums = ws + p.off_redX[0] + (size_t)w_lo * n1 * 128;

@@ -63,15 +63,51 @@ __device__ __forceinline__ uint64_t sm64_at(uint64_t seed, uint64_t idx) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
+// Where a proof's blinding values and nonces (alpha, rho, tau1, tau2, sL, sR) come from:
+//  * seeds: the SplitMix64 stream oracle/ref_corrected.c draws from, keyed by a 64-bit seed.  NOT cryptographic
+//    (invertible, 64 bits of state): for parity tests and benchmark inputs only.
+//  * keys:  one 32-byte secret per proof from the caller's CSPRNG (the reference draws every value from OpenSSL
+//    RAND_bytes, bulletproof_range_proof.cu:153); draw j = SHA-256("cbp-bp-nonce" || key || j_le32), i.e. SHA-256
+//    in counter mode as the PRF, so hiding rests on the 256-bit key.
+struct NonceSource {
+    const uint64_t* seeds;
+    const uint8_t* keys;
+};
+struct Nonce {
+    uint64_t seed;
+    const uint8_t* key;  // 32 bytes, or nullptr: seeded stream
+};
+__device__ __forceinline__ Nonce nonce_of(const NonceSource& src, uint32_t proof) {
+    Nonce nn;
+    nn.seed = src.keys ? 0 : src.seeds[proof];
+    nn.key = src.keys ? src.keys + (size_t)proof * 32 : nullptr;
+    return nn;
+}
+static __device__ __noinline__ void keyed_draw(uint32_t (&out)[8], const uint8_t* key, uint32_t j) {
+    Sha256 sh;
+    sh.init();
+    sh.update_str("cbp-bp-nonce", 12);
+    sh.update(key, 32);
+    const uint8_t ctr[4] = {(uint8_t)j, (uint8_t)(j >> 8), (uint8_t)(j >> 16), (uint8_t)(j >> 24)};
+    sh.update(ctr, 4);
+    uint32_t h[8];
+    sh.final_words(h);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = __byte_perm(h[i], 0, 0x0123);  // digest bytes as a little-endian integer
+}
 // the j-th 32-byte draw of the stream, clamped like generate_random_scalar
 // (bulletproof_range_proof.cu:153-159), then reduced mod l
-__device__ __forceinline__ void draw_scalar(sc& r, uint64_t seed, uint32_t j) {
+__device__ __forceinline__ void draw_scalar(sc& r, const Nonce& nn, uint32_t j) {
     sc t;
+    if (nn.key) {
+        keyed_draw(t.v, nn.key, j);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint64_t v = sm64_at(seed, (uint64_t)j * 4 + q);
-        t.v[2 * q] = (uint32_t)v;
-        t.v[2 * q + 1] = (uint32_t)(v >> 32);
+        for (int q = 0; q < 4; q++) {
+            uint64_t v = sm64_at(nn.seed, (uint64_t)j * 4 + q);
+            t.v[2 * q] = (uint32_t)v;
+            t.v[2 * q + 1] = (uint32_t)(v >> 32);
+        }
     }
     t.v[7] &= 0x7FFFFFFFu;
     t.v[0] &= 0xFFFFFFF8u;
@@ -117,7 +153,7 @@ __device__ __forceinline__ void hash_xy(Sha256& sh, const ge_p3& P) {  // P norm
 __global__ void __launch_bounds__(kPThreads, 8) range_prove_kernel(const uint8_t* __restrict__ gens,
                                                                 const uint64_t* __restrict__ values,
                                                                 const uint8_t* __restrict__ gammas,
-                                                                const uint64_t* __restrict__ seeds, uint32_t n, int k,
+                                                                NonceSource nsrc, uint32_t n, int k,
                                                                 uint8_t* __restrict__ proofs, size_t rec_bytes) {
     __shared__ sc sa[kMaxN], sb[kMaxN], swG[kMaxN], swH[kMaxN];
     __shared__ sc sred[kPThreads];
@@ -132,7 +168,8 @@ __global__ void __launch_bounds__(kPThreads, 8) range_prove_kernel(const uint8_t
     const uint32_t p = blockIdx.x;
     const FixTab table = fixtab_of(gens);
     uint8_t* rec = proofs + (size_t)p * rec_bytes;
-    const uint64_t v = values[p], seed = seeds[p];
+    const uint64_t v = values[p];
+    const Nonce seed = nonce_of(nsrc, p);
     const int nrows = 2 * (int)n + 2, row_g = 2 * (int)n, row_h = 2 * (int)n + 1;
 
     if (n < 64 && (v >> n) != 0) {  // validate_range_input (:238-263): initialised, invalid proof (D20)
@@ -471,14 +508,15 @@ __device__ __forceinline__ void pb_zero_rows(int8_t* rows, int nrows, int t) {
 __global__ void __launch_bounds__(kPThreads) pb_init_kernel(const uint8_t* __restrict__ gens,
                                                             const uint64_t* __restrict__ values,
                                                             const uint8_t* __restrict__ gammas,
-                                                            const uint64_t* __restrict__ seeds, uint32_t n, int k,
+                                                            NonceSource nsrc, uint32_t n, int k,
                                                             uint8_t* __restrict__ proofs, size_t rec_bytes,
                                                             PScal* __restrict__ ps, int8_t* __restrict__ digits) {
     const int t = threadIdx.x;
     const uint32_t p = blockIdx.x;
     const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
     uint8_t* rec = proofs + (size_t)p * rec_bytes;
-    const uint64_t v = values[p], seed = seeds[p];
+    const uint64_t v = values[p];
+    const Nonce seed = nonce_of(nsrc, p);
     const int nrows = 2 * (int)n + 2, row_g = 2 * (int)n, row_h = 2 * (int)n + 1;
     if (n < 64 && (v >> n) != 0) {  // validate_range_input (:238-263): initialised, invalid proof (D20)
         ge_p3 O;
@@ -684,7 +722,7 @@ __global__ void __launch_bounds__(64) pb_yz_kernel(uint8_t* __restrict__ proofs,
 // phase 3: l(X), r(X), t0..t2; digits of T1 (slot 0), T2 (slot 1)
 __global__ void __launch_bounds__(kPThreads) pb_poly_kernel(const uint8_t* __restrict__ gens,
                                                             const uint64_t* __restrict__ values,
-                                                            const uint64_t* __restrict__ seeds, uint32_t n, int k,
+                                                            NonceSource nsrc, uint32_t n, int k,
                                                             PScal* __restrict__ ps, const sc* __restrict__ inv_out,
                                                             int8_t* __restrict__ digits, sc* __restrict__ vl0,
                                                             sc* __restrict__ vr0, sc* __restrict__ vr1,
@@ -695,7 +733,8 @@ __global__ void __launch_bounds__(kPThreads) pb_poly_kernel(const uint8_t* __res
     const uint32_t p = blockIdx.x;
     if (!ps[p].valid) return;
     const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
-    const uint64_t v = values[p], seed = seeds[p];
+    const uint64_t v = values[p];
+    const Nonce seed = nonce_of(nsrc, p);
     const int nrows = 2 * (int)n + 2, row_g = 2 * (int)n, row_h = 2 * (int)n + 1;
     if (t == 0) {
         sc yi = inv_out[p];
@@ -770,7 +809,7 @@ __global__ void __launch_bounds__(kPThreads) pb_poly_kernel(const uint8_t* __res
 }
 
 // phase 4: T1, T2 -> record; x; t, taux, mu; a, b, weights; IPA transcript seed
-__global__ void __launch_bounds__(kPThreads) pb_ipa_init_kernel(const uint64_t* __restrict__ seeds, uint32_t n,
+__global__ void __launch_bounds__(kPThreads) pb_ipa_init_kernel(NonceSource nsrc, uint32_t n,
                                                                 uint8_t* __restrict__ proofs, size_t rec_bytes,
                                                                 const uint8_t* __restrict__ pts, PScal* __restrict__ ps,
                                                                 const sc* __restrict__ vl0, const sc* __restrict__ vr0,
@@ -781,7 +820,7 @@ __global__ void __launch_bounds__(kPThreads) pb_ipa_init_kernel(const uint64_t* 
     const uint32_t p = blockIdx.x;
     if (!ps[p].valid) return;
     uint8_t* rec = proofs + (size_t)p * rec_bytes;
-    const uint64_t seed = seeds[p];
+    const Nonce seed = nonce_of(nsrc, p);
     if (t == 0) {
         ge_p3 T1, T2;
         ge_load(T1, pts + ((size_t)p * 3 + 0) * 128);
@@ -1034,23 +1073,23 @@ int bpk_range_prove_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes) 
     *bytes = num_proofs >= kPbMinBatch ? pb_layout(chunk).total : 0;
     return BPK_OK;
 }
-int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas,
-                                 const uint64_t* d_seeds, size_t n, size_t num_proofs, void* d_proofs,
-                                 void* d_workspace, size_t workspace_bytes, void* stream) {
+static int range_prove_batch(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas,
+                             const uint64_t* d_seeds, const uint8_t* d_keys, size_t n, size_t num_proofs, void* d_proofs,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
     if (n == 0 || n > kMaxN || (n & (n - 1))) return fail(BPK_ERR_ARG);
     if (!num_proofs) return BPK_OK;
-    if (!d_gens_ws || !d_values || !d_gammas || !d_seeds || !d_proofs) return fail(BPK_ERR_ARG);
+    if (!d_gens_ws || !d_values || !d_gammas || (!d_seeds && !d_keys) || !d_proofs) return fail(BPK_ERR_ARG);
     int k = 0;
     while (((size_t)1 << k) < n) k++;
     const size_t rec = proof_record_bytes(k);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t chunk = num_proofs < kPbChunk ? num_proofs : kPbChunk;
-    static const bool legacy_env = getenv("CBP_PROVER_LEGACY") != nullptr;
+    const bool legacy_env = options().prover_legacy != 0;
     const int wbits = bpk_gens_window_bits(d_gens_ws);
     if (legacy_env || n < 2 || num_proofs < kPbMinBatch || !d_workspace || workspace_bytes < pb_layout(chunk).total || !wbits) {
         range_prove_kernel<<<(unsigned)num_proofs, kPThreads, 0, st>>>((const uint8_t*)d_gens_ws, d_values,
-                                                                      (const uint8_t*)d_gammas, d_seeds, (uint32_t)n, k,
-                                                                      (uint8_t*)d_proofs, rec);
+                                                                      (const uint8_t*)d_gammas, NonceSource{d_seeds, d_keys},
+                                                                      (uint32_t)n, k, (uint8_t*)d_proofs, rec);
         CBP_CHECK_LAUNCH();
         return BPK_OK;
     }
@@ -1067,7 +1106,7 @@ int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values
     for (size_t done = 0; done < num_proofs; done += chunk) {
         const uint32_t cnt = (uint32_t)((num_proofs - done) < chunk ? (num_proofs - done) : chunk);
         const uint64_t* vals = d_values + done;
-        const uint64_t* seeds = d_seeds + done;
+        const NonceSource seeds{d_keys ? nullptr : d_seeds + done, d_keys ? d_keys + done * 32 : nullptr};
         const uint8_t* gam = (const uint8_t*)d_gammas + done * 32;
         uint8_t* proofs = (uint8_t*)d_proofs + done * rec;
         auto fixed_msm = [&](int nslots, int3 first_row) -> int {
@@ -1117,6 +1156,19 @@ int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values
         }
     }
     return BPK_OK;
+}
+int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas,
+                                 const uint64_t* d_seeds, size_t n, size_t num_proofs, void* d_proofs,
+                                 void* d_workspace, size_t workspace_bytes, void* stream) {
+    return range_prove_batch(d_gens_ws, d_values, d_gammas, d_seeds, nullptr, n, num_proofs, d_proofs, d_workspace,
+                             workspace_bytes, stream);
+}
+int bpk_range_prove_batch_keyed_device(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas,
+                                       const void* d_keys, size_t n, size_t num_proofs, void* d_proofs,
+                                       void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (num_proofs && !d_keys) return fail(BPK_ERR_ARG);
+    return range_prove_batch(d_gens_ws, d_values, d_gammas, nullptr, (const uint8_t*)d_keys, n, num_proofs, d_proofs,
+                             d_workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

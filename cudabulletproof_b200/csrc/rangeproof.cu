@@ -729,10 +729,10 @@ struct VerifySide {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool ok = false;
 };
-static VerifySide g_vside[16];
-static VerifySide* verify_side() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+static VerifySide g_vside[kMaxDevices];
+// caller holds the device lock
+static VerifySide* verify_side(int dev) {
+    if (dev < 0 || dev >= kMaxDevices) return nullptr;
     VerifySide& v = g_vside[dev];
     if (!v.ok) {
         if (cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
@@ -765,7 +765,9 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     int8_t *digits = (int8_t*)(ws + L.digits), *vdigits = (int8_t*)(ws + L.vdigits);
     const int nvar = 2 + 2 * k + 3;
     cudaStream_t st = (cudaStream_t)stream;
-    VerifySide* side = verify_side();
+    DeviceLock dlock;  // the side stream and its events are shared by every call on this device
+    if (!dlock.ok()) return BPK_ERR_CUDA;
+    VerifySide* side = verify_side(dlock.dev);
     if (!side) return fail(BPK_ERR_CUDA);
     prof_begin(BPK_PROF_VERIFY_TOTAL, st);
     for (size_t done = 0; done < num_proofs; done += chunk) {

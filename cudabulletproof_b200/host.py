@@ -74,6 +74,20 @@ def cuda_field_vector_inner_product(a, b, shared=False, result=None):
     return out
 
 
+def cuda_batch_field_vector_inner_product(a_vectors, b_vectors, results=None):
+    """results[v] = <a_vectors[v], b_vectors[v]> mod l for separately allocated vectors
+    (cuda_inner_product.cu:302-348; defined in the reference, absent from its header)."""
+    from . import FieldVector
+    a_vectors = [_c(a, 4) for a in a_vectors]
+    b_vectors = [_c(b, 4) for b in b_vectors]
+    m = len(a_vectors)
+    out = np.zeros((m, 4), dtype=np.uint64) if results is None else results
+    fa = (FieldVector * max(m, 1))(*[_fv(a) for a in a_vectors])
+    fb = (FieldVector * max(m, 1))(*[_fv(b) for b in b_vectors])
+    _guard(_lib().cuda_batch_field_vector_inner_product, _ptr(out), fa, fb, m)
+    return out
+
+
 def _batch2(name, a, b):
     a, b = _c(a, 4), _c(b, 4)
     out = np.zeros_like(a)
@@ -210,20 +224,31 @@ class Generators:
         self.record_bytes = proof_record_bytes(self.n)
 
 
-def range_prove_batch(gens, values, gammas, seeds, stream=None):
-    """values: (m,) int/uint64, gammas: (m,4) uint64 scalars, seeds: (m,) -> (m, record_bytes) uint8 cuda tensor."""
+def range_prove_batch(gens, values, gammas, seeds=None, stream=None, keys=None):
+    """values: (m,) int/uint64, gammas: (m,4) uint64 scalars -> (m, record_bytes) uint8 cuda tensor.
+    keys: (m, 32) uint8 secrets from a CSPRNG, one per proof (bpk_range_prove_batch_keyed_device) — the prover.
+    seeds: (m,) 64-bit seeds of the oracle's SplitMix64 stream (bpk_range_prove_batch_device) — parity tests and
+    benchmark inputs ONLY: that stream is not cryptographic."""
     import torch
+    assert (seeds is None) != (keys is None), "exactly one of seeds / keys"
     m = len(values)
     d_v = torch.from_numpy(np.asarray(values, dtype=np.uint64).view(np.int64)).to(gens.device)
-    d_s = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(gens.device)
     d_g = torch.from_numpy(np.ascontiguousarray(gammas, dtype=np.uint64).view(np.uint8).reshape(-1)).to(gens.device)
     out = torch.zeros((m, gens.record_bytes), dtype=torch.uint8, device=gens.device)
     nbytes = C.c_size_t(0)
     _check(_lib().bpk_range_prove_workspace_bytes(gens.n, m, C.byref(nbytes)), "bpk_range_prove_workspace_bytes")
     ws = _dev_u8(max(1, nbytes.value), gens.device)  # batches of 64+ proofs take the phase-split prover
-    _check(_lib().bpk_range_prove_batch_device(gens.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(),
-                                               d_s.data_ptr(), gens.n, m, out.data_ptr(), ws.data_ptr(), nbytes.value,
-                                               _stream_ptr(stream)), "bpk_range_prove_batch_device")
+    if keys is not None:
+        d_k = torch.from_numpy(np.ascontiguousarray(keys, dtype=np.uint8).reshape(m, 32)).to(gens.device)
+        _check(_lib().bpk_range_prove_batch_keyed_device(gens.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(),
+                                                         d_k.data_ptr(), gens.n, m, out.data_ptr(), ws.data_ptr(),
+                                                         nbytes.value, _stream_ptr(stream)),
+               "bpk_range_prove_batch_keyed_device")
+    else:
+        d_s = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(gens.device)
+        _check(_lib().bpk_range_prove_batch_device(gens.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(),
+                                                   d_s.data_ptr(), gens.n, m, out.data_ptr(), ws.data_ptr(), nbytes.value,
+                                                   _stream_ptr(stream)), "bpk_range_prove_batch_device")
     torch.cuda.current_stream().synchronize()
     return out
 

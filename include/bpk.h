@@ -34,6 +34,17 @@ int bpk_clear_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t bpk_kernel_launches(void);
 
+/* measurement / test switches.  Their defaults come from the environment ONCE per process (CBP_MSM_SLOTS,
+ * CBP_MSM_NO2D, CBP_HOST_CHUNK_LOG2, CBP_PROVER_LEGACY, CBP_GROUPS, CBP_MSM_SMALL_MAX); no entry point reads the
+ * environment on its call path.  None is needed in production. */
+#define BPK_OPT_MSM_SLOTS 0       /* -1 auto, 0 / 1: slotted first digit pass off / on for every size */
+#define BPK_OPT_MSM_NO2D 1        /* 1: running-sum bucket reduction everywhere (cross-check of the 2-D one) */
+#define BPK_OPT_HOST_CHUNK_LOG2 2 /* log2 of the upload chunk of the host-pointer MSM, 0 = default */
+#define BPK_OPT_PROVER_LEGACY 3   /* 1: one-CTA-per-proof prover for every batch size */
+#define BPK_OPT_MSM_GROUPS 4      /* window groups of the MSM pipeline as hex digits, top first (0x844); 0 = auto */
+#define BPK_OPT_MSM_SMALL_MAX 5   /* largest n routed to the single-launch small-n MSM; -1 default, 0 disables */
+int bpk_debug_set_option(int option, long long value);
+
 /* ---- per-kernel device timing (bench.py's roofline): CUDA events recorded on the launching stream
  * around the named kernel of every call while enabled; read returns the mean duration in ms ---- */
 #define BPK_PROF_MSM_ACCUMULATE 0 /* msm_accumulate_kernel  */
@@ -47,6 +58,19 @@ uint64_t bpk_kernel_launches(void);
 int bpk_profile_enable(int enable);
 int bpk_profile_reset(void);
 int bpk_profile_read(int kind, float* mean_ms, int* samples); /* synchronises the recorded events */
+
+/* ---- the integer roofline denominator, measured in the caller's own run (csrc/intpeak.cu) ----
+ * Runs issue-rate microbenchmarks for about target_ms each on the current device and returns lane operations per
+ * second in rates[0..count): [0] IMAD.WIDE.U32 carry chains (fe_mul's inner pattern; the roofline denominator),
+ * [1] IMAD.WIDE.U32 independent, [2] IMAD 32-bit, [3] IMAD.HI.U32, [4] DFMA (FP64).  Synchronises; allocates and
+ * frees a small buffer: not for a hot path. */
+#define BPK_PEAK_IMAD_WIDE_CARRY 0
+#define BPK_PEAK_IMAD_WIDE 1
+#define BPK_PEAK_IMAD_LO 2
+#define BPK_PEAK_IMAD_HI 3
+#define BPK_PEAK_DFMA 4
+#define BPK_PEAK_KINDS 5
+int bpk_measure_int_peak(double target_ms, double* rates, int count);
 
 /* ---- multi-scalar multiplication: replaces cuda_point_vector_multi_scalar_mul (cuda_bulletproof.h:13) ---- */
 /* window_bits = 0 picks c(n).  *bytes = workspace needed by bpk_msm_device for that (n, window_bits). */
@@ -110,6 +134,11 @@ int bpk_gens_derive_device(void* d_points, const uint8_t seed[32], uint32_t firs
 /* test hook: out[i] = 2 a[i] (op 0), a[i] + b[i] (op 1; b NULL: a[i] + a[i]), 8 a[i] (op 2); extended points,
  * outputs not normalised.  Lets the parity tests pin the group law itself against the CPU oracle. */
 int bpk_debug_ge_op_device(int op, const void* d_a, const void* d_b, void* d_out, size_t count, void* stream);
+/* test hook: d_points[i] <- the same group element with a pseudo-random Z != 1 (all four coordinates scaled),
+ * after adding *d_torsion (one ge25519, may be NULL) to every torsion_stride-th point.  Lets full-size MSM parity
+ * tests cover projective and torsion-carrying inputs. */
+int bpk_debug_projectivize_device(void* d_points, size_t n, uint64_t seed, const void* d_torsion,
+                                  uint32_t torsion_stride, void* stream);
 /* test hook: field operations on compile-time constants; writes 6 field elements (8 words each):
  * 1^2, 1*1, 1+1, 2^2, 1-2 (canonical), 2*(2d) (canonical).  Guards the inline-asm operand constraints. */
 int bpk_debug_const_operands_device(uint32_t* d_out48, void* stream);
@@ -139,13 +168,27 @@ int bpk_range_verify_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes)
 int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, const void* d_V, size_t n,
                                   size_t num_proofs, uint8_t* d_accept, void* d_workspace, size_t workspace_bytes,
                                   void* stream);
-/* deterministic batch prover (generate_range_proof, bulletproof_range_proof.cu:1159-1714, restated):
- * proof i commits d_values[i] (< 2^n) with blinding and nonces drawn from the SplitMix64 stream
- * seeded by d_seeds[i] — the same stream oracle/ref_corrected.c draws, so proofs are bit-identical.
+/* Batch prover (generate_range_proof, bulletproof_range_proof.cu:1159-1714, restated).  Two sources for the
+ * blinding values and nonces (alpha, rho, tau1, tau2, sL, sR); same protocol, same record layout:
+ *
+ * bpk_range_prove_batch_keyed_device — THE PROVER.  d_keys: 32 secret bytes per proof from the caller's CSPRNG
+ *   (the reference draws every value from OpenSSL RAND_bytes, bulletproof_range_proof.cu:153); value j of a proof
+ *   is SHA-256("cbp-bp-nonce" || key || j_le32) shaped like generate_random_scalar and reduced mod l.  Never
+ *   reuse a key for two different (value, gamma) pairs.
+ *
+ * bpk_range_prove_batch_device — FOR TESTS AND BENCHMARKS ONLY.  Values come from a SplitMix64 stream seeded by
+ *   the 64-bit d_seeds[i]: the stream oracle/ref_corrected.c draws, so proofs are bit-identical to the oracle's.
+ *   SplitMix64 is invertible and not cryptographic: a recovered seed yields tau1, tau2, hence gamma and v.  Do not
+ *   use it for proofs that must hide anything.
+ *
  * The workspace is optional: with bpk_range_prove_workspace_bytes() bytes (28 KB per proof, capped at 2^14
  * proofs) batches of 64+ proofs run as a phase-split pipeline with batch inversions across proofs; with NULL
  * every proof is one CTA.  Same bytes either way. */
 int bpk_range_prove_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes);
+int bpk_range_prove_batch_keyed_device(const void* d_gens_ws, const uint64_t* d_values,
+                                       const void* d_gammas /* 32 B each */, const void* d_keys /* 32 B each */,
+                                       size_t n, size_t num_proofs, void* d_proofs, void* d_workspace,
+                                       size_t workspace_bytes, void* stream);
 int bpk_range_prove_batch_device(const void* d_gens_ws, const uint64_t* d_values, const void* d_gammas /* 32 B each */,
                                  const uint64_t* d_seeds, size_t n, size_t num_proofs, void* d_proofs,
                                  void* d_workspace, size_t workspace_bytes, void* stream);

@@ -66,3 +66,29 @@ def flatten_proof(proof, n):
         rec[108 + 16 * j:108 + 16 * (j + 1)] = np.frombuffer(bytes(ip.L.elements[j]), dtype=np.uint64)
         rec[108 + 16 * (k + j):108 + 16 * (k + j + 1)] = np.frombuffer(bytes(ip.R.elements[j]), dtype=np.uint64)
     return rec
+
+
+def dot_mod_l(sc_h, ks_h):
+    """sum_i s_i * k_i mod l for (n, 4) uint64 little-endian 256-bit s_i and (n,) uint64 k_i, vectorised:
+    32 x 32-bit partial products are exact in uint64; their low and high halves are summed separately so that
+    no sum over up to 2^24 terms overflows."""
+    from oracle import pyref
+    s32 = np.ascontiguousarray(sc_h, dtype=np.uint64).view(np.uint32).reshape(-1, 8).astype(np.uint64)
+    k32 = np.ascontiguousarray(ks_h, dtype=np.uint64).view(np.uint32).reshape(-1, 2).astype(np.uint64)
+    mask = np.uint64(0xFFFFFFFF)
+    total = 0
+    for a in range(8):
+        for b in range(2):
+            prod = s32[:, a] * k32[:, b]
+            lo, hi = int((prod & mask).sum(dtype=np.uint64)), int((prod >> np.uint64(32)).sum(dtype=np.uint64))
+            total += (lo + (hi << 32)) << (32 * (a + b))
+    return total % pyref.L
+
+
+def base_multiple(oracle, k):
+    """(k mod l) * B normalised, as a (16,) uint64 ge25519 (one CPU scalar multiplication by the oracle)"""
+    from oracle import pyref
+    want = np.zeros(16, dtype=np.uint64)
+    oracle.ge25519_scalarmult_base(ob.ptr(want), (k % pyref.L).to_bytes(32, "little"))
+    oracle.ge25519_normalize(ob.ptr(want))
+    return want

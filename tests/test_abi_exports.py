@@ -48,13 +48,14 @@ def test_product_never_touches_the_oracle():
                 assert not pat.search(text), f
 
 
-def test_msm_plan_is_host_only_and_consistent(monkeypatch):
+def test_msm_plan_is_host_only_and_consistent():
     """bpk_msm_window_bits / bpk_msm_workspace_bytes are pure host logic (the plan): the measured window table,
     the workspace growing with the input, the slotted front end's extra room from 2^19 points, argument checks."""
     import ctypes as C
     import cudabulletproof_b200 as cbp
     lib = cbp.load()
-    monkeypatch.delenv("CBP_MSM_SLOTS", raising=False)
+    OPT_SLOTS = 0  # include/bpk.h BPK_OPT_MSM_SLOTS: -1 auto, 0 off, 1 on (no entry point reads the environment)
+    assert lib.bpk_debug_set_option(OPT_SLOTS, -1) == 0
     assert [lib.bpk_msm_window_bits(n) for n in (1, 1 << 10, 1 << 11, 1 << 18, 1 << 19, 1 << 24)] == [13, 13, 15, 15, 16, 16]
 
     def ws(n, c=0):
@@ -65,16 +66,23 @@ def test_msm_plan_is_host_only_and_consistent(monkeypatch):
     sizes = [ws(1 << lg) for lg in range(6, 25, 2)]
     assert sizes == sorted(sizes) and sizes[0] > 0
     slotted = ws(1 << 20)
-    monkeypatch.setenv("CBP_MSM_SLOTS", "0")
+    lib.bpk_debug_set_option(OPT_SLOTS, 0)
     compact = ws(1 << 20)
     # slots: 15 windows x 2^15 buckets x cap entries (mean 32 + 8 sigma + 8, a multiple of 8 = 88) + the top window's
     # compact run and ranks, against 16 x 2^20 entries
     cap = 88
     assert slotted - compact == (15 * 32768 * cap + (1 << 20) - 16 * (1 << 20)) * 4 + 8 * (1 << 20)
-    monkeypatch.setenv("CBP_MSM_SLOTS", "1")
+    lib.bpk_debug_set_option(OPT_SLOTS, 1)
     assert ws(1 << 12, 11) > 0
+    lib.bpk_debug_set_option(OPT_SLOTS, -1)
     out = C.c_size_t(0)
     for bad in (3, 18, -1):
         assert lib.bpk_msm_workspace_bytes(1 << 12, bad, C.byref(out)) != 0
     assert lib.bpk_msm_workspace_bytes(1 << 31, 0, C.byref(out)) != 0
+    # entry offsets are 32-bit prefix sums over n * W entries: n * ceil(256 / c) must stay below 2^32
+    assert lib.bpk_msm_workspace_bytes((1 << 28) - 1, 16, C.byref(out)) == 0
+    assert lib.bpk_msm_workspace_bytes(1 << 28, 16, C.byref(out)) != 0
+    assert lib.bpk_msm_workspace_bytes(1 << 28, 0, C.byref(out)) != 0
+    assert lib.bpk_msm_workspace_bytes(1 << 27, 4, C.byref(out)) != 0
+    assert lib.bpk_debug_set_option(99, 0) != 0
     lib.bpk_last_error()  # clear

@@ -130,3 +130,63 @@ def test_batch_invert_tree_path_matches_single_kernel_and_python(count):
     for i in [0, 1, 7, 255, 256, 4095, 4096, count // 2, count - 2, count - 1]:
         v = ob.fe_to_int(h_a[i]) % P
         assert ob.fe_to_int(h_o[i]) == (pow(v, P - 2, P) if v else 0)
+
+
+@pytest.mark.parametrize("n,num_vectors", [(1, 1), (5, 3), (64, 17), (513, 4), (4096, 2), (0, 3), (700, 1)])
+def test_batched_inner_product_bit_exact(oracle, n, num_vectors):
+    """cuda_batch_field_vector_inner_product (cuda_inner_product.cu:302-348, kernel K18; defined in the reference
+    but missing from its header): num_vectors separately allocated vector pairs of one length -> one result each,
+    against the oracle's field_vector_inner_product (mod l) per pair and Python big ints."""
+    import cudabulletproof_b200 as cbp
+    rng = random.Random(7000 + 31 * n + num_vectors)
+    va = [rand_fe(rng, n, edge=(v == 0)) for v in range(num_vectors)]
+    vb = [rand_fe(rng, n, edge=(v == 1)) for v in range(num_vectors)]
+    a, b = [to_fe(x) for x in va], [to_fe(x) for x in vb]
+    got = cbp.cuda_batch_field_vector_inner_product(a, b)
+    assert got.shape == (num_vectors, 4)
+    for v in range(num_vectors):
+        assert ob.fe_to_int(got[v]) == sum(x * y for x, y in zip(va[v], vb[v])) % L, v
+        if n:
+            want = np.zeros(4, dtype=np.uint64)
+            fa, fb = ob.field_vector(a[v]), ob.field_vector(b[v])
+            oracle.field_vector_inner_product(ob.ptr(want), C.byref(fa), C.byref(fb))
+            assert np.array_equal(got[v], want), v
+
+
+def test_batched_inner_product_ragged_batch_is_refused(capfd):
+    """The reference takes n from the first pair and copies n elements of every vector
+    (cuda_inner_product.cu:306,312-315): a ragged batch reads out of bounds there.  Here it is refused like the
+    single-pair length mismatch (message on stderr, results untouched)."""
+    import cudabulletproof_b200 as cbp
+    a = [to_fe([1, 2, 3]), to_fe([4, 5])]
+    b = [to_fe([1, 2, 3]), to_fe([4, 5])]
+    res = np.full((2, 4), 0xDEADBEEF, dtype=np.uint64)
+    cbp.cuda_batch_field_vector_inner_product(a, b, results=res)
+    assert (res == 0xDEADBEEF).all()
+    assert "Vector lengths must match" in capfd.readouterr().err
+
+
+@pytest.mark.parametrize("n,num_vectors", [(64, 1000), (4096, 37), (3, 5000)])
+def test_batched_inner_product_device_api(n, num_vectors):
+    """bpk_sc_inner_product_batch_device on contiguous device arrays (one CTA per pair), against the
+    single-pair kernel pair (pinned to the oracle above) and Python big ints on a sample."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    a = cbp.synth_scalars(n * num_vectors, seed=0xBA7C4 + n, bits=256)
+    b = cbp.synth_scalars(n * num_vectors, seed=0xBA7C5 + n, bits=253)
+    out = torch.zeros((num_vectors, 32), dtype=torch.uint8, device="cuda")
+    assert lib.bpk_sc_inner_product_batch_device(out.data_ptr(), a.data_ptr(), b.data_ptr(), n, num_vectors, None) == 0
+    nb = C.c_size_t(0)
+    lib.bpk_sc_inner_product_workspace_bytes(n, C.byref(nb))
+    ws = torch.zeros(max(nb.value, 16), dtype=torch.uint8, device="cuda")
+    one = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    h_a = a.cpu().numpy().view(np.uint64).reshape(num_vectors, n, 4)
+    h_b = b.cpu().numpy().view(np.uint64).reshape(num_vectors, n, 4)
+    h_o = out.cpu().numpy().view(np.uint64).reshape(num_vectors, 4)
+    for v in sorted({0, 1, num_vectors // 2, num_vectors - 1}):
+        assert lib.bpk_sc_inner_product_device(one.data_ptr(), a[v * n:].data_ptr(), b[v * n:].data_ptr(), n,
+                                               ws.data_ptr(), ws.numel(), None) == 0
+        assert np.array_equal(one.cpu().numpy().view(np.uint64), h_o[v])
+        want = sum(ob.fe_to_int(x) * ob.fe_to_int(y) for x, y in zip(h_a[v], h_b[v])) % L
+        assert ob.fe_to_int(h_o[v]) == want

@@ -15,6 +15,16 @@ pytestmark = pytest.mark.gpu
 P, L = pyref.P, pyref.L
 
 
+@pytest.fixture
+def slot_option():
+    """forces the slotted first digit pass off / on (bpk_debug_set_option; the library never reads the environment
+    on a call path), restored to automatic afterwards"""
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    yield lambda v: cbp.check(lib.bpk_debug_set_option(0, v), "bpk_debug_set_option")
+    lib.bpk_debug_set_option(0, -1)
+
+
 def oracle_msm(oracle, sc, pts):
     out = np.zeros(16, dtype=np.uint64)
     fv, pv = ob.field_vector(sc), ob.point_vector(pts)
@@ -202,13 +212,13 @@ def test_msm_host_pointer_chunked_equal_scalars(oracle):
 
 @pytest.mark.parametrize("slots", ["0", "1"])
 @pytest.mark.parametrize("window_bits", [7, 11])
-def test_msm_slotted_front_end_small(oracle, monkeypatch, slots, window_bits):
+def test_msm_slotted_front_end_small(oracle, slot_option, slots, window_bits):
     """The first digit pass places every window but the top one into fixed bucket slots (msm.cu,
     msm_digits_kernel<0>; default from 2^19 points, forced here).  Random scalars stay inside the slots;
     repeated scalars overflow them and take the exact two-pass placement: same bytes either way."""
     import torch
     import cudabulletproof_b200 as cbp
-    monkeypatch.setenv("CBP_MSM_SLOTS", slots)
+    slot_option(int(slots))
     rng = random.Random(900 + window_bits)
     n = 600
     pts = np.stack([ob.affine_to_ge(*p) for p in curve_points(rng, n)])
@@ -229,7 +239,7 @@ def test_msm_slotted_front_end_small(oracle, monkeypatch, slots, window_bits):
         assert np.array_equal(got, oracle_msm(oracle, sc, pts)), name
 
 
-def test_msm_slotted_equals_two_pass_at_size(oracle, monkeypatch):
+def test_msm_slotted_equals_two_pass_at_size(oracle, slot_option):
     """2^18 points, both forced: the slotted and the two-pass front end give identical bytes, for
     252-bit random scalars and for an adversarial input that overflows the slots."""
     import torch
@@ -241,7 +251,7 @@ def test_msm_slotted_equals_two_pass_at_size(oracle, monkeypatch):
     adv[: n // 2] = adv[0]  # half of the scalars equal: 2^17 entries in one bucket per window
     out = {}
     for slots in ("1", "0"):
-        monkeypatch.setenv("CBP_MSM_SLOTS", slots)
+        slot_option(int(slots))
         msm = cbp.Msm(n)
         out[slots] = (msm(sc, pts).cpu().numpy().copy(), msm(adv, pts).cpu().numpy().copy())
         torch.cuda.synchronize()
@@ -290,3 +300,120 @@ def test_msm_running_sum_reduction_cross_check(oracle):
         oracle.ge25519_scalarmult_base(ob.ptr(want), (acc % L).to_bytes(32, "little"))
         oracle.ge25519_normalize(ob.ptr(want))
         assert np.array_equal(got.view(np.uint64), want)
+
+
+def test_msm_2_22_scalar_identity(oracle):
+    """BASELINE's largest sweep size (2^22 points): c = 16, window groups 8, 4, 4 (the n >= 2^21 pipeline), slotted
+    front end.  Checked against (sum s_i k_i mod l) * B — one CPU scalar multiplication."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    from tests.helpers import base_multiple, dot_mod_l
+    n = 1 << 22
+    pts, ks = cbp.synth_points(n, seed=0xC3 + 22)
+    sc = cbp.synth_scalars(n, seed=0x5CA1A000 + 22, bits=252)
+    msm = cbp.Msm(n)
+    assert msm.window_bits == 16
+    got = msm(sc, pts).cpu().numpy().view(np.uint64).copy()
+    torch.cuda.synchronize()
+    want = base_multiple(oracle, dot_mod_l(sc.cpu().numpy().view(np.uint64).reshape(n, 4), ks.cpu().numpy()))
+    assert np.array_equal(got, want)
+    assert np.array_equal(msm(sc, pts).cpu().numpy().view(np.uint64), want)  # and again (atomics reorder buckets)
+
+
+def _torsion_point():
+    """a point of order 8 (l * Q for the first curve point Q with a full torsion component), affine"""
+    y = 3
+    while True:
+        x = pyref.recover_x(y, 0)
+        if x is not None:
+            t = pyref.pt_mul(L, (x, y))
+            if pyref.pt_mul(4, t) != (0, 1):
+                return t
+        y += 1
+
+
+@pytest.mark.parametrize("log_n", [16, 18, 20])
+def test_msm_projective_and_torsion_inputs_at_size(oracle, log_n):
+    """Full-size inputs OUTSIDE the Z = 1 fast path of msm_precompute_kernel: every point re-randomised to a
+    pseudo-random Z (the Montgomery-trick branch), every 1000th point shifted by a point of order 8, scalars with
+    all 255 bits.  k = s mod p is used as an integer, never reduced mod l (cuda_bulletproof_kernels.cu:33-37), so
+    the expected value is (sum s_i k_i mod l) * B + (sum over shifted points of s_i mod 8) * T8."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    from tests.helpers import base_multiple, dot_mod_l
+    n, stride = 1 << log_n, 1000
+    pts, ks = cbp.synth_points(n, seed=0x7035 + log_n)
+    sc = cbp.synth_scalars(n, seed=0x7036 + log_n, bits=255)
+    t8 = _torsion_point()
+    d_t8 = torch.from_numpy(ob.affine_to_ge(*t8).view(np.uint8).copy()).cuda()
+    plain = cbp.Msm(n)(sc, pts).cpu().numpy().view(np.uint64).copy()
+    cbp.check(cbp.load().bpk_debug_projectivize_device(pts.data_ptr(), n, 0xABCD + log_n, d_t8.data_ptr(), stride, None),
+              "bpk_debug_projectivize_device")
+    got = cbp.Msm(n)(sc, pts).cpu().numpy().view(np.uint64).copy()
+    torch.cuda.synchronize()
+    sc_h = sc.cpu().numpy().view(np.uint64).reshape(n, 4)
+    assert (sc_h[:, 3] >> np.uint64(62)).max() > 0  # the top window is really populated
+    base = base_multiple(oracle, dot_mod_l(sc_h, ks.cpu().numpy()))
+    assert np.array_equal(plain, base)
+    m8 = int((sc_h[::stride, 0] & np.uint64(7)).sum()) % 8  # s < p for these inputs, so s mod p = s
+    want = pyref.pt_add(ob.ge_to_affine(base), pyref.pt_mul(m8, t8))
+    assert ob.ge_to_affine(got) == want
+    assert int(got[8]) == 1 and not got[9:12].any()  # normalised: Z = 1
+    # the host-pointer drop-in sees the same projective inputs
+    if log_n == 16:
+        h = cbp.cuda_point_vector_multi_scalar_mul(sc_h, pts.cpu().numpy().view(np.uint64).reshape(n, 16))
+        assert np.array_equal(h, got)
+
+
+def test_msm_concurrent_host_threads_and_streams(oracle):
+    """Four host threads, each with its own stream, inputs and workspace, call bpk_msm_device (2^16 points: the
+    window-group pipeline with its per-device side streams and events) while a fifth calls the host-pointer
+    drop-in.  The enqueue is serialised per device inside the library, so an event recorded by one call can never
+    pair with another call's wait: every result must be its own expected point, every time."""
+    import threading
+    import torch
+    import cudabulletproof_b200 as cbp
+    from tests.helpers import base_multiple, dot_mod_l
+    n, nthreads, reps = 1 << 16, 4, 12
+    jobs = []
+    for t in range(nthreads):
+        pts, ks = cbp.synth_points(n, seed=0x7E4D + t)
+        sc = cbp.synth_scalars(n, seed=0x7E5D + t, bits=253)
+        want = base_multiple(oracle, dot_mod_l(sc.cpu().numpy().view(np.uint64).reshape(n, 4), ks.cpu().numpy()))
+        jobs.append((pts, sc, want, cbp.Msm(n), torch.cuda.Stream()))
+    hn = 3000
+    h_pts_d, h_ks = cbp.synth_points(hn, seed=0x7E6D)
+    h_sc_d = cbp.synth_scalars(hn, seed=0x7E7D, bits=253)
+    h_pts = h_pts_d.cpu().numpy().view(np.uint64).reshape(hn, 16)
+    h_sc = h_sc_d.cpu().numpy().view(np.uint64).reshape(hn, 4)
+    h_want = base_multiple(oracle, dot_mod_l(h_sc, h_ks.cpu().numpy()))
+    torch.cuda.synchronize()
+    errors = []
+
+    def device_worker(t):
+        pts, sc, want, msm, stream = jobs[t]
+        try:
+            for _ in range(reps):
+                out = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                with torch.cuda.stream(stream):
+                    msm(sc, pts, out=out, stream=stream)
+                stream.synchronize()
+                if not np.array_equal(out.cpu().numpy().view(np.uint64), want):
+                    errors.append(("device", t))
+        except Exception as ex:  # noqa: BLE001
+            errors.append(("device", t, repr(ex)))
+
+    def host_worker():
+        try:
+            for _ in range(reps):
+                if not np.array_equal(cbp.cuda_point_vector_multi_scalar_mul(h_sc, h_pts), h_want):
+                    errors.append(("host",))
+        except Exception as ex:  # noqa: BLE001
+            errors.append(("host", repr(ex)))
+
+    threads = [threading.Thread(target=device_worker, args=(t,)) for t in range(nthreads)] + [threading.Thread(target=host_worker)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

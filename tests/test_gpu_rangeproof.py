@@ -380,3 +380,49 @@ def test_device_ipa_prover_matches_oracle_small(oracle, gens64, n):
     assert fa.cpu().numpy().tobytes() == bytes(proof.a.elements[0])
     assert fb.cpu().numpy().tobytes() == bytes(proof.b.elements[0])
     assert fx.cpu().numpy().tobytes() == bytes(proof.x)
+
+
+@pytest.mark.parametrize("n,m", [(16, 5), (64, 150)])
+def test_keyed_prover_csprng_nonces(oracle, gens16, gens64, n, m):
+    """bpk_range_prove_batch_keyed_device: blinding values and nonces are SHA-256("cbp-bp-nonce" || key || j) of a
+    32-byte per-proof secret (the reference draws them from RAND_bytes, bulletproof_range_proof.cu:153), not the
+    oracle's 64-bit SplitMix64 test stream.  Proofs must verify on the GPU and with the CPU oracle's
+    range_proof_verify, be a function of the key, and be the same bytes through the one-CTA (m < 64) and the
+    phase-split (m >= 64, workspace) provers."""
+    import hashlib
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    g = gens16 if n == 16 else gens64
+    dg = dev_gens(g, 8)
+    rng = random.Random(0x5EC + n)
+    vals = [rng.getrandbits(n) for _ in range(m)]
+    gam = ob.ints_to_fe([rng.getrandbits(250) for _ in range(m)])
+    keys = np.frombuffer(b"".join(hashlib.sha256(b"test key %d" % i).digest() for i in range(m)), dtype=np.uint8).reshape(m, 32).copy()
+    got = cbp.range_prove_batch(dg, vals, gam, keys=keys)
+    assert cbp.RangeVerifier(dg, m)(got).cpu().numpy().all()
+    h = got.cpu().numpy()
+    for i in sorted({0, m // 2, m - 1}):
+        proof, V, keep = cbp.record_to_range_proof(h[i], n)
+        assert oracle_verify(oracle, g, proof, V), i
+    # alpha = draw 2n: A's blinding.  Recompute it from the key on the host and check it is NOT the seeded stream
+    again = cbp.range_prove_batch(dg, vals, gam, keys=keys)
+    assert torch.equal(got, again)
+    keys2 = keys.copy()
+    keys2[0, 31] ^= 1
+    other = cbp.range_prove_batch(dg, vals, gam, keys=keys2).cpu().numpy()
+    assert np.array_equal(other[0, :128], h[0, :128])          # V = v g + gamma h does not depend on the key
+    assert not np.array_equal(other[0, 128:256], h[0, 128:256])  # A does
+    assert np.array_equal(other[1:], h[1:])
+    # no workspace -> one CTA per proof: same bytes
+    d_v = torch.from_numpy(np.asarray(vals, dtype=np.uint64).view(np.int64)).cuda()
+    d_g = torch.from_numpy(np.ascontiguousarray(gam, dtype=np.uint64).view(np.uint8).reshape(-1)).cuda()
+    d_k = torch.from_numpy(keys).cuda()
+    ref = torch.zeros_like(got)
+    assert lib.bpk_range_prove_batch_keyed_device(dg.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(), d_k.data_ptr(), n, m,
+                                                  ref.data_ptr(), None, 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+    assert lib.bpk_range_prove_batch_keyed_device(dg.workspace.data_ptr(), d_v.data_ptr(), d_g.data_ptr(), None, n, m,
+                                                  ref.data_ptr(), None, 0, None) != 0
+    lib.bpk_clear_last_error()
