@@ -31,8 +31,12 @@ sys.path.insert(0, ROOT)
 
 LOG_N_DEFAULT = 20
 VERIFY_PROOFS_DEFAULT = 1 << 14
-INT_PEAK_TIMAD = 9.0  # measured IMAD.WIDE.U32 issue rate on this pool's B200 (profiles/r01_microbench_int_pipe.jsonl)
-ACC_TRAFFIC_2_20 = 1.207e9  # DRAM bytes of the accumulation launches of one 2^20 MSM (ncu --set full, see traffic_note)
+INT_PEAK_PLANNING_TIMAD = 18.6  # SURVEY.md section 8d planning figure (148 SM x 4 x 16 lanes x 1.965 GHz, 32-bit IMAD)
+INT_PEAK_FALLBACK_TIMAD = 9.0   # round-1 measurement (profiles/r01_microbench_int_pipe.jsonl); used only if the in-run
+                                # microbenchmark fails, and then labelled "fallback"
+KERNEL_SOURCES = ("msm.cu", "ge25519.cuh", "fe25519.cuh", "rangeproof.cu", "rangeproof.cuh", "sc25519.cuh")
+P25519 = 2**255 - 19
+L25519 = 2**252 + 27742317777372353535851937790883648493
 
 
 def measured_peaks():
@@ -42,6 +46,96 @@ def measured_peaks():
         return float(d["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def measure_int_peak(lib, target_ms=20.0):
+    """The integer roofline denominator, measured in THIS run on this GPU (csrc/intpeak.cu): lane operations per
+    second of IMAD.WIDE.U32 carry chains (fe_mul's inner pattern), next to the other multiply flavours so that
+    the record shows why IMAD.WIDE is the right denominator here."""
+    rates = (C.c_double * 5)()
+    names = ["imad_wide_carry", "imad_wide_indep", "imad_lo", "imad_hi", "dfma_fp64"]
+    try:
+        rc = lib.bpk_measure_int_peak(target_ms, rates, 5)
+    except Exception:  # noqa: BLE001
+        rc = -1
+    if rc != 0 or not rates[0] > 0:
+        return {"T_per_s": INT_PEAK_FALLBACK_TIMAD, "source": "fallback (round-1 measurement)", "all": None}
+    allr = {n: rates[i] / 1e12 for i, n in enumerate(names)}
+    rec = {"T_per_s": allr["imad_wide_carry"], "all_T_per_s": allr, "target_ms_each": target_ms,
+           "source": "bpk_measure_int_peak in this run (IMAD.WIDE.U32.X carry chains, 8 CTAs x 256 threads per SM)"}
+    for d in (os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out")):
+        try:
+            if os.path.isdir(d):
+                with open(os.path.join(d, "INT_PEAK.json"), "w") as f:
+                    json.dump(dict(rec, when=time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())), f, indent=1)
+        except OSError:
+            pass
+    return rec
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources that define the profiled kernels: ties a committed ncu summary to the code it
+    was taken from (the GPU box has no .git, so a commit hash cannot be checked there)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "cudabulletproof_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_summary(kind):
+    """profiles/ncu_<kind>.json (written by tools/ncu_extract.py from a committed ncu raw CSV): DRAM traffic and
+    pipe utilisation of the dominant kernel.  Returned only when it was taken from the kernel sources this run was
+    built from; otherwise the caller prints null and says why."""
+    path = os.path.join(ROOT, "profiles", f"ncu_{kind}.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except (OSError, ValueError):
+        return None, f"no profiles/ncu_{kind}.json"
+    if d.get("source_hash") != kernel_source_hash():
+        return None, (f"profiles/ncu_{kind}.json was taken at source hash {d.get('source_hash')} (git {d.get('git')}), "
+                      f"this build is {kernel_source_hash()}: not reported")
+    return d, None
+
+
+def dot_mod_l(sc_h, ks_h):
+    """sum_i s_i k_i mod l, vectorised ((n,4) uint64 little-endian scalars, (n,) uint64 k): 32x32-bit partial products
+    are exact in uint64, their halves are summed separately so nothing overflows"""
+    import numpy as np
+    s32 = np.ascontiguousarray(sc_h, dtype=np.uint64).view(np.uint32).reshape(-1, 8).astype(np.uint64)
+    k32 = np.ascontiguousarray(ks_h, dtype=np.uint64).view(np.uint32).reshape(-1, 2).astype(np.uint64)
+    mask, total = np.uint64(0xFFFFFFFF), 0
+    for a in range(8):
+        for b in range(2):
+            prod = s32[:, a] * k32[:, b]
+            total += (int((prod & mask).sum(dtype=np.uint64)) + (int((prod >> np.uint64(32)).sum(dtype=np.uint64)) << 32)) << (32 * (a + b))
+    return total % L25519
+
+
+def base_multiple_xy_hex(k):
+    """hex of the 64 bytes x || y (little-endian) of k*B on Ed25519, in plain Python integers (independent of the
+    library and of oracle/): the check value for an MSM over points P_i = k_i B"""
+    d = -121665 * pow(121666, P25519 - 2, P25519) % P25519
+
+    def add(p, q):
+        (x1, y1), (x2, y2) = p, q
+        t = d * x1 * x2 * y1 * y2 % P25519
+        x3 = (x1 * y2 + x2 * y1) * pow(1 + t, P25519 - 2, P25519) % P25519
+        y3 = (y1 * y2 + x1 * x2) * pow(1 - t, P25519 - 2, P25519) % P25519
+        return x3, y3
+
+    by = 4 * pow(5, P25519 - 2, P25519) % P25519
+    bx = 0x216936d3cd6e53fec0a4e231fdd6dc5c692cc7609525a7b2c9562d608f25d51a
+    acc, cur = (0, 1), (bx, by)
+    k %= L25519
+    while k:
+        if k & 1:
+            acc = add(acc, cur)
+        cur = add(cur, cur)
+        k >>= 1
+    return (acc[0].to_bytes(32, "little") + acc[1].to_bytes(32, "little")).hex()
 
 
 class ClockSampler:
@@ -250,7 +344,8 @@ def run_cuda(args):
         return ms.value, cnt.value
 
     hbm_peak, peak_src = measured_peaks()
-    out = {}
+    int_peak = measure_int_peak(lib)  # ~0.1 s, before any timed region
+    INT_PEAK_TIMAD = int_peak["T_per_s"]
 
     # ---------------- MSM ----------------
     def bench_msm():
@@ -290,17 +385,23 @@ def run_cuda(args):
         result_hex = bytes(res.cpu().numpy().tobytes()[:64]).hex()
         W = (256 + msm.window_bits - 1) // msm.window_bits
         imad_acc = n * W * 504.0  # 7 fe_mul x 72 IMAD per mixed addition, N*W additions
-        roofline = {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": imad_acc / (acc_ms * 1e-3) / 1e12,
-                    "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": imad_acc / (acc_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
-                    "traffic": ACC_TRAFFIC_2_20 if args.log_n == 20 else None,
-                    "traffic_note": "dram__bytes_read+write summed over the window-group launches (8, 4, 2, 2 windows) "
-                                    "of one 2^20 MSM, ncu --set full (profiles/r01_final3_acc_ncu_raw.csv); algorithmic "
-                                    "gather bytes N*W*100 = 1.68e9, the rest is L2 hits",
+        ncu_acc, ncu_why = ncu_summary(f"msm_accumulate_2_{args.log_n}")
+        achieved = imad_acc / (acc_ms * 1e-3) / 1e12
+        roofline = {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": achieved,
+                    "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": achieved / INT_PEAK_TIMAD,
+                    "peak_source": int_peak["source"], "peak_all_T_per_s": int_peak.get("all_T_per_s"),
+                    "frac_of_planning_peak": achieved / INT_PEAK_PLANNING_TIMAD,
+                    "planning_peak_note": f"{INT_PEAK_PLANNING_TIMAD} T/s = SURVEY.md section 8d's 32-bit IMAD figure; the "
+                                          "32x32->64 IMAD.WIDE this path needs issues at half that rate (measured above)",
+                    "traffic": ncu_acc["dram_bytes"] if ncu_acc else None,
+                    "traffic_note": (ncu_acc["note"] if ncu_acc else ncu_why),
+                    "ncu": ({k: ncu_acc[k] for k in ("file", "git", "source_hash", "launches", "fmaheavy_pct_per_launch",
+                                                       "duration_us_per_launch") if k in ncu_acc} if ncu_acc else None),
+                    "algorithmic_gather_bytes": n * W * 100.0,
                     "launch_ms": acc_ms, "launches_timed": acc_n,
-                    "launch_note": "span of the window-group launches (8, 4, 2, 2 windows at 2^20) per MSM",
-                    "ncu": {"sm__pipe_fmaheavy_cycles_active_pct": 84.2, "stall_top": "math_pipe_throttle"},
-                    "peak_source": "measured IMAD.WIDE.U32 issue rate (profiles/r01_microbench_int_pipe.jsonl)",
-                    "algorithmic_imad_per_launch": imad_acc}
+                    "launch_note": "span of the window-group accumulation launches per MSM (CUDA events on the launching stream)",
+                    "algorithmic_imad_per_launch": imad_acc,
+                    "whole_call_frac": imad_acc / (ms / args.steps * 1e-3) / 1e12 / INT_PEAK_TIMAD}
         roofline_hbm = {"bound": "hbm", "kernel": "msm_precompute_kernel", "achieved": n * 224.0 / (pre_ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": n * 224.0 / (pre_ms * 1e-3) / 1e9 / hbm_peak,
                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "launch_ms": pre_ms}
@@ -323,13 +424,82 @@ def run_cuda(args):
         torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e_hex = h_out.tobytes()[:64].hex()
+        # the same call from PAGEABLE buffers (plain malloc, what the reference's own callers hand over:
+        # bulletproof_vectors.cu:18,136), then with the library's opt-in registration cache
+        pageable = {}
+        if world == 1:
+            p_sc, p_pts = np.empty((n, 32), dtype=np.uint8), np.empty((n, 128), dtype=np.uint8)
+            p_sc[:] = h_sc.numpy()
+            p_pts[:] = h_pts.numpy()
+            fvp, pvp = cbp.FieldVector(p_sc.ctypes.data, n), cbp.PointVector(p_pts.ctypes.data, n)
+            for label, reg in (("malloc", 0), ("malloc_registered_once", 1)):
+                lib.bpk_debug_set_option(6, reg)  # BPK_OPT_HOST_REGISTER
+                h_out[:] = 0
+                for _ in range(2):
+                    lib.cuda_point_vector_multi_scalar_mul(h_out.ctypes.data_as(C.c_void_p), C.byref(fvp), C.byref(pvp))
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    lib.cuda_point_vector_multi_scalar_mul(h_out.ctypes.data_as(C.c_void_p), C.byref(fvp), C.byref(pvp))
+                torch.cuda.synchronize()
+                pms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+                pageable[label] = {"ms_per_step": pms, "value": n / (pms * 1e-3), "unit": "points/s",
+                                   "result_matches_device_path": h_out.tobytes()[:64].hex() == result_hex}
+            lib.bpk_debug_set_option(6, 0)
+            lib.bpk_host_release()
         return {"ms": ms, "n": n, "clocks": clocks, "launches": int(launches), "roofline": roofline,
                 "roofline_hbm": roofline_hbm, "window_bits": msm.window_bits, "phases": phases,
                 "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "points/s",
                         "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": 128,
                         "api": "cuda_point_vector_multi_scalar_mul (host pointers, pinned)", "ms_per_step": e2e_ms / e2e_steps,
-                        "result_matches_device_path": (e2e_hex == result_hex) if world == 1 else None},
+                        "result_matches_device_path": (e2e_hex == result_hex) if world == 1 else None,
+                        "pageable": pageable or None},
                 "result_xy": result_hex}
+
+    # ---------------- strong scaling: ONE global MSM cut into point-range shards ------
+    def bench_strong(log_n):
+        """The same 2^log_n global inputs for every world size; rank r owns shard_range(n, r, world); the partial points
+        meet through an all_gather of 128 B + the point-sum kernel.  result_xy must be identical for N = 1, 2, 4, 8 and
+        equal (sum s_i k_i mod l) B, checked in plain Python outside the timed region."""
+        from cudabulletproof_b200.multi import all_gather_bytes, shard_range
+        from cudabulletproof_b200.host import Msm, point_sum
+        n = 1 << log_n
+        pts, ks = cbp.synth_points(n, seed=0x57A0 + log_n, device=dev)  # every rank derives the same global arrays
+        sc = cbp.synth_scalars(n, seed=0x57B0 + log_n, bits=252, device=dev)
+        lo, hi = shard_range(n, rank, world)
+        my_pts, my_sc = pts[lo:hi].contiguous(), sc[lo:hi].contiguous()
+        msm = Msm(hi - lo, device=dev)
+        partial = torch.zeros(128, dtype=torch.uint8, device=dev)
+        gathered = torch.zeros((world, 128), dtype=torch.uint8, device=dev)
+
+        def step():
+            if world == 1:
+                return msm(my_sc, my_pts, normalize=True)
+            msm(my_sc, my_pts, normalize=False, out=partial)
+            all_gather_bytes(partial, world, out=gathered)
+            return point_sum(gathered, normalize=True)
+
+        for _ in range(max(3, args.warmup)):
+            res = step()
+        barrier()
+        ssteps = max(5, min(args.steps, 20))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(ssteps):
+            res = step()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / ssteps
+        got = bytes(res.cpu().numpy().tobytes()[:64]).hex()
+        row = {"log2_n": log_n, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
+               "shard_points": hi - lo, "window_bits": msm.window_bits, "result_xy": got}
+        if rank == 0:
+            want = base_multiple_xy_hex(dot_mod_l(sc.cpu().numpy().view(np.uint64).reshape(n, 4),
+                                                  ks.cpu().numpy().astype(np.uint64)))
+            row["result_check"] = got == want
+            row["check"] = "(sum s_i k_i mod l) * B in plain Python integers, outside the timed region"
+        del pts, sc, ks, my_pts, my_sc, msm
+        torch.cuda.empty_cache()
+        return row
 
     # ---------------- range-proof batch verification ----------------
     def bench_verify():
@@ -397,11 +567,12 @@ def run_cuda(args):
         imad_proof = (131 * nwin * 504 + 17 * 51 * 576 + 2 * (255 * 464 + 51 * 648)) * 1.0
         imad_kernel = 131 * nwin * 504 + 2 * (nwin.bit_length() - 1) * nwin * 648.0
         per_launch = imad_kernel * (m / chunks)
+        ncu_v, ncu_v_why = ncu_summary(f"verify_fixed_{args.fixed_window_bits}_{m}")
         roofline = {"bound": "int", "kernel": "verify_fixed_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": per_launch / (k_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
-                    "traffic": 6.26e9 if (args.fixed_window_bits == 16 and m == 16384) else None,
-                    "traffic_note": "dram__bytes_read.sum of one 16384-proof launch, profiles/r01_verify16_ncu_raw.csv; "
-                                    "algorithmic table bytes 3.3e9 (96 B per addition, fetched as two 64 B DRAM atoms)",
+                    "traffic": ncu_v["dram_bytes"] if ncu_v else None,
+                    "traffic_note": ncu_v["note"] if ncu_v else ncu_v_why,
+                    "peak_source": int_peak["source"],
                     "launch_ms": k_ms, "launches_timed": k_n,
                     "algorithmic_imad_per_launch": per_launch, "algorithmic_imad_per_proof_total": imad_proof,
                     "whole_batch_frac": imad_proof * m / (ms / vsteps * 1e-3) / 1e12 / INT_PEAK_TIMAD}
@@ -524,6 +695,9 @@ def run_cuda(args):
                         f"HBM peak {hbm_peak:.0f} GB/s ({peak_src}), integer peak {INT_PEAK_TIMAD} T IMAD.WIDE/s", "rows": rows}
 
     msm_res = bench_msm() if args.workload in ("msm", "both") else None
+    strong = None
+    if args.workload in ("msm", "both") and not args.no_strong:
+        strong = [bench_strong(lg) for lg in args.strong_log_n]
     ver_res = bench_verify() if args.workload in ("verify", "both") else None
     other = None
     if rank == 0 and world == 1 and args.workload == "both":
@@ -558,6 +732,13 @@ def run_cuda(args):
                     "roofline": msm_res["roofline"], "roofline_hbm": msm_res["roofline_hbm"], "phases": msm_res["phases"],
                     "cpu_baseline": cpu,
                     "result_xy": msm_res["result_xy"]}
+            if strong is not None:
+                line["secondary_scaling"] = {
+                    "scaling": "strong", "rows": strong,
+                    "note": "ONE global MSM per row, the same inputs for every N, cut into contiguous point-range "
+                            "shards (rank r owns [r n/N, (r+1) n/N)); result_xy is the same string for every N and "
+                            "equals the scalar identity (result_check).  Strong-scaling efficiency = "
+                            "value(N) / (N * value(1)) over the driver's N = 1, 2, 4, 8 runs."}
             if ver_res is not None:
                 line["secondary"] = ver_res
             if other is not None:
@@ -588,6 +769,9 @@ def main():
                     help="window width of the generator tables (8: 51 MB in L2; 16: 6.5 GB in HBM, half the additions)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="points per host thread for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling rows (secondary_scaling)")
+    ap.add_argument("--strong-log-n", type=int, nargs="*", default=[20, 22],
+                    help="global sizes of the strong-scaling MSMs (one MSM cut into N point-range shards)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -56,6 +56,7 @@ SIGNATURES = {
     "bpk_clear_last_error": (_i, []),
     "bpk_kernel_launches": (_u64, []),
     "bpk_debug_set_option": (_i, [_i, C.c_longlong]),
+    "bpk_host_release": (_i, []),
     "bpk_profile_enable": (_i, [_i]),
     "bpk_profile_reset": (_i, []),
     "bpk_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(_i)]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "bpk_gens_derive_device": (_i, [_vp, C.c_char_p, C.c_uint32, _sz, _vp]),
     "bpk_debug_ge_op_device": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bpk_debug_const_operands_device": (_i, [_vp, _vp]),
+    "bpk_debug_fe8_op_device": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bpk_debug_projectivize_device": (_i, [_vp, _sz, _u64, _vp, C.c_uint32, _vp]),
     "bpk_ipa_prove_workspace_bytes": (_i, [_sz, C.POINTER(_sz)]),
     "bpk_ipa_prove_device": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, C.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

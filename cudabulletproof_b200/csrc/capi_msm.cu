@@ -40,6 +40,7 @@ Options& options() {
         opt.host_chunk_log2 = num("CBP_HOST_CHUNK_LOG2", 0);
         opt.prover_legacy = getenv("CBP_PROVER_LEGACY") ? 1 : 0;
         opt.msm_small_max = num("CBP_MSM_SMALL_MAX", -1);
+        opt.host_register = num("CBP_HOST_REGISTER", 0);
         if (const char* g = getenv("CBP_GROUPS")) {
             while (*g && opt.ngroups < 8) {
                 int v = atoi(g);
@@ -171,6 +172,7 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_HOST_CHUNK_LOG2: o.host_chunk_log2 = (int)value; break;
         case BPK_OPT_PROVER_LEGACY: o.prover_legacy = value != 0; break;
         case BPK_OPT_MSM_SMALL_MAX: o.msm_small_max = (int)value; break;
+        case BPK_OPT_HOST_REGISTER: o.host_register = value != 0; break;
         case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic
             o.ngroups = 0;
             for (int sh = 28; sh >= 0; sh -= 4) {
@@ -267,6 +269,30 @@ struct HostPath {
     bool ok = false;
 };
 HostPath g_hp[kMaxDevices];  // one per device, used under that device's lock
+// Opt-in registration cache (BPK_OPT_HOST_REGISTER / CBP_HOST_REGISTER=1).  The reference's callers hand over
+// plain malloc memory (bulletproof_vectors.cu:18,136); a copy from pageable memory is staged by the driver at a
+// fraction of the PCIe rate.  With the option on, a pageable buffer of 1 MiB or more is page-locked in place the
+// first time it is seen and remembered by address range, so that later calls with the same buffer copy at the
+// pinned rate.  The caller must keep such a buffer allocated until bpk_host_release() (or process exit): that
+// contract is why this is not the default.
+struct Registered {
+    const uint8_t* base;
+    size_t bytes;
+};
+std::mutex g_reg_mu;
+std::vector<Registered> g_registered;
+void maybe_register(const void* ptr, size_t bytes) {
+    if (!options().host_register || !ptr || bytes < ((size_t)1 << 20)) return;
+    const uint8_t* p = (const uint8_t*)ptr;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (const Registered& r : g_registered)
+        if (p >= r.base && p + bytes <= r.base + r.bytes) return;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) return;  // pinned already
+    (void)cudaGetLastError();
+    if (cudaHostRegister((void*)ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) g_registered.push_back({p, bytes});
+    else (void)cudaGetLastError();  // not fatal: the copy falls back to the driver's staging
+}
 cudaError_t grow(uint8_t** p, size_t* cap, size_t need) {
     if (need <= *cap) return cudaSuccess;
     if (*p) cudaFree(*p);
@@ -299,6 +325,8 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
     int launches = 0;
     const uint8_t* h_s = (const uint8_t*)scalars->elements;
     const uint8_t* h_p = (const uint8_t*)points->elements;
+    maybe_register(h_s, n * 32);
+    maybe_register(h_p, n * 128);
     if (n < kHostChunkMin) {
         // one MSM; the scalars go first so that digit recoding / sorting overlaps the (4x larger) point upload
         MsmPlan p;
@@ -359,6 +387,14 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
     if (e == cudaSuccess) e = cudaStreamSynchronize(hp.main);
     if (e != cudaSuccess) return fail(BPK_ERR_CUDA, e);
     *result = tmp;
+    return BPK_OK;
+}
+
+int bpk_host_release(void) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (const Registered& r : g_registered) cudaHostUnregister((void*)r.base);
+    g_registered.clear();
+    (void)cudaGetLastError();
     return BPK_OK;
 }
 

@@ -9,7 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
-#include "ge25519.cuh"
+#include "fe8.cuh"
 using namespace cbp;
 
 #define ITERS 4096
@@ -132,6 +132,36 @@ __global__ void __launch_bounds__(32) k_lat_inv(uint32_t* out, uint32_t seed) {
     out[blockIdx.x * 32 + threadIdx.x] = r.v[0];
 }
 
+// the same chains in octet form (fe8.cuh: one word per lane, the warp shares every point operation)
+__global__ void __launch_bounds__(32) k_lat8(uint32_t* out, uint32_t seed, int what) {
+    const Fe8Lane L = fe8_lane();
+    ge8 p, q;
+    ge8_identity(p, L);
+    ge8_identity(q, L);
+    p.X = seed + L.j;
+    p.Y = seed * 9 + L.j + blockIdx.x;
+    q.X = seed * 3 + L.j;
+    q.T = seed * 5 + blockIdx.x;
+    ge8_cached c;
+    ge8_to_cached(c, q, L);
+    uint32_t z = p.X;
+    if (what == 3) {
+        z = fe8_invert(p.Y, L);
+    } else if (what == 4) {
+        uint32_t y = p.Y;
+        for (int it = 0; it < 256; it++) z = fe8_mul(z, y, L);
+    } else if (what == 5) {
+        for (int it = 0; it < 256; it++) z = fe8_sub(z, p.Y, L);
+    } else {
+        for (int it = 0; it < 256; it++) {
+            if (what == 0) ge8_dbl(p, p, L);
+            else if (what == 1) ge8_add(p, p, q, L);
+            else ge8_add_cached(p, p, c, L);
+        }
+    }
+    out[blockIdx.x * 32 + threadIdx.x] = p.X ^ p.T ^ p.Y ^ p.Z ^ z;
+}
+
 template <typename F>
 static double time_ms(F launch, int reps) {
     cudaEvent_t e0, e1;
@@ -190,6 +220,15 @@ int main() {
         printf("{\"bench\": \"latency_ge_add%s\", \"us_per_op\": %.3f}\n", quad ? "_quad" : "", ms * 1e3 / 256);
         ms = time_ms([&] { k_lat_dbl<<<sms, 32>>>((uint32_t*)buf, 99, quad); }, 5);
         printf("{\"bench\": \"latency_ge_dbl%s\", \"us_per_op\": %.3f}\n", quad ? "_quad" : "", ms * 1e3 / 256);
+    }
+    {
+        const char* names[6] = {"latency_ge8_dbl", "latency_ge8_add", "latency_ge8_add_cached", "latency_fe8_invert",
+                                "latency_fe8_mul", "latency_fe8_sub"};
+        for (int what = 0; what < 6; what++) {
+            double ms = time_ms([&] { k_lat8<<<sms, 32>>>((uint32_t*)buf, 99, what); }, 5);
+            if (what != 3) printf("{\"bench\": \"%s\", \"us_per_op\": %.3f}\n", names[what], ms * 1e3 / 256);
+            else printf("{\"bench\": \"%s\", \"us\": %.3f}\n", names[what], ms * 1e3);
+        }
     }
     {
         double ms = time_ms([&] { k_lat_inv<<<sms, 32>>>((uint32_t*)buf, 99); }, 5);

@@ -26,7 +26,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include "ge25519.cuh"
+#include "fe8.cuh"
 #include "msm.h"
 #include "common.h"
 
@@ -835,25 +835,26 @@ __global__ void __launch_bounds__(128) msm_reduce2d_bits_kernel(const uint8_t* _
     block_quad_point_sum<4>(acc, col ? cols : rows, 0u, 1u, col ? Lo : H, mask, sh);
     if (threadIdx.x == 0) ge_store(Q + ((size_t)w * 32 + role) * 128, acc);
 }
-// one warp per window: Horner over the bit positions on a quad, acc = 2 acc + Q_p, finally + T
+// one warp per window: Horner over the bit positions, acc = 2 acc + Q_p, finally + T — a dependent chain, run in
+// octet form (fe8.cuh: the warp shares every point operation; 0.48 / 0.62 us per doubling / addition against
+// 0.72 / 0.99 us with one lane per product)
 __global__ void __launch_bounds__(32) msm_reduce2d_horner_kernel(const uint8_t* __restrict__ Q, int nb,
                                                                  uint8_t* __restrict__ winX,
                                                                  uint8_t* __restrict__ winY) {
+    const Fe8Lane L = fe8_lane();
     const uint32_t w = blockIdx.x;
     const uint8_t* q = Q + (size_t)w * 32 * 128;
-    ge_p3 acc, x;
-    ge_load(acc, q + (size_t)(nb - 1) * 128);
+    ge8 acc, x;
+    ge8_load(acc, q + (size_t)(nb - 1) * 128, L);
 #pragma unroll 1
     for (int pbit = nb - 2; pbit >= -1; pbit--) {
-        if (pbit >= 0) ge_dbl_quad(acc, acc);
-        ge_load(x, q + (size_t)(pbit >= 0 ? pbit : nb) * 128);
-        ge_add_quad(acc, acc, x);
+        if (pbit >= 0) ge8_dbl(acc, acc, L);
+        ge8_load(x, q + (size_t)(pbit >= 0 ? pbit : nb) * 128, L);
+        ge8_add(acc, acc, x, L);
     }
-    if (threadIdx.x == 0) {
-        ge_store(winX + (size_t)w * 128, acc);
-        ge_p3_0(x);
-        ge_store(winY + (size_t)w * 128, x);
-    }
+    ge8_store(winX + (size_t)w * 128, acc, L);
+    ge8_identity(x, L);  // winY: unused by the window combine after a 2-D reduction, kept defined
+    ge8_store(winY + (size_t)w * 128, x, L);
 }
 
 // ---- 7. window combine + normalise --------------------------------------------------------------
@@ -863,26 +864,126 @@ __global__ void __launch_bounds__(32) msm_reduce2d_horner_kernel(const uint8_t* 
 // The doublings after the last window of a call do not depend on the next group's sums.
 __global__ void __launch_bounds__(32) msm_horner_kernel(const uint8_t* __restrict__ X, const uint8_t* __restrict__ Y,
                                                         int w_hi, int w_lo, int c, int first, int normalize,
-                                                        uint8_t* __restrict__ state, uint8_t* __restrict__ result) {
-    // one warp; every lane holds the chain value, quads of lanes share each point operation
-    ge_p3 acc;
-    if (first) ge_p3_0(acc);
-    else ge_load(acc, state);
+                                                        int has_y, uint8_t* __restrict__ state,
+                                                        uint8_t* __restrict__ result) {
+    // one warp, octet form (fe8.cuh): the whole warp shares every operation of the chain
+    const Fe8Lane L = fe8_lane();
+    ge8 acc;
+    if (first) ge8_identity(acc, L);
+    else ge8_load(acc, state, L);
+#pragma unroll 1
     for (int w = w_hi; w >= w_lo; w--) {
-        ge_p3 x, y;
-        ge_load(x, X + (size_t)w * 128);
-        ge_load(y, Y + (size_t)w * 128);
-        ge_add_quad(x, x, y);
-        ge_add_quad(acc, acc, x);
-        if (w > 0)
-            for (int s = 0; s < c; s++) ge_dbl_quad(acc, acc);
+        ge8 x, y;
+        ge8_load(x, X + (size_t)w * 128, L);
+        if (has_y) {  // the running-sum reduction leaves two points per window, the 2-D one a single point
+            ge8_load(y, Y + (size_t)w * 128, L);
+            ge8_add(x, x, y, L);
+        }
+        ge8_add(acc, acc, x, L);
+        if (w > 0) {
+#pragma unroll 1
+            for (int s = 0; s < c; s++) ge8_dbl(acc, acc, L);
+        }
     }
-    if (threadIdx.x != 0) return;
     if (w_lo == 0) {
-        if (normalize) ge_normalize(acc);
-        ge_store(result, acc);
+        if (normalize) ge8_store_normalized(result, acc, L);
+        else ge8_store(result, acc, L);
     } else {
-        ge_store(state, acc);
+        ge8_store(state, acc, L);
+    }
+}
+
+// ---- 8. small n: Straus, three launches, no sort ------------------------------------------------------------
+// The reference's production calls into this library are MSMs of 16 / 64 points (bulletproof_range_proof.cu:724,728)
+// and it ships a dedicated n <= 64 kernel for them (cuda_bulletproof_kernels.cu:119-207: one thread per pair runs a
+// 256-step double-and-add, then a tree).  A Pippenger call costs ~0.5 ms whatever n is (~20 dependent launches and a
+// 2^14-bucket reduction per window), so up to kStrausMax points take this path instead:
+//   straus_prepare   thread per point: k = s mod p -> 64 signed 4-bit digits in [-7, 8]; multiples 1P .. 8P
+//   straus_sums      CTA per window w: S_w = sum_i sign(d_iw) T_i[|d_iw|], lane-strided sums + shuffle / shared tree
+//   straus_combine   one CTA: sum_w 16^w S_w as a binary tree over the windows (pairs: 4 doublings + 1 addition, then
+//                    8, 16, ... 128 doublings), every step a warp in octet form (fe8.cuh): 252 doublings + 6 additions
+//                    deep instead of the 252 + 63 of a plain Horner chain
+// Exact for every curve point (unified additions, all 255 scalar bits), like the Pippenger path.
+static constexpr int kStrausWindows = 64, kStrausTable = 8;
+static constexpr size_t kStrausMaxDefault = 1024;
+__global__ void __launch_bounds__(128) straus_prepare_kernel(const uint8_t* __restrict__ scalars,
+                                                             const uint8_t* __restrict__ points, uint32_t n,
+                                                             uint8_t* __restrict__ tables, int8_t* __restrict__ digits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[8];
+    load_scalar_canon(k, scalars + (size_t)i * 32);
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int w = 0; w < kStrausWindows; w++) {
+        int d = (int)((k[w >> 3] >> ((w & 7) * 4)) & 15u) + (int)carry;
+        carry = d > 8;
+        if (d > 8) d -= 16;
+        digits[(size_t)w * n + i] = (int8_t)d;  // k < 2^255: the top digit is at most 7 + 1, no carry out
+    }
+    ge_p3 P, M[kStrausTable];
+    ge_load(P, points + (size_t)i * 128);
+    M[0] = P;
+    ge_dbl(M[1], P);
+    ge_add(M[2], M[1], P);
+    ge_dbl(M[3], M[1]);
+    ge_add(M[4], M[3], P);
+    ge_dbl(M[5], M[2]);
+    ge_add(M[6], M[5], P);
+    ge_dbl(M[7], M[3]);
+#pragma unroll
+    for (int m = 0; m < kStrausTable; m++) ge_store(tables + ((size_t)i * kStrausTable + m) * 128, M[m]);
+}
+__global__ void __launch_bounds__(256) straus_sums_kernel(const uint8_t* __restrict__ tables,
+                                                          const int8_t* __restrict__ digits, uint32_t n,
+                                                          uint8_t* __restrict__ sums) {
+    __shared__ __align__(16) uint8_t sh[8][128];
+    const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    ge_p3 acc;
+    ge_p3_0(acc);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int d = digits[(size_t)w * n + i];
+        if (d == 0) continue;
+        ge_p3 t;
+        ge_load(t, tables + ((size_t)i * kStrausTable + (uint32_t)((d < 0 ? -d : d) - 1)) * 128);
+        if (d < 0) ge_neg(t, t);
+        ge_add(acc, acc, t);
+    }
+    ge_warp_sum(acc);
+    if (nwarps > 1) {
+        if (lane == 0) ge_store(sh[warp], acc);
+        __syncthreads();
+        if (warp != 0) return;
+        if (lane < nwarps) ge_load(acc, sh[lane]);
+        else ge_p3_0(acc);
+        ge_warp_sum(acc);  // nwarps <= 8: three of the five levels add identities
+    }
+    if (threadIdx.x == 0) ge_store(sums + (size_t)w * 128, acc);
+}
+__global__ void __launch_bounds__(1024) straus_combine_kernel(const uint8_t* __restrict__ sums, int normalize,
+                                                              uint8_t* __restrict__ result) {
+    __shared__ __align__(16) uint8_t sh[2][32][128];
+    const Fe8Lane L = fe8_lane();
+    const uint32_t warp = threadIdx.x >> 5;
+    int pp = 0, shift = 4;
+    for (uint32_t live = kStrausWindows / 2; live >= 1; live >>= 1, shift <<= 1, pp ^= 1) {
+        if (warp < live) {  // warp-uniform
+            const uint8_t* src = live == kStrausWindows / 2 ? sums : &sh[pp ^ 1][0][0];
+            ge8 lo, hi;
+            ge8_load(lo, src + (size_t)(2 * warp) * 128, L);
+            ge8_load(hi, src + (size_t)(2 * warp + 1) * 128, L);
+#pragma unroll 1
+            for (int s = 0; s < shift; s++) ge8_dbl(hi, hi, L);
+            ge8_add(hi, hi, lo, L);
+            if (live > 1) {
+                ge8_store(&sh[pp][warp][0], hi, L);
+            } else if (normalize) {
+                ge8_store_normalized(result, hi, L);
+            } else {
+                ge8_store(result, hi, L);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -971,6 +1072,12 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->off_winX = take((size_t)p->W * 128);
     p->off_winY = take((size_t)p->W * 128);
     p->off_state = take(128);
+    // the small-n (Straus) path: tables of 8 multiples per point, 64 digits per point, 64 window sums
+    const int smax = options().msm_small_max;
+    p->small = c <= 0 && n >= 1 && n <= (smax >= 0 ? (size_t)smax : kStrausMaxDefault);
+    p->off_stables = take(p->small ? n * kStrausTable * 128 : 0);
+    p->off_sdigits = take(p->small ? n * kStrausWindows : 0);
+    p->off_ssums = take(p->small ? (size_t)kStrausWindows * 128 : 0);
     p->workspace_bytes = off;
 }
 
@@ -1106,6 +1213,25 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
+    if (p.small && flags == 0) {
+        cudaError_t e;
+        if (points_ready && (e = cudaStreamWaitEvent(st, points_ready, 0)) != cudaSuccess) return (int)e;
+        uint8_t* tables = ws + p.off_stables;
+        int8_t* digits = (int8_t*)(ws + p.off_sdigits);
+        uint8_t* sums = ws + p.off_ssums;
+        prof_begin(BPK_PROF_MSM_TOTAL, st);
+        straus_prepare_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint8_t*)d_scalars, (const uint8_t*)d_points,
+                                                                          (uint32_t)n, tables, digits);
+        CBP_LAUNCH_CHECK(); nl++;
+        const unsigned sthreads = n <= 256 ? 32u : (n <= 512 ? 64u : (n <= 1024 ? 128u : 256u));
+        straus_sums_kernel<<<kStrausWindows, sthreads, 0, st>>>(tables, digits, (uint32_t)n, sums);
+        CBP_LAUNCH_CHECK(); nl++;
+        straus_combine_kernel<<<1, 1024, 0, st>>>(sums, normalize, (uint8_t*)d_result);
+        CBP_LAUNCH_CHECK(); nl++;
+        prof_end(BPK_PROF_MSM_TOTAL, st);
+        if (launches) *launches = nl;
+        return 0;
+    }
     // bucket offsets, cursors and entry indices are 32-bit (index << 1 | sign; prefix sums over n * W entries)
     if (n >= ((size_t)1 << 31) || n * (size_t)p.W >= ((size_t)1 << 32)) return (int)cudaErrorInvalidValue;
     const int carry = (flags & kMsmCarryIn) ? 1 : 0;
@@ -1222,6 +1348,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         const uint8_t* Y = X;
         uint32_t n_in = p.B, in_stride = p.B;
         int has_y = 0, pp = 0, level = 0;
+        bool two_d = false;
         // The shallow 2-D reduction (6c), for every group: the reductions of the overlapped groups are not
         // exposed themselves, but the Horner chain runs through them in order, and a group's ~110-operation
         // running-sum levels, starved of SM slots by the next accumulation, delayed the chain to the end
@@ -1246,6 +1373,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
                                                               winY + (size_t)w_lo * 128);
             CBP_LAUNCH_CHECK(); nl++;
             n_in = 1;
+            two_d = true;
         }
         while (n_in > 1) {
             bool seq = level == 0;  // level 0 is work-efficient (thread-sequential), upper levels warp-cooperative
@@ -1297,8 +1425,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
             if ((e = cudaEventRecord(kit->ev_red[g], tail)) != cudaSuccess) return (int)e;
             if ((e = cudaStreamWaitEvent(hs, kit->ev_red[g], 0)) != cudaSuccess) return (int)e;
         }
-        msm_horner_kernel<<<1, 32, 0, hs>>>(winX, winY, gm.w_hi[g], gm.w_lo[g], p.c, g == 0, normalize, state,
-                                            (uint8_t*)d_result);
+        msm_horner_kernel<<<1, 32, 0, hs>>>(winX, winY, gm.w_hi[g], gm.w_lo[g], p.c, g == 0, normalize, two_d ? 0 : 1,
+                                            state, (uint8_t*)d_result);
         CBP_LAUNCH_CHECK(); nl++;
     }
     if (kit) {

@@ -20,6 +20,9 @@ struct MsmPlan {
         off_entries, off_toprank, off_buckets, off_segsums;
     size_t off_redX[2], off_redY[2], off_winX, off_winY, off_state;
     size_t workspace_bytes;
+    // n <= the small-n threshold and no explicit window width: Straus in three launches (msm.cu, section 8)
+    bool small;
+    size_t off_stables, off_sdigits, off_ssums;
 };
 
 int msm_pick_window(size_t n);

@@ -146,9 +146,10 @@ class Msm:
         import torch
         self.n, self.device = int(n), torch.device(device)
         lib = _lib()
+        self._window_arg = int(window_bits)  # 0 = automatic: lets the library pick the small-n path as well
         self.window_bits = window_bits or lib.bpk_msm_window_bits(self.n)
         nbytes = C.c_size_t(0)
-        _check(lib.bpk_msm_workspace_bytes(self.n, self.window_bits, C.byref(nbytes)), "bpk_msm_workspace_bytes")
+        _check(lib.bpk_msm_workspace_bytes(self.n, self._window_arg, C.byref(nbytes)), "bpk_msm_workspace_bytes")
         self.workspace = _dev_u8(nbytes.value, self.device)
         self.result = torch.zeros(128, dtype=torch.uint8, device=self.device)
 
@@ -156,7 +157,7 @@ class Msm:
         out = self.result if out is None else out
         assert scalars.is_cuda and points.is_cuda and scalars.numel() == self.n * 32 and points.numel() == self.n * 128
         _check(_lib().bpk_msm_device(scalars.data_ptr(), points.data_ptr(), self.n, out.data_ptr(),
-                                     self.workspace.data_ptr(), self.workspace.numel(), self.window_bits,
+                                     self.workspace.data_ptr(), self.workspace.numel(), self._window_arg,
                                      1 if normalize else 0, _stream_ptr(stream)), "bpk_msm_device")
         return out
 

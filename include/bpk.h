@@ -43,7 +43,12 @@ uint64_t bpk_kernel_launches(void);
 #define BPK_OPT_PROVER_LEGACY 3   /* 1: one-CTA-per-proof prover for every batch size */
 #define BPK_OPT_MSM_GROUPS 4      /* window groups of the MSM pipeline as hex digits, top first (0x844); 0 = auto */
 #define BPK_OPT_MSM_SMALL_MAX 5   /* largest n routed to the single-launch small-n MSM; -1 default, 0 disables */
+#define BPK_OPT_HOST_REGISTER 6   /* 1: page-lock pageable caller buffers >= 1 MiB once and remember them (see below) */
 int bpk_debug_set_option(int option, long long value);
+/* With BPK_OPT_HOST_REGISTER on, the host-pointer MSM page-locks large pageable input buffers in place the first time
+ * it sees them, so that repeated calls on the same buffers upload at the pinned PCIe rate.  Such buffers must stay
+ * allocated until this call, which unregisters all of them. */
+int bpk_host_release(void);
 
 /* ---- per-kernel device timing (bench.py's roofline): CUDA events recorded on the launching stream
  * around the named kernel of every call while enabled; read returns the mean duration in ms ---- */
@@ -139,6 +144,18 @@ int bpk_debug_ge_op_device(int op, const void* d_a, const void* d_b, void* d_out
  * tests cover projective and torsion-carrying inputs. */
 int bpk_debug_projectivize_device(void* d_points, size_t n, uint64_t seed, const void* d_torsion,
                                   uint32_t torsion_stride, void* stream);
+/* test hook for the octet-form arithmetic (csrc/fe8.cuh: one 32-bit word per lane, 8 lanes per field element, used
+ * by the latency-bound chains).  Field ops: d_out[i] (32 B, canonical) = a[i] op b[i].  Point ops: d_out[i] (ge25519,
+ * normalised) = 2 a[i] | a[i] + b[i] | a[i] + b[i] through the cached form | 2^64 a[i] | a[i]. */
+#define BPK_FE8_MUL 0
+#define BPK_FE8_ADD 1
+#define BPK_FE8_SUB 2
+#define BPK_GE8_DBL 3
+#define BPK_GE8_ADD 4
+#define BPK_GE8_ADD_CACHED 5
+#define BPK_GE8_DBL_CHAIN 6
+#define BPK_GE8_NORMALIZE 7
+int bpk_debug_fe8_op_device(int op, const void* d_a, const void* d_b, void* d_out, size_t count, void* stream);
 /* test hook: field operations on compile-time constants; writes 6 field elements (8 words each):
  * 1^2, 1*1, 1+1, 2^2, 1-2 (canonical), 2*(2d) (canonical).  Guards the inline-asm operand constraints. */
 int bpk_debug_const_operands_device(uint32_t* d_out48, void* stream);

@@ -417,3 +417,45 @@ def test_msm_concurrent_host_threads_and_streams(oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 64, 147, 257, 513, 1024, 1025])
+def test_msm_small_path_matches_oracle_and_pippenger(oracle, n):
+    """Up to 1024 points an MSM with the automatic window width is Straus in three launches (msm.cu section 8: the
+    reference's production shape, cuda_bulletproof_kernels.cu:119-207); above, Pippenger.  Same bytes as the oracle's
+    naive MSM and as the Pippenger path forced onto the same inputs (BPK_OPT_MSM_SMALL_MAX = 0), edge scalars and a
+    torsion-carrying, projective point included, with and without normalisation."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    rng = random.Random(4000 + n)
+    special = [0, 1, 8, 9, 2**255 - 20, 2**256 - 1, L, L - 1, 0x8888888888888888, 0x7777777777777777 << 192, 2**252, 16**63 * 8]
+    ints = [rng.getrandbits(256) for _ in range(n)]
+    for i, v in enumerate(special[:n]):
+        ints[-1 - i] = v
+    sc = ob.ints_to_fe(ints)
+    pl = curve_points(rng, n)
+    if n > 2:  # a point with a torsion component, given projectively
+        y = 3
+        while pyref.recover_x(y, 0) is None:
+            y += 1
+        pl[1] = (pyref.recover_x(y, 0), y)
+    pts = np.stack([ob.affine_to_ge(*p) for p in pl])
+    if n > 2:
+        z = 0x1234567890ABCDEF1234567890ABCDEF1234567
+        x, y = pl[1]
+        pts[1] = np.concatenate([ob.int_to_fe(x * z % P), ob.int_to_fe(y * z % P), ob.int_to_fe(z), ob.int_to_fe(x * y % P * z % P)])
+    want = oracle_msm(oracle, sc, pts)
+    d_s = torch.from_numpy(sc.view(np.uint8).reshape(n, 32)).cuda()
+    d_p = torch.from_numpy(pts.view(np.uint8).reshape(n, 128)).cuda()
+    got = cbp.Msm(n)(d_s, d_p).cpu().numpy().view(np.uint64).copy()
+    assert np.array_equal(got, want)
+    raw = cbp.Msm(n)(d_s, d_p, normalize=False).cpu().numpy().view(np.uint64).copy()
+    assert ob.ge_to_affine(raw) == ob.ge_to_affine(want)
+    try:
+        cbp.check(lib.bpk_debug_set_option(5, 0), "set_option")  # BPK_OPT_MSM_SMALL_MAX = 0: Pippenger for every n
+        pip = cbp.Msm(n)(d_s, d_p).cpu().numpy().view(np.uint64).copy()
+    finally:
+        lib.bpk_debug_set_option(5, -1)
+    assert np.array_equal(pip, want)
+    assert np.array_equal(cbp.cuda_point_vector_multi_scalar_mul(sc, pts, shared=True), want)

@@ -27,7 +27,7 @@ def main():
     normalize = "--no-normalize" not in args
     sizes = [int(a) for a in args if not a.startswith("--")] or [10, 12, 14, 16, 17, 18, 20]
     for lg in sizes:
-        n = 1 << lg
+        n = 1 << lg if lg <= 30 else lg  # values above 30 are taken as n itself (147 = one 64-bit verification)
         pts, _ = cbp.synth_points(n, seed=0xC3 + lg)
         sc = cbp.synth_scalars(n, seed=0x5CA1A000 + lg, bits=252)
         msm = cbp.Msm(n)
