@@ -239,23 +239,16 @@ __device__ __forceinline__ void fe8_gather(fe& r, uint32_t a, const Fe8Lane& L) 
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = fe8_shfl(a, L.base + (uint32_t)i);
 }
-// (X/Z, Y/Z, 1, XY/Z^2) with canonical limbs, stored by lane 0 — what ge_normalize + ge_store produce
+// (X/Z, Y/Z, 1, XY/Z^2) with canonical limbs, stored by lane 0 — what ge_normalize + ge_store produce.  The inversion
+// is the divsteps one (every lane runs it on the same value: no divergence), the rest thread-level.
 __device__ __forceinline__ void ge8_store_normalized(void* out, const ge8& p, const Fe8Lane& L) {
-    const uint32_t zi = fe8_invert(p.Z, L);
-    fe x, y, z;
-    fe8_gather(x, fe8_mul(p.X, zi, L), L);
-    fe8_gather(y, fe8_mul(p.Y, zi, L), L);
-    if ((threadIdx.x & 31u) != 0) return;
-    fe_canon(x);
-    fe_canon(y);
     ge_p3 o;
-    o.X = x;
-    o.Y = y;
-    fe_set1(o.Z);
-    fe_mul(z, x, y);
-    fe_canon(z);
-    o.T = z;
-    ge_store(out, o);
+    fe8_gather(o.X, p.X, L);
+    fe8_gather(o.Y, p.Y, L);
+    fe8_gather(o.Z, p.Z, L);
+    fe_set0(o.T);
+    ge_normalize(o);
+    if ((threadIdx.x & 31u) == 0) ge_store(out, o);
 }
 
 }  // namespace cbp

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include "fe8.cuh"
+#include "sc25519.cuh"
 using namespace cbp;
 
 #define ITERS 4096
@@ -124,11 +125,25 @@ __global__ void __launch_bounds__(32) k_lat_dbl(uint32_t* out, uint32_t seed, in
     }
     out[blockIdx.x * 32 + threadIdx.x] = p.X.v[0] ^ p.T.v[1] ^ p.Y.v[2] ^ p.Z.v[3];
 }
-__global__ void __launch_bounds__(32) k_lat_inv(uint32_t* out, uint32_t seed) {
+// what: 0 divsteps fe_invert, same value in every lane; 1 Fermat chain; 2 divsteps, a different value per lane
+// (divergent); 3 / 4 / 5 the same for scalars mod l
+__global__ void __launch_bounds__(32) k_lat_inv(uint32_t* out, uint32_t seed, int what) {
     fe a, r;
+    const uint32_t vary = (what == 2 || what == 5) ? threadIdx.x * 0x9E3779B9u : 0u;
 #pragma unroll
-    for (int i = 0; i < 8; i++) a.v[i] = seed + i + threadIdx.x;
-    fe_invert(r, a);
+    for (int i = 0; i < 8; i++) a.v[i] = (seed + i) * 0x85EBCA6Bu + vary * (i + 1);
+    a.v[7] &= 0x0FFFFFFFu;
+    if (what == 0 || what == 2) fe_invert(r, a);
+    else if (what == 1) fe_invert_fermat(r, a);
+    else {
+        sc x, y;
+#pragma unroll
+        for (int i = 0; i < 8; i++) x.v[i] = a.v[i];
+        if (what == 4) sc_invert_fermat(y, x);
+        else sc_invert(y, x);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = y.v[i];
+    }
     out[blockIdx.x * 32 + threadIdx.x] = r.v[0];
 }
 
@@ -231,8 +246,12 @@ int main() {
         }
     }
     {
-        double ms = time_ms([&] { k_lat_inv<<<sms, 32>>>((uint32_t*)buf, 99); }, 5);
-        printf("{\"bench\": \"latency_fe_invert\", \"us\": %.3f}\n", ms * 1e3);
+        const char* inames[6] = {"latency_fe_invert_divsteps", "latency_fe_invert_fermat", "latency_fe_invert_divsteps_divergent",
+                                 "latency_sc_invert_divsteps", "latency_sc_invert_fermat", "latency_sc_invert_divsteps_divergent"};
+        for (int what = 0; what < 6; what++) {
+            double ms = time_ms([&] { k_lat_inv<<<sms, 32>>>((uint32_t*)buf, 99, what); }, 5);
+            printf("{\"bench\": \"%s\", \"us\": %.3f}\n", inames[what], ms * 1e3);
+        }
     }
     {  // PCIe: contiguous upload of 2^20 points (128 B each) against a pitched upload of X,Y,Z only (96 of 128 B)
         const size_t n = (size_t)1 << 20;

@@ -905,7 +905,10 @@ __global__ void __launch_bounds__(32) msm_horner_kernel(const uint8_t* __restric
 //                    deep instead of the 252 + 63 of a plain Horner chain
 // Exact for every curve point (unified additions, all 255 scalar bits), like the Pippenger path.
 static constexpr int kStrausWindows = 64, kStrausTable = 8;
-static constexpr size_t kStrausMaxDefault = 1024;
+// measured crossover with Pippenger (ms, Straus / Pippenger c = 15): 2^10 0.30 / 0.47, 2^12 0.35 / 0.47, 2^13 0.42 / 0.45,
+// 2^14 0.53 / 0.46, 2^15 0.78 / 0.49 (the window sums are n * 64 unified additions against n * 18 mixed ones)
+static constexpr size_t kStrausMaxDefault = (size_t)1 << 13;
+static constexpr uint32_t kStrausSlice = 1024;               // points per CTA of the window-sum kernel
 __global__ void __launch_bounds__(128) straus_prepare_kernel(const uint8_t* __restrict__ scalars,
                                                              const uint8_t* __restrict__ points, uint32_t n,
                                                              uint8_t* __restrict__ tables, int8_t* __restrict__ digits) {
@@ -934,14 +937,16 @@ __global__ void __launch_bounds__(128) straus_prepare_kernel(const uint8_t* __re
 #pragma unroll
     for (int m = 0; m < kStrausTable; m++) ge_store(tables + ((size_t)i * kStrausTable + m) * 128, M[m]);
 }
+// grid (64 windows, S slices of the point range); slice sums land in sums[(slice * 64 + window)]
 __global__ void __launch_bounds__(256) straus_sums_kernel(const uint8_t* __restrict__ tables,
                                                           const int8_t* __restrict__ digits, uint32_t n,
-                                                          uint8_t* __restrict__ sums) {
+                                                          uint32_t slice_len, uint8_t* __restrict__ sums) {
     __shared__ __align__(16) uint8_t sh[8][128];
     const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t lo = blockIdx.y * slice_len, hi = lo + slice_len < n ? lo + slice_len : n;
     ge_p3 acc;
     ge_p3_0(acc);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const int d = digits[(size_t)w * n + i];
         if (d == 0) continue;
         ge_p3 t;
@@ -958,7 +963,20 @@ __global__ void __launch_bounds__(256) straus_sums_kernel(const uint8_t* __restr
         else ge_p3_0(acc);
         ge_warp_sum(acc);  // nwarps <= 8: three of the five levels add identities
     }
-    if (threadIdx.x == 0) ge_store(sums + (size_t)w * 128, acc);
+    if (threadIdx.x == 0) ge_store(sums + ((size_t)blockIdx.y * kStrausWindows + w) * 128, acc);
+}
+// more than one slice: one warp per window adds the slice sums up (lane = slice), result in sums[window]
+__global__ void __launch_bounds__(32) straus_slices_kernel(uint8_t* sums, uint32_t nslices) {
+    const uint32_t w = blockIdx.x, lane = threadIdx.x;
+    ge_p3 acc;
+    ge_p3_0(acc);
+    for (uint32_t sl = lane; sl < nslices; sl += 32) {
+        ge_p3 t;
+        ge_load(t, sums + ((size_t)sl * kStrausWindows + w) * 128);
+        ge_add(acc, acc, t);
+    }
+    ge_warp_sum(acc);
+    if (lane == 0) ge_store(sums + (size_t)w * 128, acc);
 }
 __global__ void __launch_bounds__(1024) straus_combine_kernel(const uint8_t* __restrict__ sums, int normalize,
                                                               uint8_t* __restrict__ result) {
@@ -1077,7 +1095,7 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->small = c <= 0 && n >= 1 && n <= (smax >= 0 ? (size_t)smax : kStrausMaxDefault);
     p->off_stables = take(p->small ? n * kStrausTable * 128 : 0);
     p->off_sdigits = take(p->small ? n * kStrausWindows : 0);
-    p->off_ssums = take(p->small ? (size_t)kStrausWindows * 128 : 0);
+    p->off_ssums = take(p->small ? ((n + kStrausSlice - 1) / kStrausSlice) * kStrausWindows * 128 : 0);
     p->workspace_bytes = off;
 }
 
@@ -1224,8 +1242,13 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
                                                                           (uint32_t)n, tables, digits);
         CBP_LAUNCH_CHECK(); nl++;
         const unsigned sthreads = n <= 256 ? 32u : (n <= 512 ? 64u : (n <= 1024 ? 128u : 256u));
-        straus_sums_kernel<<<kStrausWindows, sthreads, 0, st>>>(tables, digits, (uint32_t)n, sums);
+        const unsigned nslices = (unsigned)((n + kStrausSlice - 1) / kStrausSlice);
+        straus_sums_kernel<<<dim3(kStrausWindows, nslices), sthreads, 0, st>>>(tables, digits, (uint32_t)n, kStrausSlice, sums);
         CBP_LAUNCH_CHECK(); nl++;
+        if (nslices > 1) {
+            straus_slices_kernel<<<kStrausWindows, 32, 0, st>>>(sums, nslices);
+            CBP_LAUNCH_CHECK(); nl++;
+        }
         straus_combine_kernel<<<1, 1024, 0, st>>>(sums, normalize, (uint8_t*)d_result);
         CBP_LAUNCH_CHECK(); nl++;
         prof_end(BPK_PROF_MSM_TOTAL, st);

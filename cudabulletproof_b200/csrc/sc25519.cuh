@@ -195,8 +195,9 @@ __device__ __forceinline__ void sc_sq(sc& r, const sc& a) {
     sq_wide(w, fa);
     sc_reduce512(r, w);
 }
-// a^(l-2); inv(0) = 0
-__device__ __noinline__ static void sc_invert(sc& r, const sc& a) {
+// a^(l-2); inv(0) = 0: the Fermat chain, 253 squarings + ~130 multiplications with a Barrett reduction each (~200 us
+// for a lone thread).  Kept as the cross-check of sc_invert below.
+__device__ __noinline__ static void sc_invert_fermat(sc& r, const sc& a) {
     const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0, 0, 0, 0x10000000u};
     sc acc;
     sc_set1(acc);
@@ -206,6 +207,16 @@ __device__ __noinline__ static void sc_invert(sc& r, const sc& a) {
         if ((e[bit >> 5] >> (bit & 31)) & 1) sc_mul(acc, acc, a);
     }
     r = acc;
+}
+// 1 / a mod l in [0, l); inv(0) = 0.  Divsteps (modinv.cuh): every scalar inverted on this path is a public
+// Fiat-Shamir challenge (y, the round challenges u_j), so variable time is fine.
+__device__ __noinline__ static void sc_invert(sc& r, const sc& a) {
+    const uint32_t lw[8] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0, 0, 0, 0x10000000u};
+    const ModInfo mi = modinfo_from_words(lw);
+    uint32_t out[8];
+    modinv_words(out, a.v, mi);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = out[i];
 }
 
 }  // namespace cbp
