@@ -48,6 +48,7 @@ struct Options {
     int ngroups = 0;          // CBP_GROUPS="8,4,4": explicit window groups of the MSM pipeline, top down
     int groups[8] = {};
     int msm_small_max = -1;   // CBP_MSM_SMALL_MAX: largest n taken by the single-launch small-n MSM (-1 default)
+    int ipa_composite_max = -1;  // largest vector length whose IPA rounds run unfolded (-1: default 4096; tests lower it)
     int host_register = 0;    // CBP_HOST_REGISTER: 1 = page-lock large pageable caller buffers once and remember them
 };
 Options& options();

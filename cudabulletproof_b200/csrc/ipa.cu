@@ -11,6 +11,7 @@
 #include <mutex>
 #include "../../include/cuda_bulletproof.h"
 #include "common.h"
+#include "ipa_straus.h"
 #include "msm.h"
 #include "rangeproof.cuh"
 #include "sha256.cuh"
@@ -339,8 +340,13 @@ static IpaSide* ipa_side(int dev) {
     }
     return &v;
 }
+// longest vector whose rounds run unfolded: kIpaCompositeMax unless a test lowered it (BPK_OPT_IPA_COMPOSITE_MAX)
+static size_t ipa_comp_max() {
+    const int o = options().ipa_composite_max;
+    return (o >= 2 && (size_t)o <= kIpaCompositeMax && !(o & (o - 1))) ? (size_t)o : kIpaCompositeMax;
+}
 struct IpaProveLayout {
-    size_t a, b, g, h, scal[2], pts[2], small, ipws, msmws[2], total;
+    size_t a, b, g, h, scal[2], pts[2], small, ipws, msmws[2], comp, total;
 };
 static int ipa_prove_layout(size_t n, IpaProveLayout* L) {
     size_t off = 0;
@@ -368,8 +374,10 @@ static int ipa_prove_layout(size_t n, IpaProveLayout* L) {
         msm_make_plan(&p, m + 1, 0);
         if (p.workspace_bytes > msm_bytes) msm_bytes = p.workspace_bytes;
     }
+    if (n <= ipa_comp_max()) msm_bytes = 0;  // every round is a composite round: no MSM workspace
     L->msmws[0] = take(msm_bytes);
     L->msmws[1] = take(msm_bytes);
+    L->comp = take(ipa_composite_workspace_bytes(n < ipa_comp_max() ? n : ipa_comp_max()));
     L->total = off;
     return BPK_OK;
 }
@@ -404,9 +412,18 @@ int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, cons
     ipa_prove_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a, b, g, h, (const uint8_t*)d_a, (const uint8_t*)d_b,
                                                                       (const uint8_t*)d_G, (const uint8_t*)d_H, n);
     CBP_CHECK_LAUNCH();
+    const size_t comp_max = ipa_comp_max();
     int round = 0;
+    // Rounds over more than kIpaCompositeMax generators fold the points and run Pippenger MSMs; from there on the
+    // rounds are written over the (by then folded) generators without folding a point again (ipa_straus.cu).
     for (size_t np = n >> 1; np >= 1; np >>= 1, round++) {
         int rc;
+        if (2 * np <= comp_max) {
+            if ((rc = ipa_prove_composite(a, b, g, h, (const uint8_t*)d_Q, 2 * np, round, tr, u, ui, (uint8_t*)d_L,
+                                          (uint8_t*)d_R, (uint8_t*)d_x_out, ws + Ly.comp, st)) != BPK_OK)
+                return rc;
+            break;
+        }
         if ((rc = bpk_sc_inner_product_device(cL, a, b + np * 32, np, ws + Ly.ipws, ipb + 256, st)) != BPK_OK) return rc;
         if ((rc = bpk_sc_inner_product_device(cR, a + np * 32, b, np, ws + Ly.ipws, ipb + 256, st)) != BPK_OK) return rc;
         MsmPlan p;

@@ -44,6 +44,7 @@ uint64_t bpk_kernel_launches(void);
 #define BPK_OPT_MSM_GROUPS 4      /* window groups of the MSM pipeline as hex digits, top first (0x844); 0 = auto */
 #define BPK_OPT_MSM_SMALL_MAX 5   /* largest n routed to the single-launch small-n MSM; -1 default, 0 disables */
 #define BPK_OPT_HOST_REGISTER 6   /* 1: page-lock pageable caller buffers >= 1 MiB once and remember them (see below) */
+#define BPK_OPT_IPA_COMPOSITE_MAX 7 /* longest vector whose IPA rounds run unfolded (power of two <= 4096); -1 default */
 int bpk_debug_set_option(int option, long long value);
 /* With BPK_OPT_HOST_REGISTER on, the host-pointer MSM page-locks large pageable input buffers in place the first time
  * it sees them, so that repeated calls on the same buffers upload at the pinned PCIe rate.  Such buffers must stay
@@ -116,8 +117,11 @@ int bpk_ipa_fold_points_device(void* d_G_out, void* d_H_out, const void* d_G, co
 /* Inner-product argument, prover side, for any power-of-two n (inner_product_prove,
  * bulletproof_vectors.cu:375-509): d_L / d_R receive log2 n normalised points each, d_a_out / d_b_out the final
  * scalars (32 B), d_x_out the raw first-round challenge the reference stores in the proof (32 B).
- * transcript0: 32 bytes (HOST pointer).  Bit-identical to the CPU oracle.  Per round: two mod-l inner products,
- * L and R as one Pippenger MSM each over 2n'+1 points, the challenge hash and inversion, the a/b and G/H folds. */
+ * transcript0: 32 bytes (HOST pointer).  Bit-identical to the CPU oracle for generators of prime order (every
+ * Bulletproofs generator set; bpk_gens_derive_device clears the cofactor).  Rounds over at most 4096 generators never
+ * fold a point: L and R are multi-scalar multiplications over the base generators with composite scalars
+ * (csrc/ipa_straus.cu, 6 launches per round); longer vectors are first folded as the reference does
+ * (bulletproof_vectors.cu:641-663) with L and R as Pippenger MSMs. */
 int bpk_ipa_prove_workspace_bytes(size_t n, size_t* bytes);
 int bpk_ipa_prove_device(const void* d_G, const void* d_H, const void* d_Q, const void* d_a, const void* d_b, size_t n,
                          const uint8_t transcript0[32], void* d_L, void* d_R, void* d_a_out, void* d_b_out, void* d_x_out,

@@ -63,8 +63,11 @@ def test_msm_plan_is_host_only_and_consistent():
         assert lib.bpk_msm_workspace_bytes(n, c, C.byref(out)) == 0
         return out.value
 
-    sizes = [ws(1 << lg) for lg in range(6, 25, 2)]
+    sizes = [ws(1 << lg) for lg in range(14, 25, 2)]  # Pippenger sizes (up to 2^13 points the Straus tables are added)
     assert sizes == sorted(sizes) and sizes[0] > 0
+    small = [ws(1 << lg) for lg in range(0, 14)]
+    assert small == sorted(small) and small[0] > 0
+    assert ws(1 << 13) - ws(1 << 13, 15) >= (1 << 13) * (8 * 128 + 64)  # the multiples 1..8 and 64 digits per point
     slotted = ws(1 << 20)
     lib.bpk_debug_set_option(OPT_SLOTS, 0)
     compact = ws(1 << 20)

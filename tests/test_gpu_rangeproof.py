@@ -382,6 +382,38 @@ def test_device_ipa_prover_matches_oracle_small(oracle, gens64, n):
     assert fx.cpu().numpy().tobytes() == bytes(proof.x)
 
 
+def test_device_ipa_prover_hybrid_fold_then_unfolded_rounds(oracle, gens64):
+    """Vectors longer than 4096 are first folded like the reference (bulletproof_vectors.cu:641-663, Pippenger MSMs for
+    L and R), then the remaining rounds run unfolded over the folded generators (csrc/ipa_straus.cu).  Forced here at
+    n = 64 by lowering the switch-over (BPK_OPT_IPA_COMPOSITE_MAX) to 16, 8 and 2: every split point gives the oracle's
+    bytes."""
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    n = 64
+    rng = random.Random(0x4B1D)
+    G, H, Q = gens64.G[:n].copy(), gens64.H[:n].copy(), gens64.h.copy()
+    a = ob.ints_to_fe([rng.getrandbits(253) for _ in range(n)])
+    b = ob.ints_to_fe([rng.getrandbits(253) for _ in range(n)])
+    tr0 = bytes(rng.getrandbits(8) for _ in range(32))
+    av, bv, Gv, Hv = ob.field_vector(a), ob.field_vector(b), ob.point_vector(G), ob.point_vector(H)
+    c = np.zeros(4, dtype=np.uint64)
+    oracle.field_vector_inner_product(ob.ptr(c), C.byref(av), C.byref(bv))
+    proof = ob.InnerProductProof()
+    oracle.inner_product_prove(C.byref(proof), C.byref(av), C.byref(bv), C.byref(Gv), C.byref(Hv), ob.ptr(Q), ob.ptr(c), tr0)
+    try:
+        for comp_max in (16, 8, 2, -1):
+            cbp.check(lib.bpk_debug_set_option(7, comp_max), "set_option")
+            dL, dR, fa, fb, fx = cbp.ipa_prove(G, H, Q, a, b, transcript0=tr0)
+            for j in range(6):
+                assert dL[j].cpu().numpy().tobytes() == bytes(proof.L.elements[j]), (comp_max, j)
+                assert dR[j].cpu().numpy().tobytes() == bytes(proof.R.elements[j]), (comp_max, j)
+            assert fa.cpu().numpy().tobytes() == bytes(proof.a.elements[0])
+            assert fb.cpu().numpy().tobytes() == bytes(proof.b.elements[0])
+            assert fx.cpu().numpy().tobytes() == bytes(proof.x)
+    finally:
+        lib.bpk_debug_set_option(7, -1)
+
+
 @pytest.mark.parametrize("n,m", [(16, 5), (64, 150)])
 def test_keyed_prover_csprng_nonces(oracle, gens16, gens64, n, m):
     """bpk_range_prove_batch_keyed_device: blinding values and nonces are SHA-256("cbp-bp-nonce" || key || j) of a
