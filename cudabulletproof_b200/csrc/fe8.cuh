@@ -53,12 +53,14 @@ __device__ __forceinline__ uint32_t fe8_normalize(uint64_t s, const Fe8Lane& L) 
     const uint32_t lo = (uint32_t)s & (top ? 0x7FFFFFFFu : 0xFFFFFFFFu);
     const uint32_t hi = (uint32_t)(s >> (top ? 31 : 32));  // < 2^26
     const uint32_t r = fe8_shfl(hi, L.base + ((L.j - 1u) & 7u));
-    const uint64_t v = (uint64_t)lo + (uint64_t)(r * (L.j == 0 ? 19u : 1u));
-    const uint32_t vlo = (uint32_t)v, c = (uint32_t)(v >> 32);
-    const uint32_t g = (__ballot_sync(0xffffffffu, c != 0) >> L.base) & 0xFFu;
-    const uint32_t p = (__ballot_sync(0xffffffffu, vlo == 0xFFFFFFFFu) >> L.base) & 0xFFu;
-    const uint32_t x = p | g;
-    const uint32_t cin = (((x + g) ^ x ^ g) >> L.j) & 1u;
+    const uint64_t v = (uint64_t)r * (L.j == 0 ? 19u : 1u) + lo;
+    const uint32_t vlo = (uint32_t)v;
+    // generate / propagate masks of all four octets at once: lane 7 of an octet neither generates (its word has
+    // 31 bits) nor propagates, so bit 7 of every byte of both masks is clear and the integer addition below cannot
+    // carry from one octet into the next
+    const uint32_t g = __ballot_sync(0xffffffffu, (uint32_t)(v >> 32) != 0);
+    const uint32_t x = g | __ballot_sync(0xffffffffu, vlo == 0xFFFFFFFFu);
+    const uint32_t cin = (((x + g) ^ x ^ g) >> (threadIdx.x & 31u)) & 1u;
     return vlo + cin;
 }
 // product of two elements given as 32-bit words (any values < 2^256) -> tight.

@@ -23,9 +23,10 @@
 namespace cbp {
 
 static constexpr int kWin = 64, kTab = 8;
-static constexpr uint32_t kSlice = 1024;
+static constexpr uint32_t kSlice = 256;  // points per warp of the window-sum kernel
 
-// multiples 1..8 of G[0..m), H[0..m), Q: row t = i | m + i | 2m
+// multiples 1..8 of G[0..m), H[0..m), Q in affine precomputed form (y+x, y-x, 2dxy; 96 B, one inversion per
+// generator by Montgomery's trick — built once per argument): row t = i | m + i | 2m
 __global__ void __launch_bounds__(128) ipa_tables_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ h,
                                                          const uint8_t* __restrict__ Q, uint32_t m,
                                                          uint8_t* __restrict__ tables, uint8_t* __restrict__ wG,
@@ -42,8 +43,25 @@ __global__ void __launch_bounds__(128) ipa_tables_kernel(const uint8_t* __restri
     ge_dbl(M[5], M[2]);
     ge_add(M[6], M[5], P);
     ge_dbl(M[7], M[3]);
+    fe pre[kTab], run, inv;
+    fe_set1(run);
 #pragma unroll
-    for (int k = 0; k < kTab; k++) ge_store(tables + ((size_t)t * kTab + k) * 128, M[k]);
+    for (int k = 0; k < kTab; k++) {
+        pre[k] = run;
+        fe_mul(run, run, M[k].Z);
+    }
+    fe_invert(inv, run);
+#pragma unroll
+    for (int k = kTab - 1; k >= 0; k--) {
+        fe zi, x, y;
+        fe_mul(zi, inv, pre[k]);
+        fe_mul(inv, inv, M[k].Z);
+        fe_mul(x, M[k].X, zi);
+        fe_mul(y, M[k].Y, zi);
+        ge_niels q;
+        ge_to_niels_affine(q, x, y);
+        ge_niels_store(tables + ((size_t)t * kTab + k) * 96, q);
+    }
     if (t < 2 * m) {  // folding weights start at 1
         sc one;
         sc_set1(one);
@@ -123,25 +141,25 @@ __global__ void __launch_bounds__(128) ipa_digits_kernel(uint32_t mb, uint32_t m
         digits[((size_t)side * kWin + w) * npts + q] = (int8_t)d;  // s < l < 2^253: no carry out of the top digit
     }
 }
-// grid (64 windows, slices, 2 sides): sums[((side * nslices + slice) * 64 + w)]
-__global__ void __launch_bounds__(256) ipa_sums_kernel(const uint8_t* __restrict__ tables, const int8_t* __restrict__ digits,
-                                                       const uint32_t* __restrict__ rows, uint32_t npts,
-                                                       uint32_t slice_len, uint8_t* __restrict__ sums) {
-    __shared__ __align__(16) uint8_t sh[8][128];
-    const uint32_t w = blockIdx.x, side = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5,
-                   nwarps = blockDim.x >> 5;
+// grid (64 windows, slices, 2 sides), ONE WARP per CTA: sums[((side * nslices + slice) * 64 + w)].
+// Lane-strided mixed additions (7M) from the affine tables, then a shuffle tree of unified additions.  (A first
+// version with 256-thread CTAs over 1024-point slices spent most of its time in the trees: 4 additions per thread,
+// then 5 shuffle levels and 7 serial additions by one lane — 182 us per round at n = 4096.)
+__global__ void __launch_bounds__(32) ipa_sums_kernel(const uint8_t* __restrict__ tables, const int8_t* __restrict__ digits,
+                                                      const uint32_t* __restrict__ rows, uint32_t npts,
+                                                      uint32_t slice_len, uint8_t* __restrict__ sums) {
+    const uint32_t w = blockIdx.x, side = blockIdx.z, lane = threadIdx.x;
     const uint32_t lo = blockIdx.y * slice_len, hi = lo + slice_len < npts ? lo + slice_len : npts;
     const int8_t* dg = digits + ((size_t)side * kWin + w) * npts;
     const uint32_t* rw = rows + (size_t)side * npts;
     ge_p3 acc;
     ge_p3_0(acc);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
         const int d = dg[i];
         if (d == 0) continue;
-        ge_p3 t;
-        ge_load(t, tables + ((size_t)rw[i] * kTab + (uint32_t)((d < 0 ? -d : d) - 1)) * 128);
-        if (d < 0) ge_neg(t, t);
-        ge_add(acc, acc, t);
+        ge_niels q;
+        ge_niels_load(q, tables + ((size_t)rw[i] * kTab + (uint32_t)((d < 0 ? -d : d) - 1)) * 96);
+        ge_madd(acc, acc, q, d < 0);
     }
 #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
@@ -155,21 +173,7 @@ __global__ void __launch_bounds__(256) ipa_sums_kernel(const uint8_t* __restrict
         }
         ge_add(acc, acc, other);
     }
-    if (nwarps > 1) {
-        if (lane == 0) ge_store(sh[warp], acc);
-        __syncthreads();
-        if (warp != 0) return;
-        ge_p3_0(acc);
-        if (lane == 0) {
-            ge_load(acc, sh[0]);
-            for (uint32_t k = 1; k < nwarps; k++) {
-                ge_p3 t;
-                ge_load(t, sh[k]);
-                ge_add(acc, acc, t);
-            }
-        }
-    }
-    if (threadIdx.x == 0) ge_store(sums + (((size_t)side * gridDim.y + blockIdx.y) * kWin + w) * 128, acc);
+    if (lane == 0) ge_store(sums + (((size_t)side * gridDim.y + blockIdx.y) * kWin + w) * 128, acc);
 }
 // more than one slice: one warp per (window, side) adds the slice sums up into slice 0's slot
 __global__ void __launch_bounds__(32) ipa_slices_kernel(uint8_t* sums, uint32_t nslices) {
@@ -296,7 +300,7 @@ static CompositeLayout composite_layout(size_t mb) {
         return o;
     };
     const size_t npts = mb + 1, nslices = (npts + kSlice - 1) / kSlice;
-    Ly.tables = take((2 * mb + 1) * kTab * 128);
+    Ly.tables = take((2 * mb + 1) * kTab * 96);
     Ly.wG = take(mb * 32);
     Ly.wH = take(mb * 32);
     Ly.digits = take(2 * (size_t)kWin * npts);
@@ -337,8 +341,7 @@ int ipa_prove_composite(uint8_t* a, uint8_t* b, const uint8_t* g, const uint8_t*
         IPA_LAUNCHED();
         ipa_digits_kernel<<<(2 * npts + 127) / 128, 128, 0, st>>>(m, mcur, a, b, wG, wH, cL, cR, digits, rows);
         IPA_LAUNCHED();
-        const unsigned sthreads = npts <= 256 ? 32u : (npts <= 512 ? 64u : (npts <= 1024 ? 128u : 256u));
-        ipa_sums_kernel<<<dim3(kWin, nslices, 2), sthreads, 0, st>>>(tables, digits, rows, npts, kSlice, sums);
+        ipa_sums_kernel<<<dim3(kWin, nslices, 2), 32, 0, st>>>(tables, digits, rows, npts, kSlice, sums);
         IPA_LAUNCHED();
         if (nslices > 1) {
             ipa_slices_kernel<<<dim3(kWin, 2), 32, 0, st>>>(sums, nslices);

@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(32) k_lat_inv(uint32_t* out, uint32_t seed, in
     out[blockIdx.x * 32 + threadIdx.x] = r.v[0];
 }
 
-// the same chains in octet form (fe8.cuh: one word per lane, the warp shares every point operation)
-__global__ void __launch_bounds__(32) k_lat8(uint32_t* out, uint32_t seed, int what) {
+// the same chains in octet form (fe8.cuh: one word per lane, the warp shares every point operation); one kernel
+// per operation so that no measurement shares its loop body (and its instruction fetches) with another
+template <int WHAT>
+__global__ void __launch_bounds__(32) k_lat8(uint32_t* out, uint32_t seed) {
     const Fe8Lane L = fe8_lane();
     ge8 p, q;
     ge8_identity(p, L);
@@ -160,22 +162,30 @@ __global__ void __launch_bounds__(32) k_lat8(uint32_t* out, uint32_t seed, int w
     ge8_cached c;
     ge8_to_cached(c, q, L);
     uint32_t z = p.X;
-    if (what == 3) {
+    if (WHAT == 3) {
         z = fe8_invert(p.Y, L);
-    } else if (what == 4) {
+    } else if (WHAT == 4) {
         uint32_t y = p.Y;
+#pragma unroll 1
         for (int it = 0; it < 256; it++) z = fe8_mul(z, y, L);
-    } else if (what == 5) {
+    } else if (WHAT == 5) {
+#pragma unroll 1
         for (int it = 0; it < 256; it++) z = fe8_sub(z, p.Y, L);
+    } else if (WHAT == 6) {
+#pragma unroll 1
+        for (int it = 0; it < 256; it++) z = fe8_mul(z, z, L);
     } else {
+#pragma unroll 1
         for (int it = 0; it < 256; it++) {
-            if (what == 0) ge8_dbl(p, p, L);
-            else if (what == 1) ge8_add(p, p, q, L);
+            if (WHAT == 0) ge8_dbl(p, p, L);
+            else if (WHAT == 1) ge8_add(p, p, q, L);
             else ge8_add_cached(p, p, c, L);
         }
     }
     out[blockIdx.x * 32 + threadIdx.x] = p.X ^ p.T ^ p.Y ^ p.Z ^ z;
 }
+template <int WHAT>
+static void lat8_row(const char* name, int sms, void* buf);
 
 template <typename F>
 static double time_ms(F launch, int reps) {
@@ -191,6 +201,13 @@ static double time_ms(F launch, int reps) {
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     return ms / reps;
+}
+
+template <int WHAT>
+static void lat8_row(const char* name, int sms, void* buf) {
+    double ms = time_ms([&] { k_lat8<WHAT><<<sms, 32>>>((uint32_t*)buf, 99); }, 5);
+    if (WHAT != 3) printf("{\"bench\": \"%s\", \"us_per_op\": %.3f}\n", name, ms * 1e3 / 256);
+    else printf("{\"bench\": \"%s\", \"us\": %.3f}\n", name, ms * 1e3);
 }
 
 int main() {
@@ -237,13 +254,13 @@ int main() {
         printf("{\"bench\": \"latency_ge_dbl%s\", \"us_per_op\": %.3f}\n", quad ? "_quad" : "", ms * 1e3 / 256);
     }
     {
-        const char* names[6] = {"latency_ge8_dbl", "latency_ge8_add", "latency_ge8_add_cached", "latency_fe8_invert",
-                                "latency_fe8_mul", "latency_fe8_sub"};
-        for (int what = 0; what < 6; what++) {
-            double ms = time_ms([&] { k_lat8<<<sms, 32>>>((uint32_t*)buf, 99, what); }, 5);
-            if (what != 3) printf("{\"bench\": \"%s\", \"us_per_op\": %.3f}\n", names[what], ms * 1e3 / 256);
-            else printf("{\"bench\": \"%s\", \"us\": %.3f}\n", names[what], ms * 1e3);
-        }
+        lat8_row<0>("latency_ge8_dbl", sms, buf);
+        lat8_row<1>("latency_ge8_add", sms, buf);
+        lat8_row<2>("latency_ge8_add_cached", sms, buf);
+        lat8_row<3>("latency_fe8_invert", sms, buf);
+        lat8_row<4>("latency_fe8_mul", sms, buf);
+        lat8_row<5>("latency_fe8_sub", sms, buf);
+        lat8_row<6>("latency_fe8_sq", sms, buf);
     }
     {
         const char* inames[6] = {"latency_fe_invert_divsteps", "latency_fe_invert_fermat", "latency_fe_invert_divsteps_divergent",

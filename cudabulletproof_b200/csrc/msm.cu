@@ -908,7 +908,7 @@ static constexpr int kStrausWindows = 64, kStrausTable = 8;
 // measured crossover with Pippenger (ms, Straus / Pippenger c = 15): 2^10 0.30 / 0.47, 2^12 0.35 / 0.47, 2^13 0.42 / 0.45,
 // 2^14 0.53 / 0.46, 2^15 0.78 / 0.49 (the window sums are n * 64 unified additions against n * 18 mixed ones)
 static constexpr size_t kStrausMaxDefault = (size_t)1 << 13;
-static constexpr uint32_t kStrausSlice = 1024;               // points per CTA of the window-sum kernel
+static constexpr uint32_t kStrausSlice = 256;                // points per warp of the window-sum kernel
 __global__ void __launch_bounds__(128) straus_prepare_kernel(const uint8_t* __restrict__ scalars,
                                                              const uint8_t* __restrict__ points, uint32_t n,
                                                              uint8_t* __restrict__ tables, int8_t* __restrict__ digits) {
@@ -937,16 +937,17 @@ __global__ void __launch_bounds__(128) straus_prepare_kernel(const uint8_t* __re
 #pragma unroll
     for (int m = 0; m < kStrausTable; m++) ge_store(tables + ((size_t)i * kStrausTable + m) * 128, M[m]);
 }
-// grid (64 windows, S slices of the point range); slice sums land in sums[(slice * 64 + window)]
-__global__ void __launch_bounds__(256) straus_sums_kernel(const uint8_t* __restrict__ tables,
-                                                          const int8_t* __restrict__ digits, uint32_t n,
-                                                          uint32_t slice_len, uint8_t* __restrict__ sums) {
-    __shared__ __align__(16) uint8_t sh[8][128];
-    const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+// grid (64 windows, S slices of the point range), ONE WARP per CTA; slice sums land in sums[(slice * 64 + window)].
+// Lane-strided additions, then a shuffle tree.  (CTAs of 256 threads over 1024-point slices spent most of their time
+// in the trees — 4 additions per thread, then 5 shuffle levels and 7 serial additions by one lane.)
+__global__ void __launch_bounds__(32) straus_sums_kernel(const uint8_t* __restrict__ tables,
+                                                         const int8_t* __restrict__ digits, uint32_t n,
+                                                         uint32_t slice_len, uint8_t* __restrict__ sums) {
+    const uint32_t w = blockIdx.x, lane = threadIdx.x;
     const uint32_t lo = blockIdx.y * slice_len, hi = lo + slice_len < n ? lo + slice_len : n;
     ge_p3 acc;
     ge_p3_0(acc);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
         const int d = digits[(size_t)w * n + i];
         if (d == 0) continue;
         ge_p3 t;
@@ -955,15 +956,7 @@ __global__ void __launch_bounds__(256) straus_sums_kernel(const uint8_t* __restr
         ge_add(acc, acc, t);
     }
     ge_warp_sum(acc);
-    if (nwarps > 1) {
-        if (lane == 0) ge_store(sh[warp], acc);
-        __syncthreads();
-        if (warp != 0) return;
-        if (lane < nwarps) ge_load(acc, sh[lane]);
-        else ge_p3_0(acc);
-        ge_warp_sum(acc);  // nwarps <= 8: three of the five levels add identities
-    }
-    if (threadIdx.x == 0) ge_store(sums + ((size_t)blockIdx.y * kStrausWindows + w) * 128, acc);
+    if (lane == 0) ge_store(sums + ((size_t)blockIdx.y * kStrausWindows + w) * 128, acc);
 }
 // more than one slice: one warp per window adds the slice sums up (lane = slice), result in sums[window]
 __global__ void __launch_bounds__(32) straus_slices_kernel(uint8_t* sums, uint32_t nslices) {
@@ -1241,9 +1234,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         straus_prepare_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint8_t*)d_scalars, (const uint8_t*)d_points,
                                                                           (uint32_t)n, tables, digits);
         CBP_LAUNCH_CHECK(); nl++;
-        const unsigned sthreads = n <= 256 ? 32u : (n <= 512 ? 64u : (n <= 1024 ? 128u : 256u));
         const unsigned nslices = (unsigned)((n + kStrausSlice - 1) / kStrausSlice);
-        straus_sums_kernel<<<dim3(kStrausWindows, nslices), sthreads, 0, st>>>(tables, digits, (uint32_t)n, kStrausSlice, sums);
+        straus_sums_kernel<<<dim3(kStrausWindows, nslices), 32, 0, st>>>(tables, digits, (uint32_t)n, kStrausSlice, sums);
         CBP_LAUNCH_CHECK(); nl++;
         if (nslices > 1) {
             straus_slices_kernel<<<kStrausWindows, 32, 0, st>>>(sums, nslices);
