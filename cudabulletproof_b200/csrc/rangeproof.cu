@@ -25,6 +25,7 @@
 #include <unordered_map>
 #include "../../include/cuda_bulletproof.h"
 #include "common.h"
+#include "fe8.cuh"
 #include "rangeproof.cuh"
 #include "sha256.cuh"
 
@@ -611,11 +612,127 @@ __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restri
     fe_mul(d, acc.Y, F.Z);
     flags[id] = (fe_equal(a, b) && fe_equal(c, d)) ? 1 : 0;
 }
+// ---- a handful of proofs: latency instead of throughput -------------------------------------------------------
+// The two kernels above give one (half-)warp resp. one thread to a proof: 131 dependent table additions per lane
+// (0.40 ms) and a 255-doubling chain per thread (0.51 ms) — fine with 2^14 proofs in flight, but it is all the time
+// ONE proof takes, and one proof per call is what the reference's cuda_range_proof_verify hands over
+// (complete_bulletproof_test.cu:153).  For small batches:
+//   verify_fixed_small   CTA of 1024 threads per proof: the (2n+3) x LP table additions spread over all threads
+//                        (warps 0-1: identity 1, warps 2-31: identity 2), shuffle trees, shared-memory combine
+//   verify_finish_small  CTA per (proof, identity): the 51 window sums in groups of four (13 warps side by side,
+//                        octet form), then one warp runs the Horner chain over the groups: 255 doublings and
+//                        15 additions deep at 0.52 / 0.73 us instead of 255 + 51 at 1.67 / 2.2 us
+__device__ __forceinline__ void ge_warp_tree_sum(ge_p3& v) {  // result in lane 0
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        ge_p3 other;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            other.X.v[j] = __shfl_down_sync(0xffffffffu, v.X.v[j], o);
+            other.Y.v[j] = __shfl_down_sync(0xffffffffu, v.Y.v[j], o);
+            other.Z.v[j] = __shfl_down_sync(0xffffffffu, v.Z.v[j], o);
+            other.T.v[j] = __shfl_down_sync(0xffffffffu, v.T.v[j], o);
+        }
+        ge_add(v, v, other);
+    }
+}
+__global__ void __launch_bounds__(1024) verify_fixed_small_kernel(const uint8_t* __restrict__ gens,
+                                                                  const VScal* __restrict__ vscal,
+                                                                  const int8_t* __restrict__ digits, uint32_t n,
+                                                                  uint8_t* __restrict__ fsum) {
+    __shared__ __align__(16) uint8_t sh[32][128];
+    const uint32_t p = blockIdx.x;
+    if (!vscal[p].valid) return;  // whole CTA
+    const FixTab ft = fixtab_of(gens);
+    const int LP = ft.nwin;
+    const int8_t* drow = digits + (size_t)p * kRowsMax * kFixRowBytes;
+    const int nrows2 = 2 * (int)n + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ge_p3 acc;
+    ge_p3_0(acc);
+    if (warp < 2) {  // identity 1: rows 2n+1 (g) and 2n+2 (h), bases 2n and 2n+1
+        for (int item = (int)threadIdx.x; item < 2 * LP; item += 64) {
+            const int r = item / LP, win = item % LP;
+            fixed_base_madd(acc, ft, 2 * n + (uint32_t)r, win, drow + (size_t)(nrows2 + r) * kFixRowBytes);
+        }
+    } else {  // identity 2: rows 0..2n (G_i, H_i, h with base 2n+1)
+        for (int item = (int)threadIdx.x - 64; item < nrows2 * LP; item += 960) {
+            const int r = item / LP, win = item % LP;
+            fixed_base_madd(acc, ft, r < 2 * (int)n ? (uint32_t)r : 2 * n + 1, win, drow + (size_t)r * kFixRowBytes);
+        }
+    }
+    ge_warp_tree_sum(acc);
+    if (lane == 0) ge_store(sh[warp], acc);
+    __syncthreads();
+    if (warp == 0) {  // lanes 0-1 hold identity 1's two warp sums
+        ge_p3_0(acc);
+        if (lane < 2) ge_load(acc, sh[lane]);
+        ge_warp_tree_sum(acc);
+        if (lane == 0) ge_store(fsum + ((size_t)p * 2 + 0) * 128, acc);
+    } else if (warp == 1) {  // lanes 0-29: identity 2's thirty warp sums
+        ge_p3_0(acc);
+        if (lane < 30) ge_load(acc, sh[2 + lane]);
+        ge_warp_tree_sum(acc);
+        if (lane == 0) ge_store(fsum + ((size_t)p * 2 + 1) * 128, acc);
+    }
+}
+static constexpr int kFinGroup = 4, kFinGroups = (kVarWin + kFinGroup - 1) / kFinGroup;  // 51 windows -> 13 groups
+__global__ void __launch_bounds__(32 * kFinGroups) verify_finish_small_kernel(const VScal* __restrict__ vscal,
+                                                                              const uint8_t* __restrict__ fsum,
+                                                                              const uint8_t* __restrict__ winsum,
+                                                                              uint8_t* __restrict__ flags) {
+    __shared__ __align__(16) uint8_t sh[kFinGroups][128];
+    const uint32_t id = blockIdx.x;  // proof * 2 + identity
+    if (!vscal[id >> 1].valid) {
+        if (threadIdx.x == 0) flags[id] = 0;
+        return;
+    }
+    const Fe8Lane L = fe8_lane();
+    const int warp = threadIdx.x >> 5;
+    const uint8_t* ws = winsum + (size_t)id * kVarWin * 128;
+    {  // group g = windows 4g .. 4g+3 (the top group is shorter): T_g = sum_i 2^(5 i) S_(4g+i), Horner inside the group
+        const int w0 = warp * kFinGroup, w1 = w0 + kFinGroup < kVarWin ? w0 + kFinGroup : kVarWin;
+        ge8 acc, x;
+        ge8_load(acc, ws + (size_t)(w1 - 1) * 128, L);
+#pragma unroll 1
+        for (int w = w1 - 2; w >= w0; w--) {
+#pragma unroll 1
+            for (int d = 0; d < kVarBits; d++) ge8_dbl(acc, acc, L);
+            ge8_load(x, ws + (size_t)w * 128, L);
+            ge8_add(acc, acc, x, L);
+        }
+        ge8_store(sh[warp], acc, L);
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    ge8 acc, x;
+    ge8_load(acc, sh[kFinGroups - 1], L);
+#pragma unroll 1
+    for (int g = kFinGroups - 2; g >= 0; g--) {
+#pragma unroll 1
+        for (int d = 0; d < kVarBits * kFinGroup; d++) ge8_dbl(acc, acc, L);
+        ge8_load(x, sh[g], L);
+        ge8_add(acc, acc, x, L);
+    }
+    // F == acc as projective points: X_F Z == X Z_F and Y_F Z == Y Z_F (thread-level, every lane the same values)
+    ge_p3 V, F;
+    fe8_gather(V.X, acc.X, L);
+    fe8_gather(V.Y, acc.Y, L);
+    fe8_gather(V.Z, acc.Z, L);
+    ge_load(F, fsum + (size_t)id * 128);
+    fe a, b, c, d;
+    fe_mul(a, F.X, V.Z);
+    fe_mul(b, V.X, F.Z);
+    fe_mul(c, F.Y, V.Z);
+    fe_mul(d, V.Y, F.Z);
+    if (threadIdx.x == 0) flags[id] = (fe_equal(a, b) && fe_equal(c, d)) ? 1 : 0;
+}
 __global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_t num, uint8_t* __restrict__ accept) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < num) accept[p] = flags[2 * p] & flags[2 * p + 1];
 }
 
+static constexpr uint32_t kVerifySmallBatch = 64;  // up to this many proofs per call take the latency kernels
 static constexpr size_t kVerifyChunk = 16384;  // proofs per pass (~62 KiB of scratch per proof); large passes keep the thread-per-proof kernels busy
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -788,8 +905,11 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits,
                                                            vdigits);
         CBP_CHECK_LAUNCH();
+        const bool small = cnt <= kVerifySmallBatch;  // latency path: a CTA per proof / per identity
         prof_begin(BPK_PROF_VERIFY_MSM, st);
-        if (wbits == 8)
+        if (small)
+            verify_fixed_small_kernel<<<cnt, 1024, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits, (uint32_t)n, fsum);
+        else if (wbits == 8)
             verify_fixed_kernel<8><<<(cnt * 32 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
                                                                            (uint32_t)n, cnt, fsum);
         else
@@ -800,7 +920,8 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
         verify_winsum_kernel<<<(cnt * 2 * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, vseed, k, cnt, winsum);
         CBP_CHECK_LAUNCH();
-        verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
+        if (small) verify_finish_small_kernel<<<cnt * 2, 32 * kFinGroups, 0, st>>>(vscal, fsum, winsum, flags);
+        else verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags);
         CBP_CHECK_LAUNCH();
         verify_combine_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(flags, cnt, d_accept + done);
         CBP_CHECK_LAUNCH();
