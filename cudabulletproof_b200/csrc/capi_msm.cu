@@ -177,6 +177,7 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_MSM_SMALL_MAX: o.msm_small_max = (int)value; break;
         case BPK_OPT_HOST_REGISTER: o.host_register = value != 0; break;
         case BPK_OPT_IPA_COMPOSITE_MAX: o.ipa_composite_max = (int)value; break;
+        case BPK_OPT_MSM_SEG_SHIFT: o.msm_seg_shift = (int)value; break;
         case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic
             o.ngroups = 0;
             for (int sh = 28; sh >= 0; sh -= 4) {

@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(kInvThreads) fe_batch_invert_kernel(uint8_t* _
 // operation).  Then the levels unwind: inverse of a thread's total x the stored prefixes -> the inverses.
 // 3 multiplications per element per level, levels shrink 16x: 3.2 multiplications per element overall
 // (the single-kernel version above spends 4.1 and idles 7 of 8 warps during one inversion per 4096 elements).
-static constexpr size_t kInvDirect = 1024;
+// (1024 at first: the two extra levels below 2^14 values were four launches of 4 and 64 CTAs, 90 us of pure latency
+// out of 267 us per 2^22 elements; one thread per value with the divsteps inversion takes 27 us for 2^14 of them)
+static constexpr size_t kInvDirect = (size_t)1 << 14;
 __global__ void __launch_bounds__(kInvThreads) fe_inv_forward_kernel(uint8_t* __restrict__ out,
                                                                      const uint8_t* __restrict__ in, size_t in_stride,
                                                                      size_t count, uint8_t* __restrict__ totals) {
@@ -256,6 +258,18 @@ __device__ __forceinline__ void acc_reduce_mod_l(sc& r, const Acc18& a) {
     sc_reduce512(r1, hi);
     sc_add(r, r0, r1);
 }
+// CTA-level combine of the per-thread accumulators, result valid in thread 0
+__device__ __forceinline__ void block_acc_reduce(Acc18& acc, Acc18* s_warp) {
+    acc_warp_reduce(acc);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) s_warp[wid] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        if (lane < nw) acc = s_warp[lane];
+        else acc_zero(acc);
+        acc_warp_reduce(acc);
+    }
+}
 // block-level accumulate of a[i]*b[i] over [begin, end), result valid in thread 0
 __device__ __forceinline__ void block_inner_product(Acc18& acc, const uint8_t* __restrict__ a,
                                                     const uint8_t* __restrict__ b, size_t begin, size_t end,
@@ -267,17 +281,13 @@ __device__ __forceinline__ void block_inner_product(Acc18& acc, const uint8_t* _
         fe_load_nc(y, b + i * 32);
         acc_add_product(acc, x, y);
     }
-    acc_warp_reduce(acc);
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (lane == 0) s_warp[wid] = acc;
-    __syncthreads();
-    if (wid == 0) {
-        if (lane < nw) acc = s_warp[lane];
-        else acc_zero(acc);
-        acc_warp_reduce(acc);
-    }
+    block_acc_reduce(acc, s_warp);
 }
-// stage 1: grid-stride partial sums, one 72-byte accumulator per CTA
+// stage 1: grid-stride partial sums, one 72-byte accumulator per CTA.
+// Measured and rejected (ncu: 0.55 of HBM and 50 % of the multiply pipe at once, long_scoreboard the top stall at 39 %
+// achieved occupancy, 54 registers): two elements in flight per thread in registers (spills at 64 registers: 80 -> 99 us
+// per 2^22 elements) and a three-stage cp.async pipeline through shared memory (90 us): the 16-word carry chains of the
+// 576-bit accumulation, not the loads, are what the warps wait on.
 __global__ void __launch_bounds__(256) sc_ip_partial_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                             size_t n, uint32_t* __restrict__ partials) {
     __shared__ Acc18 s_warp[8];

@@ -1032,7 +1032,12 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     // segment length: a power of two, at least 64 and at least twice the mean run length n / B
     p->seg_shift = 6;
     while (((size_t)1 << p->seg_shift) < 2 * (n / p->B + 1) && p->seg_shift < 20) p->seg_shift++;
-    int min_shift = p->seg_shift >= 6 ? p->seg_shift - 2 : 4;  // small window groups use shorter segments
+    // 2^15 < n <= 2^17: the accumulation launches are partial waves of latency-bound threads; segments of 16 put 4x
+    // the threads on the machine (tools/probe_seg.py, c = 15, ms with 64 / 16: 2^16 0.535 / 0.508, 2^17 0.659 / 0.624,
+    // 2^18 0.820 / 0.961, 2^14 0.435 / 0.441)
+    if (n > ((size_t)1 << 15) && n <= ((size_t)1 << 17) && p->seg_shift == 6) p->seg_shift = 4;
+    if (const int o = options().msm_seg_shift; o >= 2 && o <= 20) p->seg_shift = o;  // measurement switch
+    int min_shift = p->seg_shift >= 6 ? p->seg_shift - 2 : (p->seg_shift >= 4 ? 4 : p->seg_shift);  // small window groups use shorter segments
     p->max_segs = (size_t)p->nbuckets + ((n * (size_t)p->W) >> min_shift) + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -1185,7 +1190,7 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
             if (nwin <= 1) shift -= 2;
             else if (nwin <= 3) shift -= 1;
         }
-        if (shift < 4) shift = 4;
+        if (shift < 4) shift = seg_shift < 4 ? seg_shift : 4;
         for (int w = gm->w_lo[g]; w <= gm->w_hi[g]; w++) {
             gm->group_of_window[w] = (uint8_t)g;
             gm->seg_shift_of_window[w] = (uint8_t)shift;
