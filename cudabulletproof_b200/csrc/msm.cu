@@ -1132,6 +1132,10 @@ StreamKit* stream_kit(int dev, int idx) {
 }
 }  // namespace
 
+// Measured (round 2, tools/probe_groups_phases.py, 2^20): the accumulation span plus the exposed tail is the same
+// ~1.52 ms for every grouping (8,4,2,2: 1.38 + 0.14; 8,4,4: 1.25 + 0.25; 12,4: 1.21 + 0.31; 15,1: 1.23 + 0.30) and also
+// with the reduction / chain streams at the highest stream priority (8,4,4: 1.34 + 0.17): the bucket sums, the
+// reductions and the chain add up to a fixed amount of multiply-pipe time, the schedule only moves it around.
 // Measured and rejected: sorting the lower half of the windows on a side stream while the upper half is being
 // accumulated.  The exposed front end shrinks (0.50 -> 0.34 ms) but the accumulation, whose table gathers
 // share the L2 with the sort's atomics, slows down by the same amount (1.48 -> 1.69 ms): 2.29 ms either way.
