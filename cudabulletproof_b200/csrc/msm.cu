@@ -1142,7 +1142,8 @@ StreamKit* stream_kit(int dev, int idx) {
 // windows are processed top-down in groups of halving size (.., 4, 2, 2): while the lower groups are
 // still being accumulated, the upper groups are reduced and folded into the Horner chain on a second
 // stream, so only the last (single-window) group's reduction latency is exposed.
-static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline, int last_max) {
+static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline, int last_max,
+                        const int* preset = nullptr, int npreset = 0) {
     gm->ngroups = 0;
     gm->log2B = c - 1;
     int hi = W - 1;
@@ -1156,11 +1157,13 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
         // group (ms at 2^20 / 2^22): 8,4,2,2 1.97 / 6.58; 8,4,4 2.03 / 6.36; 10,4,2 2.01 / 6.42; 9,4,3 2.01 / 6.40;
         // 10,3,3 2.02 / 6.47; 11,3,2 2.02 / 6.44; 12,4 2.02 / 6.38; 10,6 2.02 / 6.41.
         const Options& opt = options();
+        const int* glist = opt.ngroups ? opt.groups : preset;
+        const int nlist = opt.ngroups ? opt.ngroups : npreset;
         int gi = 0;
         while (remaining > 0) {
             int take = remaining > 1 ? remaining / 2 : 1;
-            if (gi < opt.ngroups) {
-                int v = opt.groups[gi++];
+            if (gi < nlist) {
+                int v = glist[gi++];
                 if (v >= 1 && v <= remaining && gm->ngroups < kMaxGroups - 1) {
                     gm->w_hi[gm->ngroups] = hi;
                     gm->w_lo[gm->ngroups] = hi - v + 1;
@@ -1269,7 +1272,12 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     // the last group's reduction is exposed: 16 windows go as 8, 4, 2, 2 up to 2^20 points and as 8, 4, 4 above
     // (measured with the 2-D reduction on every group, 8,4,2,2 / 8,4,4: 2^19 1.30 / 1.31 ms, 2^20 2.00 / 2.03,
     // 2^22 6.65 / 6.43)
-    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 21) ? 4 : 3);
+    // Round 2, with the octet-form chain and the divsteps inversion (tools/probe_groups_phases.py, ms): 2^20 8,4,2,2 1.919,
+    // 8,4,4 1.896, 8,8 1.918; 2^22 8,4,4 6.48, 8,8 6.30, 15,1 6.32 — two groups of eight from 2^21 points.
+    static const int kTwoEights[2] = {8, 8};
+    const bool two_eights = p.W == 16 && n >= ((size_t)1 << 21);
+    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 20) ? 4 : 3, two_eights ? kTwoEights : nullptr,
+                two_eights ? 2 : 0);
 
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
