@@ -44,6 +44,7 @@ Options& options() {
         opt.prover_legacy = getenv("CBP_PROVER_LEGACY") ? 1 : 0;
         opt.msm_small_max = num("CBP_MSM_SMALL_MAX", -1);
         opt.host_register = num("CBP_HOST_REGISTER", 0);
+        opt.msm_acc_streams = num("CBP_MSM_ACC_STREAMS", -1);
         if (const char* g = getenv("CBP_GROUPS")) {
             while (*g && opt.ngroups < 8) {
                 int v = atoi(g);
@@ -178,6 +179,7 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_HOST_REGISTER: o.host_register = value != 0; break;
         case BPK_OPT_IPA_COMPOSITE_MAX: o.ipa_composite_max = (int)value; break;
         case BPK_OPT_MSM_SEG_SHIFT: o.msm_seg_shift = (int)value; break;
+        case BPK_OPT_MSM_ACC_STREAMS: o.msm_acc_streams = (int)value; break;
         case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic
             o.ngroups = 0;
             for (int sh = 28; sh >= 0; sh -= 4) {

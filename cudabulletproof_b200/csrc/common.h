@@ -50,6 +50,7 @@ struct Options {
     int msm_small_max = -1;   // CBP_MSM_SMALL_MAX: largest n taken by the single-launch small-n MSM (-1 default)
     int ipa_composite_max = -1;  // largest vector length whose IPA rounds run unfolded (-1: default 4096; tests lower it)
     int msm_seg_shift = -1;   // log2 of the accumulation segment length (-1: max(64, 2 * mean run)); measurements
+    int msm_acc_streams = -1; // accumulation of every window group on its own stream (see msm_run); -1 auto, 0 / 1
     int host_register = 0;    // CBP_HOST_REGISTER: 1 = page-lock large pageable caller buffers once and remember them
 };
 Options& options();

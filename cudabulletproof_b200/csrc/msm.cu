@@ -1109,7 +1109,7 @@ struct StreamKit {
     cudaStream_t red[kMaxGroups] = {};  // one reduction stream per window group: group tails overlap each other
     cudaStream_t aux = nullptr;         // the Horner chain, in group order
     cudaEvent_t ev_group[kMaxGroups] = {}, ev_red[kMaxGroups] = {};
-    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_front = nullptr;
     bool ok = false;
 };
 StreamKit g_kits[kMaxDevices][kMsmKits];
@@ -1118,14 +1118,21 @@ StreamKit* stream_kit(int dev, int idx) {
     if (dev < 0 || dev >= kMaxDevices || idx < 0 || idx >= kMsmKits) return nullptr;
     StreamKit& k = g_kits[dev][idx];
     if (!k.ok) {
-        if (cudaStreamCreateWithFlags(&k.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        // Group streams carry descending priorities (group 0 = top windows first): with the accumulations of all
+        // groups in flight at once (msm_run), the block scheduler drains them in pipeline order and a group's
+        // reduction outranks the accumulation of the groups below it.  The Horner chain is the critical path.
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&k.aux, cudaStreamNonBlocking, greatest) != cudaSuccess) return nullptr;
         for (int i = 0; i < kMaxGroups; i++) {
-            if (cudaStreamCreateWithFlags(&k.red[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            int prio = greatest + i < least ? greatest + i : least;
+            if (cudaStreamCreateWithPriority(&k.red[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
             if (cudaEventCreateWithFlags(&k.ev_group[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
             if (cudaEventCreateWithFlags(&k.ev_red[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
         if (cudaEventCreateWithFlags(&k.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&k.ev_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&k.ev_front, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         k.ok = true;
     }
     return &k;
@@ -1269,15 +1276,24 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     // a chunk that only adds into the buckets has no tails to overlap: one group, everything on `st`
     StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(dlock.dev, kit_index) : nullptr;
     GroupMap gm;
-    // the last group's reduction is exposed: 16 windows go as 8, 4, 2, 2 up to 2^20 points and as 8, 4, 4 above
-    // (measured with the 2-D reduction on every group, 8,4,2,2 / 8,4,4: 2^19 1.30 / 1.31 ms, 2^20 2.00 / 2.03,
-    // 2^22 6.65 / 6.43)
-    // Round 2, with the octet-form chain and the divsteps inversion (tools/probe_groups_phases.py, ms): 2^20 8,4,2,2 1.919,
-    // 8,4,4 1.896, 8,8 1.918; 2^22 8,4,4 6.48, 8,8 6.30, 15,1 6.32 — two groups of eight from 2^21 points.
-    static const int kTwoEights[2] = {8, 8};
-    const bool two_eights = p.W == 16 && n >= ((size_t)1 << 21);
-    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 20) ? 4 : 3, two_eights ? kTwoEights : nullptr,
-                two_eights ? 2 : 0);
+    // Window groups.  With every group's accumulation on its own stream (below) the grouping no longer costs
+    // multiply-pipe utilisation — a small group's partial last wave is filled by the next group's blocks — so from
+    // 2^19 points the windows go in pairs (the last group's reduction, the exposed tail, is then the smallest):
+    // tools/probe_groups_phases.py, ms per MSM, groups in turn on one stream / all at once on their own streams:
+    //   2^20  8,4,4 1.917 / 1.894   8,4,2,2 1.947 / 1.892   4,4,4,4 2.050 / 1.859   2 x 8 2.311 / 1.829
+    //   2^22  8,8 6.282 / 6.219     8,4,4 6.473 / 6.200     2 x 8 - / 6.143          2^19  9,4,3 1.196   2 x 8 1.138
+    // Below 2^19 points (c = 15, 18 windows) every grouping measures the same within 2 % (2^16 0.52-0.53 ms, 2^17
+    // 0.63-0.64, 2^18 0.81-0.83): those calls are bound by the chain front end -> top group -> its reduction -> 270
+    // doublings of the window combine, not by the accumulation.
+    static const int kPairs[kMaxGroups] = {2, 2, 2, 2, 2, 2, 2, 2};
+    int pairs[kMaxGroups];
+    int npairs = 0;
+    if (p.W >= 4 && p.W <= 2 * kMaxGroups && n >= ((size_t)1 << 19) && options().msm_acc_streams != 0) {
+        npairs = (p.W + 1) / 2;
+        for (int i = 0; i < npairs; i++) pairs[i] = kPairs[i];
+        if (p.W & 1) pairs[0] = 3;
+    }
+    make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 20) ? 4 : 3, npairs ? pairs : nullptr, npairs);
 
     prof_begin(BPK_PROF_MSM_TOTAL, st);
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
@@ -1344,24 +1360,35 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     if (kit) {  // join the table build (side stream) before the first accumulation
         if ((e = cudaStreamWaitEvent(st, kit->ev_ready, 0)) != cudaSuccess) return (int)e;
     }
+    // Accumulation of the groups: in turn on `st` (each group's tail forks off behind its accumulation), or — the
+    // groups touch disjoint buckets — all at once, every group on its own stream ahead of its own tail: the next
+    // group's thread blocks then fill the SMs while the previous launch drains (no partial last wave per group),
+    // and the stream priorities keep the pipeline order.
+    const int acc_opt = options().msm_acc_streams;
+    const bool acc_streams = kit != nullptr && gm.ngroups > 1 && (acc_opt < 0 ? true : acc_opt != 0);
+    if (acc_streams && (e = cudaEventRecord(kit->ev_front, st)) != cudaSuccess) return (int)e;
     for (int g = 0; g < gm.ngroups; g++) {
         cudaStream_t tail = kit ? kit->red[g] : st;
+        cudaStream_t as = acc_streams ? tail : st;
         int nwin = gm.w_hi[g] - gm.w_lo[g] + 1, w_lo = gm.w_lo[g];
         // upper bound on this group's segments: its buckets + its share of the entries
         const int gshift = gm.seg_shift_of_window[w_lo];
         size_t seg_bound = (size_t)nwin * p.B + ((n * (size_t)nwin) >> gshift) + 1;
         if (g == 0) prof_begin(BPK_PROF_MSM_ACCUMULATE, st);
-        msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, st>>>(table, entries, desc, ends, segoff,
+        if (acc_streams && (e = cudaStreamWaitEvent(as, kit->ev_front, 0)) != cudaSuccess) return (int)e;
+        msm_accumulate_kernel<<<(unsigned)((seg_bound + 127) / 128), 128, 0, as>>>(table, entries, desc, ends, segoff,
                                                                                   gm, order, binstart, g, carry,
                                                                                   buckets, segsums);
+        CBP_LAUNCH_CHECK(); nl++;
+        if (kit) {
+            if ((e = cudaEventRecord(kit->ev_group[g], as)) != cudaSuccess) return (int)e;
+            if (acc_streams) {  // `st` follows every accumulation: the phase timers below, and nothing else, run on it
+                if ((e = cudaStreamWaitEvent(st, kit->ev_group[g], 0)) != cudaSuccess) return (int)e;
+            } else if ((e = cudaStreamWaitEvent(tail, kit->ev_group[g], 0)) != cudaSuccess) return (int)e;
+        }
         if (g == gm.ngroups - 1) {
             prof_end(BPK_PROF_MSM_ACCUMULATE, st);
             prof_begin(BPK_PROF_MSM_TAIL, st);
-        }
-        CBP_LAUNCH_CHECK(); nl++;
-        if (kit) {
-            if ((e = cudaEventRecord(kit->ev_group[g], st)) != cudaSuccess) return (int)e;
-            if ((e = cudaStreamWaitEvent(tail, kit->ev_group[g], 0)) != cudaSuccess) return (int)e;
         }
         size_t heavy_bound = ((n * (size_t)nwin) >> gshift) + 1;
         if (heavy_bound > (size_t)nwin * p.B) heavy_bound = (size_t)nwin * p.B;
