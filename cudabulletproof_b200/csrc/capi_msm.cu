@@ -2,6 +2,8 @@
 // drop-ins cuda_point_vector_multi_scalar_mul{,_shared} (reference cuda_bulletproof_kernels.cu:62-207).
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -44,6 +46,7 @@ Options& options() {
         opt.prover_legacy = getenv("CBP_PROVER_LEGACY") ? 1 : 0;
         opt.msm_small_max = num("CBP_MSM_SMALL_MAX", -1);
         opt.host_register = num("CBP_HOST_REGISTER", 0);
+        opt.host_taper_log2 = num("CBP_HOST_TAPER_LOG2", 0);
         opt.msm_acc_streams = num("CBP_MSM_ACC_STREAMS", -1);
         if (const char* g = getenv("CBP_GROUPS")) {
             while (*g && opt.ngroups < 8) {
@@ -180,6 +183,8 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_IPA_COMPOSITE_MAX: o.ipa_composite_max = (int)value; break;
         case BPK_OPT_MSM_SEG_SHIFT: o.msm_seg_shift = (int)value; break;
         case BPK_OPT_MSM_ACC_STREAMS: o.msm_acc_streams = (int)value; break;
+        case BPK_OPT_HOST_TRACE: o.host_trace = value != 0; break;
+        case BPK_OPT_HOST_TAPER_LOG2: o.host_taper_log2 = (value >= 10 && value <= 30) ? (int)value : 0; break;
         case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic
             o.ngroups = 0;
             for (int sh = 28; sh >= 0; sh -= 4) {
@@ -265,14 +270,16 @@ namespace {
 // n = 2^20: a mid-size MSM is latency-bound, ~1.4 ms — hence the shared buckets)
 constexpr size_t kHostChunk = (size_t)1 << 17;
 constexpr size_t kHostChunkMin = (size_t)1 << 20;  // below this a single MSM (scalars first) is faster
-constexpr int kMaxChunks = 4096;
+constexpr int kMaxChunks = 64;  // every chunk keeps its sorted scalars (a front workspace) until its points arrive
 struct HostPath {
     uint8_t *d_s = nullptr, *d_p = nullptr, *d_r = nullptr;
     uint8_t* d_ws[1] = {};
-    size_t cap_s = 0, cap_p = 0, cap_ws[1] = {};
-    cudaStream_t main = nullptr, copy = nullptr;
+    uint8_t* d_front = nullptr;  // chunked path: the sorted scalars (front part of the MSM workspace) of every chunk
+    size_t cap_s = 0, cap_p = 0, cap_ws[1] = {}, cap_front = 0;
+    static constexpr int kFrontStreams = 4;  // the chunks' sorts are chains of small launches: several run side by side
+    cudaStream_t main = nullptr, copy = nullptr, front[kFrontStreams] = {};
     cudaEvent_t ev_points = nullptr;
-    std::vector<cudaEvent_t> ev_chunk;
+    std::vector<cudaEvent_t> ev_chunk, ev_scalars, ev_front;
     uint8_t* stage[2] = {};      // pinned staging buffers for pageable inputs (one chunk of scalars + points each)
     size_t cap_stage = 0;
     cudaEvent_t ev_stage[2] = {};  // the copy out of a staging buffer has finished
@@ -393,6 +400,39 @@ cudaError_t grow(uint8_t** p, size_t* cap, size_t need) {
 }
 }  // namespace
 
+// Timeline of one chunked call (BPK_OPT_HOST_TRACE, measurements only): events on the copy / sort / bucket streams,
+// printed relative to the first one after the call has been synchronised.
+namespace {
+struct TracePoint {
+    const char* what;
+    size_t chunk;
+    cudaEvent_t ev;
+    double host_us;
+};
+std::vector<TracePoint> g_trace;
+std::chrono::steady_clock::time_point g_trace_t0;
+void trace_mark(const char* what, size_t chunk, cudaStream_t st) {
+    if (!options().host_trace) return;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (g_trace.empty()) g_trace_t0 = std::chrono::steady_clock::now();
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    g_trace.push_back({what, chunk, ev, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - g_trace_t0).count()});
+}
+void trace_dump() {
+    if (g_trace.empty()) return;
+    for (const TracePoint& t : g_trace) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_trace[0].ev, t.ev);
+        fprintf(stderr, "[host-trace] %-12s chunk %2zu  gpu %8.3f ms   enqueued at %8.3f ms\n", t.what, t.chunk, ms, t.host_us / 1e3);
+    }
+    for (const TracePoint& t : g_trace) cudaEventDestroy(t.ev);
+    g_trace.clear();
+}
+}  // namespace
+
 static int msm_host(ge25519* result, const FieldVector* scalars, const PointVector* points) {
     size_t n = scalars->length;
     DeviceLock dlock;
@@ -400,7 +440,15 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
     HostPath& hp = g_hp[dlock.dev];
     cudaError_t e;
     if (!hp.ok) {
-        if ((e = cudaStreamCreateWithFlags(&hp.main, cudaStreamNonBlocking)) != cudaSuccess ||
+        // the scalar-side sorts of the chunked path (hp.front) have slack, the bucket sums behind each arriving chunk
+        // of points (hp.main) do not
+        int least = 0, greatest = 0;
+        if ((e = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+        if ((e = cudaStreamCreateWithPriority(&hp.main, cudaStreamNonBlocking, least > greatest ? least - 1 : least)) != cudaSuccess ||
+            (e = cudaStreamCreateWithPriority(&hp.front[0], cudaStreamNonBlocking, least)) != cudaSuccess ||
+            (e = cudaStreamCreateWithPriority(&hp.front[1], cudaStreamNonBlocking, least)) != cudaSuccess ||
+            (e = cudaStreamCreateWithPriority(&hp.front[2], cudaStreamNonBlocking, least)) != cudaSuccess ||
+            (e = cudaStreamCreateWithPriority(&hp.front[3], cudaStreamNonBlocking, least)) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&hp.ev_points, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaMalloc(&hp.d_r, 256)) != cudaSuccess)
@@ -442,20 +490,51 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
             nchunks = (n + chunk - 1) / chunk;
         }
         // every chunk adds into the SAME buckets (window width of the whole input, one workspace laid out for
-        // a full chunk); only the last chunk runs the bucket reduction and the window combine
-        MsmPlan p_full, p_last;
+        // a full chunk); only the last chunk runs the bucket reduction and the window combine.  The scalars travel
+        // first (a fifth of the bytes): every chunk's scalar side — digit recoding, bucket sort, segments — then runs
+        // on its own stream while the points are still on the wire, into a front workspace of its own, and what is
+        // left behind an arriving chunk of points is the affine table and the bucket sums (measured at 2^20 pairs from
+        // pinned memory, PCIe floor 3.0 ms: sort behind each chunk 3.95 ms, sorts ahead 3.5 ms).
+        MsmPlan p_full;
         msm_make_plan(&p_full, chunk, msm_pick_window(n));
-        p_last = p_full;
-        p_last.n = n - (nchunks - 1) * chunk;
-        if ((e = grow(&hp.d_ws[0], &hp.cap_ws[0], p_full.workspace_bytes)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
-        while (hp.ev_chunk.size() < nchunks) {
-            cudaEvent_t ev;
-            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
-            hp.ev_chunk.push_back(ev);
+        // chunk boundaries; the last chunk — the only one whose bucket sums are not hidden under a copy — is halved
+        // down to 2^host_taper_log2 points (its sort is off the critical path now, so small chunks cost little)
+        std::vector<size_t> lo_of, cnt_of;
+        for (size_t c = 0, lo = 0; c < nchunks; c++) {
+            size_t cnt = n - lo < chunk ? n - lo : chunk;
+            if (c + 1 == nchunks) {
+                const size_t floor_sz = (size_t)1 << options().host_taper_log2;
+                while (options().host_taper_log2 > 0 && cnt >= 2 * floor_sz && lo_of.size() + 2 < (size_t)kMaxChunks + 32) {
+                    lo_of.push_back(lo);
+                    cnt_of.push_back(cnt - cnt / 2);
+                    lo += cnt - cnt / 2;
+                    cnt = cnt / 2;
+                }
+            }
+            lo_of.push_back(lo);
+            cnt_of.push_back(cnt);
+            lo += cnt;
         }
-        // pageable inputs go through two pinned staging buffers, filled by the copy pool while the previous chunk
+        nchunks = lo_of.size();
+        auto plan_of = [&](size_t c) {
+            MsmPlan q = p_full;
+            q.n = cnt_of[c];
+            return q;
+        };
+        const size_t front_bytes = (msm_front_bytes(p_full) + 255) & ~(size_t)255;
+        if ((e = grow(&hp.d_ws[0], &hp.cap_ws[0], p_full.workspace_bytes)) != cudaSuccess ||
+            (e = grow(&hp.d_front, &hp.cap_front, front_bytes * nchunks)) != cudaSuccess)
+            return fail(BPK_ERR_CUDA, e);
+        for (std::vector<cudaEvent_t>* pool : {&hp.ev_chunk, &hp.ev_scalars, &hp.ev_front})
+            while (pool->size() < nchunks) {
+                cudaEvent_t ev;
+                if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+                pool->push_back(ev);
+            }
+        // pageable inputs go through two pinned staging buffers, filled by the copy pool while the previous piece
         // is on the wire
-        if (staged && hp.cap_stage < chunk * 160) {
+        const size_t stage_bytes = chunk * 128;
+        if (staged && hp.cap_stage < stage_bytes) {
             for (int b = 0; b < 2; b++) {
                 if (hp.stage[b]) cudaFreeHost(hp.stage[b]);
                 hp.stage[b] = nullptr;
@@ -463,38 +542,108 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
                     return fail(BPK_ERR_CUDA, e);
             }
             hp.cap_stage = 0;
-            if ((e = cudaMallocHost(&hp.stage[0], chunk * 160)) != cudaSuccess ||
-                (e = cudaMallocHost(&hp.stage[1], chunk * 160)) != cudaSuccess)
+            if ((e = cudaMallocHost(&hp.stage[0], stage_bytes)) != cudaSuccess ||
+                (e = cudaMallocHost(&hp.stage[1], stage_bytes)) != cudaSuccess)
                 return fail(BPK_ERR_CUDA, e);
-            hp.cap_stage = chunk * 160;
+            hp.cap_stage = stage_bytes;
         }
-        for (size_t c = 0; c < nchunks; c++) {
-            const bool last = c + 1 == nchunks;
-            const size_t lo = c * chunk, cnt = last ? p_last.n : chunk;
-            const uint8_t *src_s = h_s + lo * 32, *src_p = h_p + lo * 128;
-            if (staged) {
-                uint8_t* buf = hp.stage[c & 1];
-                if (c >= 2 && (e = cudaEventSynchronize(hp.ev_stage[c & 1])) != cudaSuccess) return fail(BPK_ERR_CUDA, e);
-                g_copy_pool.copy(buf, src_s, cnt * 32);
-                g_copy_pool.copy(buf + cnt * 32, src_p, cnt * 128);
-                src_s = buf;
-                src_p = buf + cnt * 32;
+        size_t pieces = 0;  // staging pieces issued so far (they alternate between the two buffers)
+        auto upload = [&](uint8_t* dst, const uint8_t* src, size_t bytes) -> cudaError_t {
+            if (!staged) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, hp.copy);
+            for (size_t off = 0; off < bytes; off += hp.cap_stage, pieces++) {
+                const size_t len = bytes - off < hp.cap_stage ? bytes - off : hp.cap_stage;
+                uint8_t* buf = hp.stage[pieces & 1];
+                cudaError_t r;
+                if (pieces >= 2 && (r = cudaEventSynchronize(hp.ev_stage[pieces & 1])) != cudaSuccess) return r;
+                g_copy_pool.copy(buf, src + off, len);
+                if ((r = cudaMemcpyAsync(dst + off, buf, len, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
+                    (r = cudaEventRecord(hp.ev_stage[pieces & 1], hp.copy)) != cudaSuccess)
+                    return r;
             }
-            if ((e = cudaMemcpyAsync(hp.d_s + lo * 32, src_s, cnt * 32, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(hp.d_p + lo * 128, src_p, cnt * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
-                (staged && (e = cudaEventRecord(hp.ev_stage[c & 1], hp.copy)) != cudaSuccess) ||
-                (e = cudaEventRecord(hp.ev_chunk[c], hp.copy)) != cudaSuccess ||
-                (e = cudaStreamWaitEvent(hp.main, hp.ev_chunk[c], 0)) != cudaSuccess)
-                return fail(BPK_ERR_CUDA, e);
+            return cudaSuccess;
+        };
+        auto chunk_flags = [&](size_t c) { return (c > 0 ? kMsmCarryIn : 0) | (c + 1 == nchunks ? 0 : kMsmNoTail); };
+        // Enqueue order.  From pinned memory every copy is queued before the first kernel (the launches of a sort
+        // take the host ~60 us per chunk, which would otherwise delay the point copies behind them); staged pieces
+        // are copied by the calling thread, so there the sorts are queued between the scalars and the points and
+        // each chunk's bucket sums right behind its points.
+        auto copy_scalars = [&](size_t c) -> cudaError_t {
+            cudaError_t r;
+            if (c == 0) trace_mark("start", 0, hp.copy);
+            if ((r = upload(hp.d_s + lo_of[c] * 32, h_s + lo_of[c] * 32, cnt_of[c] * 32)) != cudaSuccess) return r;
+            return cudaEventRecord(hp.ev_scalars[c], hp.copy);
+        };
+        auto copy_points = [&](size_t c) -> cudaError_t {
+            cudaError_t r;
+            if ((r = upload(hp.d_p + lo_of[c] * 128, h_p + lo_of[c] * 128, cnt_of[c] * 128)) != cudaSuccess) return r;
+            r = cudaEventRecord(hp.ev_chunk[c], hp.copy);
+            trace_mark("points-in", c, hp.copy);
+            return r;
+        };
+        // the scalar side of chunk c on one of the hp.front streams (it cannot overtake work of an earlier call that still reads the
+        // front workspaces: every call ends with a synchronisation)
+        auto sort_chunk = [&](size_t c) -> int {
+            cudaError_t r;
+            cudaStream_t fs = hp.front[c % HostPath::kFrontStreams];
+            if ((r = cudaStreamWaitEvent(fs, hp.ev_scalars[c], 0)) != cudaSuccess) return (int)r;
             int nl = 0;
-            int flags = (c > 0 ? kMsmCarryIn : 0) | (last ? 0 : kMsmNoTail);
-            int rc = msm_run(last ? p_last : p_full, hp.d_s + lo * 32, hp.d_p + lo * 128, hp.d_r, hp.d_ws[0], 1, hp.main, &nl,
-                             nullptr, 0, flags);
+            int rc = msm_run(plan_of(c), hp.d_s + lo_of[c] * 32, nullptr, hp.d_r, hp.d_ws[0], 1, fs, &nl, nullptr, 0,
+                             chunk_flags(c) | kMsmFrontOnly, hp.d_front + c * front_bytes);
             launches += nl;
-            if (rc) {
-                count_launches(launches);
-                return fail_cuda(rc);
-            }
+            if (rc == 0) rc = (int)cudaEventRecord(hp.ev_front[c], fs);
+            trace_mark("sorted", c, fs);
+            return rc;
+        };
+        // table and bucket sums of chunk c on hp.main; behind the last chunk the reduction and the window combine
+        auto sum_chunk = [&](size_t c) -> int {
+            cudaError_t r;
+            if ((r = cudaStreamWaitEvent(hp.main, hp.ev_chunk[c], 0)) != cudaSuccess ||
+                (r = cudaStreamWaitEvent(hp.main, hp.ev_front[c], 0)) != cudaSuccess)
+                return (int)r;
+            int nl = 0;
+            int rc = msm_run(plan_of(c), hp.d_s + lo_of[c] * 32, hp.d_p + lo_of[c] * 128, hp.d_r, hp.d_ws[0], 1, hp.main, &nl,
+                             nullptr, 0, chunk_flags(c) | kMsmBackOnly, hp.d_front + c * front_bytes);
+            launches += nl;
+            trace_mark("summed", c, hp.main);
+            return rc;
+        };
+        int rc = 0;
+        if (!staged) {
+            for (size_t c = 0; c < nchunks && rc == 0; c++) rc = (int)copy_scalars(c);
+            for (size_t c = 0; c < nchunks && rc == 0; c++) rc = (int)copy_points(c);
+            for (size_t c = 0; c < nchunks && rc == 0; c++) rc = sort_chunk(c);
+            for (size_t c = 0; c < nchunks && rc == 0; c++) rc = sum_chunk(c);
+        } else {
+            // a helper thread feeds the staging buffers (scalars, then points) while this thread queues the kernels; a
+            // kernel may only be made to wait for an event that has been recorded, hence the progress counter
+            std::atomic<size_t> uploaded{0};
+            std::atomic<int> upload_rc{0};
+            const int dev = dlock.dev;
+            std::thread feeder([&] {
+                cudaError_t r = cudaSetDevice(dev);
+                for (size_t u = 0; u < 2 * nchunks && r == cudaSuccess; u++) {
+                    r = u < nchunks ? copy_scalars(u) : copy_points(u - nchunks);
+                    if (r == cudaSuccess) uploaded.store(u + 1, std::memory_order_release);
+                }
+                if (r != cudaSuccess) {
+                    upload_rc.store((int)r);
+                    uploaded.store(2 * nchunks, std::memory_order_release);  // let the waiting thread go; it checks upload_rc
+                }
+            });
+            auto wait_for = [&](size_t units) {
+                while (uploaded.load(std::memory_order_acquire) < units) std::this_thread::yield();
+                return upload_rc.load();
+            };
+            for (size_t c = 0; c < nchunks && rc == 0; c++)
+                if ((rc = wait_for(c + 1)) == 0) rc = sort_chunk(c);
+            for (size_t c = 0; c < nchunks && rc == 0; c++)
+                if ((rc = wait_for(nchunks + c + 1)) == 0) rc = sum_chunk(c);
+            feeder.join();
+            if (rc == 0) rc = upload_rc.load();
+        }
+        if (rc) {
+            count_launches(launches);
+            return fail_cuda(rc);
         }
         count_launches(launches);
     }
@@ -502,6 +651,7 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
     e = cudaMemcpyAsync(&tmp, hp.d_r, 128, cudaMemcpyDeviceToHost, hp.main);
     if (e == cudaSuccess) e = cudaStreamSynchronize(hp.main);
     if (e != cudaSuccess) return fail(BPK_ERR_CUDA, e);
+    trace_dump();
     *result = tmp;
     return BPK_OK;
 }

@@ -51,6 +51,8 @@ struct Options {
     int ipa_composite_max = -1;  // largest vector length whose IPA rounds run unfolded (-1: default 4096; tests lower it)
     int msm_seg_shift = -1;   // log2 of the accumulation segment length (-1: max(64, 2 * mean run)); measurements
     int msm_acc_streams = -1; // accumulation of every window group on its own stream (see msm_run); -1 auto, 0 / 1
+    int host_taper_log2 = 0;  // chunked host path: the last chunk is halved down to 2^this points (0: not at all)
+    int host_trace = 0;       // chunked host path: print the timeline of every call to stderr (measurements)
     int host_register = 0;    // CBP_HOST_REGISTER: 1 = page-lock large pageable caller buffers once and remember them
 };
 Options& options();

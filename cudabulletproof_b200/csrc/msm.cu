@@ -1214,22 +1214,24 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
 
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
-            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index, int flags) {
+            int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index, int flags,
+            void* d_front_ws) {
     uint8_t* ws = (uint8_t*)d_ws;
-    uint8_t* table = ws + p.off_table;
-    uint32_t* counts = (uint32_t*)(ws + p.off_counts);
-    uint32_t* offsets = (uint32_t*)(ws + p.off_offsets);
-    uint32_t* cursors = (uint32_t*)(ws + p.off_cursors);
-    uint32_t* tiles = (uint32_t*)(ws + p.off_tiles);
-    uint32_t* segoff = (uint32_t*)(ws + p.off_segoff);
-    uint2* desc = (uint2*)(ws + p.off_desc);
-    uint32_t* order = (uint32_t*)(ws + p.off_order);
-    uint32_t* bins = (uint32_t*)(ws + p.off_bins);
+    uint8_t* fw = d_front_ws ? (uint8_t*)d_front_ws : ws;  // front part: everything the scalar side produces + the table
+    uint8_t* table = fw + p.off_table;
+    uint32_t* counts = (uint32_t*)(fw + p.off_counts);
+    uint32_t* offsets = (uint32_t*)(fw + p.off_offsets);
+    uint32_t* cursors = (uint32_t*)(fw + p.off_cursors);
+    uint32_t* tiles = (uint32_t*)(fw + p.off_tiles);
+    uint32_t* segoff = (uint32_t*)(fw + p.off_segoff);
+    uint2* desc = (uint2*)(fw + p.off_desc);
+    uint32_t* order = (uint32_t*)(fw + p.off_order);
+    uint32_t* bins = (uint32_t*)(fw + p.off_bins);
     uint32_t* binstart = bins + kSegBins;
     uint32_t* heavy_cnt = binstart + kSegBins + 1;
     uint32_t* overflow = heavy_cnt + kMaxGroups;
-    uint32_t* heavy = (uint32_t*)(ws + p.off_heavy);
-    uint32_t* entries = (uint32_t*)(ws + p.off_entries);
+    uint32_t* heavy = (uint32_t*)(fw + p.off_heavy);
+    uint32_t* entries = (uint32_t*)(fw + p.off_entries);
     uint8_t* buckets = ws + p.off_buckets;
     uint8_t* segsums = ws + p.off_segsums;
     uint8_t* winX = ws + p.off_winX;
@@ -1273,8 +1275,13 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     // the side streams and events of a kit are shared by every call on this device: serialise the enqueue
     DeviceLock dlock;
     if (!dlock.ok()) return (int)cudaErrorInvalidDevice;
+    const bool do_front = !(flags & kMsmBackOnly), do_back = !(flags & kMsmFrontOnly);
     // a chunk that only adds into the buckets has no tails to overlap: one group, everything on `st`
-    StreamKit* kit = (n >= (1u << 15) && !no_tail) ? stream_kit(dlock.dev, kit_index) : nullptr;
+    // (a front-only call and its back-only call pass the same kMsmNoTail: the window groups shape the segments)
+    // (the last chunk of a chunked input may be small, but its tail reduces the buckets of the whole input)
+    const bool pipeline = (n >= (1u << 15) || carry) && !no_tail;
+    StreamKit* kit = pipeline ? stream_kit(dlock.dev, kit_index) : nullptr;
+    if (pipeline && !kit) return (int)cudaErrorInitializationError;
     GroupMap gm;
     // Window groups.  With every group's accumulation on its own stream (below) the grouping no longer costs
     // multiply-pipe utilisation — a small group's partial last wave is filled by the next group's blocks — so from
@@ -1288,7 +1295,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     static const int kPairs[kMaxGroups] = {2, 2, 2, 2, 2, 2, 2, 2};
     int pairs[kMaxGroups];
     int npairs = 0;
-    if (p.W >= 4 && p.W <= 2 * kMaxGroups && n >= ((size_t)1 << 19) && options().msm_acc_streams != 0) {
+    if (p.W >= 4 && p.W <= 2 * kMaxGroups && (n >= ((size_t)1 << 19) || carry) && options().msm_acc_streams != 0) {
         npairs = (p.W + 1) / 2;
         for (int i = 0; i < npairs; i++) pairs[i] = kPairs[i];
         if (p.W & 1) pairs[0] = 3;
@@ -1296,11 +1303,12 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     make_groups(&gm, p.W, p.c, p.seg_shift, kit != nullptr, n >= ((size_t)1 << 20) ? 4 : 3, npairs ? pairs : nullptr, npairs);
 
     prof_begin(BPK_PROF_MSM_TOTAL, st);
-    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 2 + kMaxGroups) * 4, st);
-    if (e != cudaSuccess) return (int)e;
-    {
+    cudaError_t e = cudaSuccess;
+    if (do_front) {
+        if ((e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 2 + kMaxGroups) * 4, st)) != cudaSuccess) return (int)e;
+    }
+    if (do_back) {
         // the affine table depends only on the points: build it on a side stream while the scalar-only
         // front end (recoding, histogram, sort) runs on the main stream
         cudaStream_t ps = st;
@@ -1317,10 +1325,12 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         CBP_LAUNCH_CHECK(); nl++;
         if (kit && (e = cudaEventRecord(kit->ev_ready, ps)) != cudaSuccess) return (int)e;
     }
+    const uint32_t* ends = cursors;  // after the placing pass: end of every bucket's run
+    if (do_front) {
     prof_begin(BPK_PROF_MSM_FRONT, st);
     unsigned dgrid = (unsigned)((n + 255) / 256);
     const uint32_t slotted_ids = (uint32_t)p.w_exact * p.B;  // buckets placed by the first pass (0: none)
-    uint2* toprank = p.cap ? (uint2*)(ws + p.off_toprank) : nullptr;
+    uint2* toprank = p.cap ? (uint2*)(fw + p.off_toprank) : nullptr;
     msm_digits_kernel<0><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, counts,
                                                 entries, overflow, offsets, toprank);
     CBP_LAUNCH_CHECK(); nl++;
@@ -1336,7 +1346,6 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
                                                 entries, overflow, offsets, toprank);
     CBP_LAUNCH_CHECK(); nl++;
-    const uint32_t* ends = cursors;  // after the placing pass: end of every bucket's run
     // segments
     scan_tile_sums_kernel<true><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, 0u, overflow, tiles);
     CBP_LAUNCH_CHECK(); nl++;
@@ -1357,6 +1366,12 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     CBP_LAUNCH_CHECK(); nl++;
 
     prof_end(BPK_PROF_MSM_FRONT, st);
+    }  // do_front
+    if (!do_back) {
+        prof_end(BPK_PROF_MSM_TOTAL, st);
+        if (launches) *launches = nl;
+        return 0;
+    }
     if (kit) {  // join the table build (side stream) before the first accumulation
         if ((e = cudaStreamWaitEvent(st, kit->ev_ready, 0)) != cudaSuccess) return (int)e;
     }

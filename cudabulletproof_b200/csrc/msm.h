@@ -37,8 +37,15 @@ constexpr int kMsmKits = 3;
 // kMsmNoTail — stop once the buckets are updated (no reduction, no result).  The last chunk passes
 // kMsmCarryIn alone and produces the result for the whole input.
 constexpr int kMsmCarryIn = 1, kMsmNoTail = 2;
+// kMsmFrontOnly — only the scalar side (digit recoding, bucket sort, segments): needs no points and leaves its arrays
+// in the front part of the workspace; kMsmBackOnly — everything else, on a front part prepared by an earlier
+// kMsmFrontOnly call with the same plan.  d_front_workspace (optional, msm_front_bytes(plan) bytes) holds that front
+// part instead of the head of d_workspace, so that the sorted scalars of several chunks can wait for their points
+// while the chunks share one set of buckets (the chunked host path sorts every chunk while the points upload).
+constexpr int kMsmFrontOnly = 4, kMsmBackOnly = 8;
+inline size_t msm_front_bytes(const MsmPlan& p) { return p.off_buckets; }
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
             int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready, int kit_index = 0,
-            int flags = 0);
+            int flags = 0, void* d_front_workspace = nullptr);
 
 }  // namespace cbp

@@ -5,7 +5,16 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cudabulletproof_b200 as cbp
 lib = cbp.load()
-for lg in [int(a) for a in sys.argv[1:]] or [16, 18, 19, 20, 22]:
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+trace = False
+for a in sys.argv[1:]:
+    if a.startswith("--taper="):
+        lib.bpk_debug_set_option(10, int(a.split("=")[1]))  # BPK_OPT_HOST_TAPER_LOG2
+    if a == "--trace":
+        trace = True
+    if a.startswith("--chunk="):
+        lib.bpk_debug_set_option(2, int(a.split("=")[1]))  # BPK_OPT_HOST_CHUNK_LOG2
+for lg in [int(a) for a in args] or [16, 18, 19, 20, 22]:
     n = 1 << lg
     pts, _ = cbp.synth_points(n, seed=5)
     sc = cbp.synth_scalars(n, seed=6, bits=252)
@@ -25,6 +34,10 @@ for lg in [int(a) for a in sys.argv[1:]] or [16, 18, 19, 20, 22]:
         for _ in range(5):
             lib.cuda_point_vector_multi_scalar_mul(out.ctypes.data_as(C.c_void_p), C.byref(fv), C.byref(pv))
         row[label + "_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
+        if trace and label == "pinned":
+            lib.bpk_debug_set_option(11, 1)
+            lib.cuda_point_vector_multi_scalar_mul(out.ctypes.data_as(C.c_void_p), C.byref(fv), C.byref(pv))
+            lib.bpk_debug_set_option(11, 0)
         assert out.tobytes() == ref, label
     lib.bpk_debug_set_option(6, 0)
     lib.bpk_host_release()
