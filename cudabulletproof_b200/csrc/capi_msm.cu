@@ -184,6 +184,7 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_MSM_SEG_SHIFT: o.msm_seg_shift = (int)value; break;
         case BPK_OPT_MSM_ACC_STREAMS: o.msm_acc_streams = (int)value; break;
         case BPK_OPT_HOST_TRACE: o.host_trace = value != 0; break;
+        case BPK_OPT_DEBUG_VARIANT: o.debug_variant = (int)value; break;
         case BPK_OPT_HOST_TAPER_LOG2: o.host_taper_log2 = (value >= 10 && value <= 30) ? (int)value : 0; break;
         case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic
             o.ngroups = 0;

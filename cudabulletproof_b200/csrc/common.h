@@ -53,6 +53,7 @@ struct Options {
     int msm_acc_streams = -1; // accumulation of every window group on its own stream (see msm_run); -1 auto, 0 / 1
     int host_taper_log2 = 0;  // chunked host path: the last chunk is halved down to 2^this points (0: not at all)
     int host_trace = 0;       // chunked host path: print the timeline of every call to stderr (measurements)
+    int debug_variant = 0;    // A/B switch for kernels under measurement (tools/probe_ops.py)
     int host_register = 0;    // CBP_HOST_REGISTER: 1 = page-lock large pageable caller buffers once and remember them
 };
 Options& options();

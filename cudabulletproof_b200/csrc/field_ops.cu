@@ -287,7 +287,11 @@ __device__ __forceinline__ void block_inner_product(Acc18& acc, const uint8_t* _
 // Measured and rejected (ncu: 0.55 of HBM and 50 % of the multiply pipe at once, long_scoreboard the top stall at 39 %
 // achieved occupancy, 54 registers): two elements in flight per thread in registers (spills at 64 registers: 80 -> 99 us
 // per 2^22 elements) and a three-stage cp.async pipeline through shared memory (90 us): the 16-word carry chains of the
-// 576-bit accumulation, not the loads, are what the warps wait on.
+// 576-bit accumulation, not the loads, are what the warps wait on.  Round 2, again: a register double buffer written so
+// that the next pair of elements is requested before the current product (plain loads, then volatile asm loads with
+// compiler barriers; 2 / 3 / 4 CTAs per SM) — ptxas sinks the four LDG.128 behind the 64 multiplies either way (they
+// sit ~50 instructions ahead of the loop branch, 58 registers) and the kernel takes 85-88 us instead of 75.6.
+// Floors at 2^22 elements: HBM 41 us, multiply pipe 30 us (ncu: pipe 50 % busy, issue 44 %, 25 warps / SM resident).
 __global__ void __launch_bounds__(256) sc_ip_partial_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                             size_t n, uint32_t* __restrict__ partials) {
     __shared__ Acc18 s_warp[8];

@@ -24,7 +24,11 @@ ops = {
     "point_pack": (lambda: lib.bpk_point_pack_device(enc.data_ptr(), pts.data_ptr(), 1 << 20, None), 160 << 20),
 }
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-for name, (fn, nbytes) in ops.items():
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+for variant, (name, (fn, nbytes)) in [(v, it) for v in variants for it in ops.items()]:
+    lib.bpk_debug_set_option(12, variant)  # BPK_OPT_DEBUG_VARIANT
+    if len(variants) > 1:
+        name = f"v{variant} {name}"
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
