@@ -533,6 +533,11 @@ def run_cuda(args):
         proofs[torch.from_numpy(bad).to(dev)] = torch.from_numpy(hb).to(dev)
         ver = cbp.RangeVerifier(gens, m)
         masks = torch.zeros((world, m), dtype=torch.uint8, device=dev)
+        # grouped verification (csrc/rangeproof.cu): K proofs share one combined identity; 0 / 1 = one by one
+        K = args.verify_group if args.verify_group >= 0 else (8 if m >= 256 else 0)
+        lib.bpk_debug_set_option(13, K)  # BPK_OPT_VERIFY_GROUP
+        groups_hit = len(set(int(b) // K for b in bad)) if K >= 2 else 0
+        second_pass = min(m, groups_hit * K) if K >= 2 else 0  # proofs verified again one by one (upper bound)
 
         def step():
             acc = ver(proofs)
@@ -560,21 +565,46 @@ def run_cuda(args):
         chunks = max(1, k_n // vsteps)
         rejected = int((acc == 0).sum().item())
         ok = rejected == len(bad) and bool((acc[torch.from_numpy(bad).to(dev)] == 0).all().item())
+        # the same batch one by one (two identities per proof, the round-1 algorithm), for comparison
+        one_by_one = None
+        if K >= 2:
+            lib.bpk_debug_set_option(13, 0)
+            for _ in range(2):
+                acc1 = ver(proofs)
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record()
+            for _ in range(3):
+                acc1 = ver(proofs)
+            o1.record()
+            torch.cuda.synchronize()
+            one_by_one = {"value": m * 3 / (o0.elapsed_time(o1) * 1e-3), "unit": "verifies/s per GPU",
+                          "ms_per_step": o0.elapsed_time(o1) / 3, "same_decisions": bool((acc1 == acc).all().item())}
+            lib.bpk_debug_set_option(13, K)
         # algorithmic IMAD (SURVEY.md §8d units).  Whole proof: 131 bases x nwin windows mixed additions (504)
         # + 17 points x 51 signed 5-bit windows x 8M (576) + 2 x (255 doublings (464) + 51 additions (648)) Horner.
         # The timed kernel (verify_fixed_kernel, nwin lanes per proof) does the first term plus two
         # log2(nwin)-level shuffle trees of 9M additions.
-        imad_proof = (131 * nwin * 504 + 17 * 51 * 576 + 2 * (255 * 464 + 51 * 648)) * 1.0
-        imad_kernel = 131 * nwin * 504 + 2 * (nwin.bit_length() - 1) * nwin * 648.0
+        imad_single = (131 * nwin * 504 + 17 * 51 * 576 + 2 * (255 * 464 + 51 * 648)) * 1.0
+        if K >= 2:
+            # grouped: per proof its own points (A carries a 128-bit weight: 26 windows) + 1/K of one fixed-base sum over
+            # 130 bases and one Horner chain, + the second pass (members of failed groups, one by one)
+            var_proof = (16 * 51 + 26) * 576.0
+            imad_proof = var_proof + (130 * nwin * 504 + 255 * 464 + 51 * 648) / K + imad_single * second_pass / m
+            imad_kernel, kernel_name, ncu_kind = var_proof, "vg_winsum_kernel", f"vg_winsum_{m}"
+        else:
+            imad_proof = imad_single
+            imad_kernel = 131 * nwin * 504 + 2 * (nwin.bit_length() - 1) * nwin * 648.0
+            kernel_name, ncu_kind = "verify_fixed_kernel", f"verify_fixed_{args.fixed_window_bits}_{m}"
         per_launch = imad_kernel * (m / chunks)
-        ncu_v, ncu_v_why = ncu_summary(f"verify_fixed_{args.fixed_window_bits}_{m}")
-        roofline = {"bound": "int", "kernel": "verify_fixed_kernel", "achieved": per_launch / (k_ms * 1e-3) / 1e12,
+        ncu_v, ncu_v_why = ncu_summary(ncu_kind)
+        roofline = {"bound": "int", "kernel": kernel_name, "achieved": per_launch / (k_ms * 1e-3) / 1e12,
                     "peak": INT_PEAK_TIMAD, "unit": "TIMAD/s", "frac": per_launch / (k_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
                     "traffic": ncu_v["dram_bytes"] if ncu_v else None,
                     "traffic_note": ncu_v["note"] if ncu_v else ncu_v_why,
                     "peak_source": int_peak["source"],
                     "launch_ms": k_ms, "launches_timed": k_n,
                     "algorithmic_imad_per_launch": per_launch, "algorithmic_imad_per_proof_total": imad_proof,
+                    "algorithmic_imad_per_proof_one_by_one": imad_single,
                     "whole_batch_frac": imad_proof * m / (ms / vsteps * 1e-3) / 1e12 / INT_PEAK_TIMAD}
         # e2e: proof records in pinned host memory -> device -> accept mask back on the host
         h_proofs = torch.empty_like(proofs, device="cpu").pin_memory()
@@ -589,9 +619,15 @@ def run_cuda(args):
             h_acc.copy_(a, non_blocking=True)
             torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        lib.bpk_debug_set_option(13, -1)
         return {"metric": "range_proof_verifies_per_sec", "value": world * m * vsteps / (ms * 1e-3), "unit": "verifies/s",
                 "ms_per_step": ms / vsteps, "steps": vsteps, "proofs_per_gpu": m, "distinct_proofs": distinct,
                 "tampered": len(bad), "decisions_correct": ok, "gpu_launches": int(launches), "roofline": roofline,
+                "algorithm": ({"grouped": K, "second_pass_proofs": second_pass,
+                               "note": f"groups of {K} proofs share one combined identity (128-bit weights from SHA-256 over "
+                                       "all records of the group); members of failed groups are verified again one by one; "
+                                       "accept bits per proof"} if K >= 2 else {"grouped": 0, "note": "two identities per proof"}),
+                "one_by_one": one_by_one,
                 "prover": {"proofs_per_s": distinct / (prove_ms * 1e-3), "ms": prove_ms, "proofs": distinct,
                            "note": "bpk_range_prove_batch_device, 64-bit proofs, byte-identical to the CPU oracle's "
                                    "(host-to-device copy of values / blinding factors included)"},
@@ -768,6 +804,8 @@ def main():
     ap.add_argument("--fixed-window-bits", type=int, default=16, choices=[8, 16],
                     help="window width of the generator tables (8: 51 MB in L2; 16: 6.5 GB in HBM, half the additions)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="points per host thread for the CPU baseline")
+    ap.add_argument("--verify-group", type=int, default=-1,
+                    help="proofs per combined identity in batch verification (-1: library default, 0: one by one)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling rows (secondary_scaling)")
     ap.add_argument("--strong-log-n", type=int, nargs="*", default=[20, 22],

@@ -147,7 +147,9 @@ static __device__ __noinline__ void sc_mul_nf(sc& r, const sc& a, const sc& b) {
 
 __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes,
                                                                const uint8_t* __restrict__ Vext, uint32_t n, int k,
-                                                               uint32_t num, VScal* __restrict__ out) {
+                                                               uint32_t num, VScal* __restrict__ out,
+                                                               const uint32_t* __restrict__ dyn_num = nullptr) {
+    if (dyn_num) num = *dyn_num;  // second pass of the grouped verification: the count is only known on the device
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= num) return;
     const uint8_t* rec = proofs + (size_t)p * rec_bytes;
@@ -347,9 +349,11 @@ __device__ __forceinline__ int var_point_offset(int q, int k) {  // record offse
 __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8_t* __restrict__ gens,
                                                                      const VScal* __restrict__ vscal, uint32_t n, int k,
                                                                      int8_t* __restrict__ digits,
-                                                                     int8_t* __restrict__ vdigits) {
+                                                                     int8_t* __restrict__ vdigits,
+                                                                     const uint32_t* __restrict__ dyn_num = nullptr) {
     __shared__ sc s_sh[kMaxN], y_sh[kMaxN];
     const uint32_t p = blockIdx.x;
+    if (dyn_num && p >= *dyn_num) return;  // whole CTA
     const int t = threadIdx.x;
     const VScal& vs = vscal[p];
     if (!vs.valid) return;  // whole CTA
@@ -432,7 +436,9 @@ template <int WBITS>
 __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __restrict__ gens,
                                                               const VScal* __restrict__ vscal,
                                                               const int8_t* __restrict__ digits, uint32_t n,
-                                                              uint32_t num, uint8_t* __restrict__ fsum) {
+                                                              uint32_t num, uint8_t* __restrict__ fsum,
+                                                              const uint32_t* __restrict__ dyn_num = nullptr) {
+    if (dyn_num) num = *dyn_num;
     constexpr int LP = 256 / WBITS;  // lanes (= windows) per proof
     constexpr uint32_t E = 1u << (WBITS - 1);
     const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) / LP;
@@ -510,7 +516,9 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
 // are also kept in extended form: the window sums START from that entry instead of adding it to the identity.
 __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, int k,
                                                           uint32_t num, uint8_t* __restrict__ vtab,
-                                                          uint8_t* __restrict__ vseed) {
+                                                          uint8_t* __restrict__ vseed,
+                                                          const uint32_t* __restrict__ dyn_num = nullptr) {
+    if (dyn_num) num = *dyn_num;
     const int nvar = 2 + 2 * k + 3;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * (uint32_t)nvar) return;
@@ -542,7 +550,9 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
                                                             const int8_t* __restrict__ vdigits,
                                                             const uint8_t* __restrict__ vtab,
                                                             const uint8_t* __restrict__ vseed, int k, uint32_t num,
-                                                            uint8_t* __restrict__ winsum) {
+                                                            uint8_t* __restrict__ winsum,
+                                                            const uint32_t* __restrict__ dyn_num = nullptr) {
+    if (dyn_num) num = *dyn_num;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * 2 * kVarWin) return;
     int which = id >= num * kVarWin;  // 1: identity 1
@@ -584,7 +594,9 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
 __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restrict__ vscal,
                                                            const uint8_t* __restrict__ fsum,
                                                            const uint8_t* __restrict__ winsum, uint32_t num,
-                                                           uint8_t* __restrict__ flags) {
+                                                           uint8_t* __restrict__ flags,
+                                                           const uint32_t* __restrict__ dyn_num = nullptr) {
+    if (dyn_num) num = *dyn_num;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * 2) return;
     if (!vscal[id >> 1].valid) {
@@ -727,9 +739,378 @@ __global__ void __launch_bounds__(32 * kFinGroups) verify_finish_small_kernel(co
     fe_mul(d, V.Y, F.Z);
     if (threadIdx.x == 0) flags[id] = (fe_equal(a, b) && fe_equal(c, d)) ? 1 : 0;
 }
-__global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_t num, uint8_t* __restrict__ accept) {
+__global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_t num, uint8_t* __restrict__ accept,
+                                      const uint32_t* __restrict__ dyn_num = nullptr,
+                                      const uint32_t* __restrict__ scatter = nullptr) {
+    if (dyn_num) num = *dyn_num;
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < num) accept[p] = flags[2 * p] & flags[2 * p + 1];
+    if (p < num) accept[scatter ? scatter[p] : p] = flags[2 * p] & flags[2 * p + 1];
+}
+
+
+// ---- grouped verification: one combined identity per group of proofs ---------------------------------------------
+// Both identities of every proof of a group are checked as ONE multi-scalar identity
+//     sum_p [ w1_p (LHS1_p - RHS1_p) + w2_p (LHS2_p - RHS2_p) ] == 0
+// with 128-bit weights w1_p, w2_p drawn by SHA-256 from a digest of ALL records of the group (Bulletproofs paper,
+// section 6.2; in the random-oracle model a group that contains an invalid proof passes with probability ~2^-128).
+// The 2n+2 shared generators then cost one fixed-base sum per GROUP instead of one per proof (their coefficients add up
+// mod l), and the 255 doublings of the window combine run once per group; the 2 log n + 5 points of every proof still
+// cost their window sums.  Accept bits stay per proof: malformed records are excluded from the sums and rejected on
+// the spot, and the members of a group whose combined identity fails are verified again one by one, on gathered
+// copies of their records, by the two-identity pipeline above (the kernels take that second pass's count from device
+// memory).  With 1 % of the proofs tampered and groups of 8, ~8 % of the proofs take the second pass.
+struct VWeights {
+    sc w1, w2;
+};
+// digest of one record, as a two-level hash tree so that the leaves run side by side:
+// leaf_c = H("bpkVRFY0" || c || bytes [192 c, 192 c + 192)),  digest = H("bpkVRFY1" || leaf_0 || leaf_1 || ...)
+static constexpr int kLeafWords = 48;  // 192 bytes per leaf; a record has 864 + 256 k bytes, at most 13 leaves
+__global__ void __launch_bounds__(64) vg_leaf_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, uint32_t num,
+                                                     uint32_t nleaves, uint32_t* __restrict__ leaves) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= num * nleaves) return;
+    const uint32_t p = id / nleaves, c = id % nleaves;
+    const uint32_t* rec = reinterpret_cast<const uint32_t*>(proofs + (size_t)p * rec_bytes);
+    const int words = (int)(rec_bytes / 4), off = (int)c * kLeafWords;
+    Sha256 sh;
+    sh.init();
+    sh.update_str("bpkVRFY0", 8);
+    sh.put((uint8_t)c);
+    sh.put(0);
+    sh.put(0);
+    sh.put(0);
+#pragma unroll 1
+    for (int j = 0; j < 6 && off + 8 * j < words; j++) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = rec[off + 8 * j + i];  // records are multiples of 32 bytes
+        sh.update_words(w);
+    }
+    uint32_t d[8];
+    sh.final_words(d);
+#pragma unroll
+    for (int i = 0; i < 8; i++) leaves[(size_t)id * 8 + i] = d[i];
+}
+// digest = chain over the leaf digests of the record (at most 7 per hash: the message buffer holds 256 bytes)
+__global__ void __launch_bounds__(64) vg_digest_kernel(const uint32_t* __restrict__ leaves, uint32_t num, uint32_t nleaves,
+                                                       uint32_t* __restrict__ digest) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num) return;
+    uint32_t d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = 0;
+    Sha256 sh;
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < nleaves; c0 += 6) {
+        sh.init();
+        sh.update_str("bpkVRFY1", 8);
+        sh.update_words(d);
+#pragma unroll 1
+        for (uint32_t c = c0; c < c0 + 6 && c < nleaves; c++) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = leaves[((size_t)p * nleaves + c) * 8 + i];
+            sh.update_words(w);
+        }
+        sh.final_words(d);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) digest[(size_t)p * 8 + i] = d[i];
+}
+// weights of proof p: seed = chain over the digests of its group, (w1, w2) = the two halves of H(seed || index)
+__global__ void __launch_bounds__(64) vg_weights_kernel(const uint32_t* __restrict__ digest, uint32_t num, uint32_t K,
+                                                        VWeights* __restrict__ wts) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num) return;
+    const uint32_t g0 = p / K * K;
+    uint32_t seed[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) seed[i] = 0;
+    Sha256 sh;
+#pragma unroll 1
+    for (uint32_t j = g0; j < g0 + K && j < num; j++) {
+        uint32_t d[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) d[i] = digest[(size_t)j * 8 + i];
+        sh.init();
+        sh.update_str("bpkVRFY2", 8);
+        sh.update_words(seed);
+        sh.update_words(d);
+        sh.final_words(seed);
+    }
+    uint32_t h[8];
+    sh.init();
+    sh.update_str("bpkVRFY3", 8);
+    sh.update_words(seed);
+    sh.put((uint8_t)(p - g0));
+    sh.final_words(h);
+    VWeights w;
+    sc_set0(w.w1);
+    sc_set0(w.w2);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        w.w1.v[i] = h[i];
+        w.w2.v[i] = h[4 + i];
+    }
+    w.w1.v[0] |= 1u;  // never zero
+    w.w2.v[0] |= 1u;
+    wts[p] = w;
+}
+// coefficients: one CTA per group.  The members' coefficients of the shared generators are weighted and summed
+// (thread t < n: G_t and H_t, thread n: h, thread n + 1: g), the scalars of their own points weighted and recoded.
+__global__ void __launch_bounds__(kCoeffThreads) vg_coeff_kernel(const uint8_t* __restrict__ gens,
+                                                                 const VScal* __restrict__ vscal,
+                                                                 const VWeights* __restrict__ wts, uint32_t n, int k,
+                                                                 uint32_t K, uint32_t num, int8_t* __restrict__ gdigits,
+                                                                 int8_t* __restrict__ vdigits) {
+    __shared__ sc s_sh[kMaxN], y_sh[kMaxN];
+    __shared__ sc wsc[4];  // w2 a, w2 b, w2 z, w2 z^2 of the current member: the weight enters every G_i / H_i
+                           // coefficient through these four products instead of two more multiplications per i
+    const uint32_t g = blockIdx.x;
+    const int t = threadIdx.x;
+    const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
+    const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
+    sc sum0, sum1;
+    sc_set0(sum0);
+    sc_set0(sum1);
+#pragma unroll 1
+    for (uint32_t p = g * K; p < g * K + K && p < num; p++) {
+        const VScal& vs = vscal[p];
+        if (!vs.valid) continue;  // whole CTA
+        const sc w1 = wts[p].w1, w2 = wts[p].w2;
+        if (t == (int)n) {  // h: w1 taux + w2 (mu + ab - t)
+            sc a, b;
+            sc_mul_nf(a, w1, vs.h1);
+            sc_mul_nf(b, w2, vs.h2);
+            sc_add(a, a, b);
+            sc_add(sum0, sum0, a);
+        } else if (t == (int)n + 1) {  // g: w1 (t - delta)
+            sc a;
+            sc_mul_nf(a, w1, vs.g1);
+            sc_add(sum0, sum0, a);
+        } else if (t == (int)n + 2) {
+            sc a;
+            sc_mul_nf(a, w2, vs.a);
+            wsc[0] = a;
+            sc_mul_nf(a, w2, vs.b);
+            wsc[1] = a;
+            sc_mul_nf(a, w2, vs.z);
+            wsc[2] = a;
+            sc_mul_nf(a, w2, vs.z2);
+            wsc[3] = a;
+        } else if (t >= (int)n + 3 && t - (int)n - 3 < nvar) {
+            int q = t - (int)n - 3;
+            sc sv;
+            if (q == 0) sv = w2;
+            else {
+                if (q == 1) sv = vs.x;
+                else if (q < 2 + k) sv = vs.usq[q - 2];
+                else if (q < nvar2) sv = vs.uinvsq[q - 2 - k];
+                else if (q == nvar2) sv = vs.z2;
+                else if (q == nvar2 + 1) sv = vs.x;
+                else sv = vs.x2;
+                sc_mul_nf(sv, sv, q < nvar2 ? w2 : w1);
+            }
+            sc_recode_signed<kVarBits>(vdigits + ((size_t)p * kVarMax + q) * 64, sv, kVarWin);
+        }
+        if (t == 0) {
+            s_sh[0] = vs.s0;
+            sc one;
+            sc_set1(one);
+            y_sh[0] = one;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int m = 0; m < k; m++) {
+            const int half = 1 << m;
+            if (half >= 32) __syncthreads();
+            if (t >= half && t < 2 * half) {
+                sc a = s_sh[t - half], b = y_sh[t - half];
+                sc_mul_nf(a, a, vs.usq[k - 1 - m]);
+                sc_mul_nf(b, b, vs.ypow[m]);
+                s_sh[t] = a;
+                y_sh[t] = b;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (t < (int)n) {
+            sc cg, ch, tmp, two_i;
+            const sc wa = wsc[0], wb = wsc[1], wz = wsc[2], wz2 = wsc[3];  // written before the barriers above
+            sc_mul_nf(cg, wa, s_sh[t]);
+            sc_add(cg, cg, wz);
+            sc_set0(two_i);
+            two_i.v[t >> 5] = 1u << (t & 31);
+            sc_mul_nf(tmp, wz2, two_i);
+            sc_mul_nf(ch, wb, s_sh[n - 1 - t]);
+            sc_sub(ch, ch, tmp);
+            sc_mul_nf(ch, ch, y_sh[t]);
+            sc_sub(ch, ch, wz);
+            sc_add(sum0, sum0, cg);
+            sc_add(sum1, sum1, ch);
+        }
+        __syncthreads();  // the next member overwrites the ladders
+    }
+    int8_t* grow = gdigits + (size_t)g * kRowsMax * kFixRowBytes;
+    if (t < (int)n) {
+        fix_recode(grow + (size_t)t * kFixRowBytes, sum0, wbits);
+        fix_recode(grow + (size_t)(n + t) * kFixRowBytes, sum1, wbits);
+    } else if (t == (int)n) {
+        fix_recode(grow + (size_t)(2 * n + 1) * kFixRowBytes, sum0, wbits);  // base 2n + 1 = h
+    } else if (t == (int)n + 1) {
+        fix_recode(grow + (size_t)(2 * n) * kFixRowBytes, sum0, wbits);  // base 2n = g
+    }
+}
+// fixed-base sum of a group: one CTA of 128 threads, lane = window, the 2n+2 rows dealt round-robin to the 128 / LP
+// row slices (16-bit tables: 8 slices of 16 lanes); warp butterflies, then the four warp sums through shared memory
+template <int WBITS>
+__global__ void __launch_bounds__(128) vg_fixed_kernel(const uint8_t* __restrict__ gens, const int8_t* __restrict__ gdigits,
+                                                       uint32_t n, uint8_t* __restrict__ gfsum) {
+    __shared__ __align__(16) uint8_t sh[4][128];
+    constexpr int LP = 256 / WBITS;
+    constexpr int S = 128 / LP;
+    constexpr uint32_t E = 1u << (WBITS - 1);
+    const uint32_t g = blockIdx.x;
+    const int win = threadIdx.x & (LP - 1), slice = threadIdx.x / LP;
+    const GensHeader* gh = reinterpret_cast<const GensHeader*>(gens);
+    const uint8_t* table = gens + gh->table_off + (size_t)win * E * 96;
+    const int8_t* drow = gdigits + (size_t)g * kRowsMax * kFixRowBytes;
+    const int nrows = 2 * (int)n + 2;
+    auto digit_of = [&](int row, uint32_t& mag, bool& neg) {
+        if (WBITS == 8) fixed_digit(drow[(size_t)row * kFixRowBytes + win], mag, neg);
+        else fixed_digit16(reinterpret_cast<const int16_t*>(drow + (size_t)row * kFixRowBytes)[win], mag, neg);
+    };
+    ge_p3 acc;
+    ge_p3_0(acc);
+    uint32_t mag = 0;
+    bool neg = false;
+    ge_niels q;
+    if (slice < nrows) {
+        digit_of(slice, mag, neg);
+        if (mag) ge_niels_load(q, table + ((size_t)slice * LP * E + (mag - 1)) * 96);
+    }
+#pragma unroll 1
+    for (int row = slice; row < nrows; row += S) {
+        const uint32_t cmag = mag;
+        const bool cneg = neg;
+        const ge_niels cur = q;
+        if (row + S < nrows) {
+            digit_of(row + S, mag, neg);
+            if (mag) ge_niels_load(q, table + ((size_t)(row + S) * LP * E + (mag - 1)) * 96);
+        }
+        if (cmag) ge_madd(acc, acc, cur, cneg);
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        ge_p3 other;
+        ge_shfl_xor(other, acc, o);
+        ge_add(acc, acc, other);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) ge_store(sh[warp], acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int w = 1; w < 4; w++) {
+            ge_p3 other;
+            ge_load(other, sh[w]);
+            ge_add(acc, acc, other);
+        }
+        ge_store(gfsum + (size_t)g * 128, acc);
+    }
+}
+// window sums of a group: thread per (group, window) over the points of all its valid members
+__global__ void __launch_bounds__(128) vg_winsum_kernel(const VScal* __restrict__ vscal, const int8_t* __restrict__ vdigits,
+                                                        const uint8_t* __restrict__ vtab, int k, uint32_t K, uint32_t num,
+                                                        uint32_t ngroups, uint8_t* __restrict__ gwinsum) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= ngroups * kVarWin) return;
+    const uint32_t g = id / kVarWin;
+    const int w = (int)(id % kVarWin);
+    const int nvar = 2 + 2 * k + 3;
+    ge_p3 ws;
+    ge_p3_0(ws);
+#pragma unroll 1
+    for (uint32_t p = g * K; p < g * K + K && p < num; p++) {
+        if (!vscal[p].valid) continue;
+#pragma unroll 1
+        for (int q = 0; q < nvar; q++) {
+            int d = vdigits[((size_t)p * kVarMax + q) * 64 + w];
+            if (d != 0) {
+                int mag = d < 0 ? -d : d;
+                const uint8_t* src = vtab + (((size_t)p * kVarMax + q) * kVarEntries + (mag - 1)) * 128;
+                ge_cached c;
+                fe_load(c.YplusX, src);
+                fe_load(c.YminusX, src + 32);
+                fe_load(c.Z2, src + 64);
+                fe_load(c.T2d, src + 96);
+                ge_add_cached(ws, ws, c, d < 0);
+            }
+        }
+    }
+    ge_store(gwinsum + ((size_t)g * kVarWin + w) * 128, ws);
+}
+// Horner over the window sums of a group and the comparison with its fixed-base sum: one warp per group in octet
+// form (255 doublings + 51 additions deep at 0.63 / 0.82 us; all groups of a pass are resident at once)
+__global__ void __launch_bounds__(128) vg_finish_kernel(const uint8_t* __restrict__ gfsum, const uint8_t* __restrict__ gwinsum,
+                                                        uint32_t ngroups, uint8_t* __restrict__ gflags) {
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= ngroups) return;  // whole warp
+    const Fe8Lane L = fe8_lane();
+    const uint8_t* ws = gwinsum + (size_t)g * kVarWin * 128;
+    ge8 acc, x;
+    ge8_load(acc, ws + (size_t)(kVarWin - 1) * 128, L);
+#pragma unroll 1
+    for (int w = kVarWin - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int d = 0; d < kVarBits; d++) ge8_dbl(acc, acc, L);
+        ge8_load(x, ws + (size_t)w * 128, L);
+        ge8_add(acc, acc, x, L);
+    }
+    ge_p3 V, F;
+    fe8_gather(V.X, acc.X, L);
+    fe8_gather(V.Y, acc.Y, L);
+    fe8_gather(V.Z, acc.Z, L);
+    ge_load(F, gfsum + (size_t)g * 128);
+    fe a, b, c, d;
+    fe_mul(a, F.X, V.Z);
+    fe_mul(b, V.X, F.Z);
+    fe_mul(c, F.Y, V.Z);
+    fe_mul(d, V.Y, F.Z);
+    if ((threadIdx.x & 31) == 0) gflags[g] = (fe_equal(a, b) && fe_equal(c, d)) ? 1 : 0;
+}
+// per proof: rejected (malformed), accepted with its group, or queued for the second pass
+__global__ void vg_decide_kernel(const VScal* __restrict__ vscal, const uint8_t* __restrict__ gflags, uint32_t K,
+                                 uint32_t num, uint8_t* __restrict__ accept, uint32_t* __restrict__ fb_count,
+                                 uint32_t* __restrict__ fb_index) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num) return;
+    if (!vscal[p].valid) {
+        accept[p] = 0;
+    } else if (gflags[p / K]) {
+        accept[p] = 1;
+    } else {
+        accept[p] = 0;
+        fb_index[atomicAdd(fb_count, 1u)] = p;
+    }
+}
+// copies of the queued records (and of their external commitments), 16 bytes per thread
+__global__ void vg_gather_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, const uint8_t* __restrict__ Vext,
+                                 const uint32_t* __restrict__ fb_count, const uint32_t* __restrict__ fb_index,
+                                 uint8_t* __restrict__ fb_records, uint8_t* __restrict__ fb_V) {
+    const uint32_t per = (uint32_t)(rec_bytes / 16) + 8;  // + the 128 bytes of V
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slot = (uint32_t)(id / per), part = (uint32_t)(id % per);
+    if (slot >= *fb_count) return;
+    const uint32_t p = fb_index[slot];
+    const uint32_t rparts = per - 8;
+    if (part < rparts) {
+        reinterpret_cast<uint4*>(fb_records + (size_t)slot * rec_bytes)[part] =
+            reinterpret_cast<const uint4*>(proofs + (size_t)p * rec_bytes)[part];
+    } else if (Vext) {
+        reinterpret_cast<uint4*>(fb_V + (size_t)slot * 128)[part - rparts] =
+            reinterpret_cast<const uint4*>(Vext + (size_t)p * 128)[part - rparts];
+    }
 }
 
 static constexpr uint32_t kVerifySmallBatch = 64;  // up to this many proofs per call take the latency kernels
@@ -812,9 +1193,15 @@ int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, cons
 }
 
 struct VerifyLayout {
-    size_t vscal, fsum, winsum, flags, digits, vdigits, vtab, vseed, total;
+    size_t vscal, fsum, winsum, flags, digits, vdigits, vtab, vseed;
+    // grouped verification: record digests, weights, per-group digit rows / sums / flags, second-pass queue and copies
+    size_t leaves, digest, wts, gdigits, gfsum, gwinsum, gflags, fb_count, fb_index, fb_records, fb_V;
+    size_t total;
 };
-static VerifyLayout verify_layout(size_t chunk) {
+static constexpr uint32_t kVerifyGroupMin = 2;     // smallest group the grouped path is used with
+static constexpr uint32_t kVerifyGroupDefault = 8;
+static constexpr uint32_t kVerifyGroupBatchMin = 256;  // below this many proofs per call: one by one
+static VerifyLayout verify_layout(size_t chunk, size_t rec_bytes) {
     VerifyLayout L;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -830,6 +1217,18 @@ static VerifyLayout verify_layout(size_t chunk) {
     L.vdigits = take(chunk * kVarMax * 64);
     L.vtab = take(chunk * kVarMax * kVarEntries * 128);
     L.vseed = take(chunk * 2 * kVarEntries * 128);
+    const size_t groups = (chunk + kVerifyGroupMin - 1) / kVerifyGroupMin;  // upper bound for any group size
+    L.leaves = take(chunk * ((rec_bytes + 191) / 192) * 32);
+    L.digest = take(chunk * 32);
+    L.wts = take(chunk * sizeof(VWeights));
+    L.gdigits = take(groups * kRowsMax * kFixRowBytes);
+    L.gfsum = take(groups * 128);
+    L.gwinsum = take(groups * kVarWin * 128);
+    L.gflags = take(groups);
+    L.fb_count = take(4);
+    L.fb_index = take(chunk * 4);
+    L.fb_records = take(chunk * rec_bytes);
+    L.fb_V = take(chunk * 128);
     L.total = off;
     return L;
 }
@@ -837,13 +1236,13 @@ int bpk_range_verify_workspace_bytes(size_t n, size_t num_proofs, size_t* bytes)
     if (!bytes || n == 0 || n > kMaxN || (n & (n - 1))) return fail(BPK_ERR_ARG);
     size_t chunk = num_proofs < kVerifyChunk ? num_proofs : kVerifyChunk;
     if (chunk == 0) chunk = 1;
-    *bytes = verify_layout(chunk).total;
+    *bytes = verify_layout(chunk, bpk_proof_record_bytes(n)).total;
     return BPK_OK;
 }
 // one side stream per device for the work that does not depend on the transcript
 struct VerifySide {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_weights = nullptr;
     bool ok = false;
 };
 static VerifySide g_vside[kMaxDevices];
@@ -855,6 +1254,7 @@ static VerifySide* verify_side(int dev) {
         if (cudaStreamCreateWithFlags(&v.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&v.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&v.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&v.ev_weights, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         v.ok = true;
     }
     return &v;
@@ -874,7 +1274,7 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
     while (((size_t)1 << k) < n) k++;
     size_t rec = proof_record_bytes(k);
     size_t chunk = num_proofs < kVerifyChunk ? num_proofs : kVerifyChunk;
-    VerifyLayout L = verify_layout(chunk);
+    VerifyLayout L = verify_layout(chunk, rec);
     uint8_t* ws = (uint8_t*)d_workspace;
     VScal* vscal = (VScal*)(ws + L.vscal);
     uint8_t *fsum = ws + L.fsum, *winsum = ws + L.winsum, *flags = ws + L.flags, *vtab = ws + L.vtab;
@@ -899,8 +1299,84 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
         CBP_CUDA(cudaStreamWaitEvent(ss, side->ev_fork, 0));
         verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(pr, rec, ve, (uint32_t)n, k, cnt, vscal);
         CBP_CHECK_LAUNCH();
-        verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab, vseed);
-        CBP_CHECK_LAUNCH();
+        // grouped verification (block comment above vg_leaf_kernel)
+        uint32_t K = options().verify_group < 0 ? (cnt >= kVerifyGroupBatchMin ? kVerifyGroupDefault : 0u)
+                                                : (uint32_t)options().verify_group;
+        if (K > 64) K = 64;
+        if (K < kVerifyGroupMin) {
+            verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab, vseed);
+            CBP_CHECK_LAUNCH();
+        } else {
+            uint32_t *leaves = (uint32_t*)(ws + L.leaves), *digest = (uint32_t*)(ws + L.digest);
+            VWeights* wts = (VWeights*)(ws + L.wts);
+            int8_t* gdigits = (int8_t*)(ws + L.gdigits);
+            uint8_t *gfsum = ws + L.gfsum, *gwinsum = ws + L.gwinsum, *gflags = ws + L.gflags;
+            uint32_t *fb_count = (uint32_t*)(ws + L.fb_count), *fb_index = (uint32_t*)(ws + L.fb_index);
+            uint8_t *fb_records = ws + L.fb_records, *fb_V = ve ? ws + L.fb_V : nullptr;
+            const uint32_t G = (cnt + K - 1) / K;
+            // side stream, under the transcript: record digests and weights (the coefficients wait for them), then
+            // the tables of the per-proof points (the window sums wait for those); all need only the records
+            const uint32_t nleaves = (uint32_t)((rec + 191) / 192);
+            vg_leaf_kernel<<<(cnt * nleaves + 63) / 64, 64, 0, ss>>>(pr, rec, cnt, nleaves, leaves);
+            CBP_CHECK_LAUNCH();
+            vg_digest_kernel<<<(cnt + 63) / 64, 64, 0, ss>>>(leaves, cnt, nleaves, digest);
+            CBP_CHECK_LAUNCH();
+            vg_weights_kernel<<<(cnt + 63) / 64, 64, 0, ss>>>(digest, cnt, K, wts);
+            CBP_CHECK_LAUNCH();
+            CBP_CUDA(cudaEventRecord(side->ev_weights, ss));
+            verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, ss>>>(pr, rec, k, cnt, vtab, vseed);
+            CBP_CHECK_LAUNCH();
+            CBP_CUDA(cudaEventRecord(side->ev_join, ss));
+            CBP_CUDA(cudaMemsetAsync(fb_count, 0, 4, st));
+            CBP_CUDA(cudaStreamWaitEvent(st, side->ev_weights, 0));
+            vg_coeff_kernel<<<G, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, wts, (uint32_t)n, k, K, cnt, gdigits,
+                                                         vdigits);
+            CBP_CHECK_LAUNCH();
+            CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
+            // the groups' fixed-base sums (few, latency-bound CTAs) on the side stream, under the window sums
+            CBP_CUDA(cudaEventRecord(side->ev_fork, st));
+            CBP_CUDA(cudaStreamWaitEvent(ss, side->ev_fork, 0));
+            if (wbits == 8) vg_fixed_kernel<8><<<G, 128, 0, ss>>>((const uint8_t*)d_gens_ws, gdigits, (uint32_t)n, gfsum);
+            else vg_fixed_kernel<16><<<G, 128, 0, ss>>>((const uint8_t*)d_gens_ws, gdigits, (uint32_t)n, gfsum);
+            CBP_CHECK_LAUNCH();
+            CBP_CUDA(cudaEventRecord(side->ev_join, ss));
+            prof_begin(BPK_PROF_VERIFY_MSM, st);
+            vg_winsum_kernel<<<(G * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, K, cnt, G, gwinsum);
+            prof_end(BPK_PROF_VERIFY_MSM, st);
+            CBP_CHECK_LAUNCH();
+            CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
+            vg_finish_kernel<<<(G * 32 + 127) / 128, 128, 0, st>>>(gfsum, gwinsum, G, gflags);
+            CBP_CHECK_LAUNCH();
+            vg_decide_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(vscal, gflags, K, cnt, d_accept + done, fb_count, fb_index);
+            CBP_CHECK_LAUNCH();
+            // second pass: the members of failed groups, one by one, count on the device (grids sized for all of them)
+            const size_t gthreads = (size_t)cnt * (rec / 16 + 8);
+            vg_gather_kernel<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(pr, rec, ve, fb_count, fb_index, fb_records,
+                                                                                fb_V);
+            CBP_CHECK_LAUNCH();
+            verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(fb_records, rec, fb_V, (uint32_t)n, k, cnt, vscal, fb_count);
+            CBP_CHECK_LAUNCH();
+            verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, st>>>(fb_records, rec, k, cnt, vtab, vseed, fb_count);
+            CBP_CHECK_LAUNCH();
+            verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits, vdigits,
+                                                               fb_count);
+            CBP_CHECK_LAUNCH();
+            if (wbits == 8)
+                verify_fixed_kernel<8><<<(cnt * 32 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
+                                                                               (uint32_t)n, cnt, fsum, fb_count);
+            else
+                verify_fixed_kernel<16><<<(cnt * 16 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
+                                                                                (uint32_t)n, cnt, fsum, fb_count);
+            CBP_CHECK_LAUNCH();
+            verify_winsum_kernel<<<(cnt * 2 * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, vseed, k, cnt, winsum,
+                                                                                   fb_count);
+            CBP_CHECK_LAUNCH();
+            verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags, fb_count);
+            CBP_CHECK_LAUNCH();
+            verify_combine_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(flags, cnt, d_accept + done, fb_count, fb_index);
+            CBP_CHECK_LAUNCH();
+            continue;
+        }
         CBP_CUDA(cudaEventRecord(side->ev_join, ss));
         verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits,
                                                            vdigits);

@@ -117,6 +117,50 @@ def test_batch_verify_matches_oracle_honest_and_tampered(oracle, gens16, gens64,
         assert oracle_verify(oracle, g, proof, V) == got[idx]
 
 
+@pytest.mark.parametrize("group", [2, 3, 8, 64])
+def test_grouped_verification_same_decisions_as_one_by_one(oracle, gens16, group):
+    """Grouped verification (one combined identity per `group` proofs, hash-derived weights, members of failed groups
+    verified again one by one; BPK_OPT_VERIFY_GROUP) on a batch that mixes honest proofs, one bit flipped in every field
+    of the record, and runs of consecutive honest proofs long enough to fill whole groups: decisions equal the oracle's
+    and those of the one-by-one path, for groups that are all honest, all bad, mixed, and ragged at the end."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    n, g = 16, gens16
+    dg = dev_gens(g, 16)
+    k = n.bit_length() - 1
+    rng = random.Random(1000 + group)
+    honest = []
+    for s, v in [(21, 7), (22, 2**n - 1), (23, 0), (24, 31337)]:
+        proof, V = oracle_prove(oracle, g, v, s)
+        assert oracle_verify(oracle, g, proof, V)
+        honest.append(flatten_proof(proof, n).view(np.uint8).copy())
+        oracle.range_proof_free(C.byref(proof))
+    recs, expect = [], []
+    for i in range(20):  # whole groups of honest proofs first
+        recs.append(honest[i % 4])
+        expect.append(True)
+    for off in tamper_cases(len(honest[0]), k, rng):
+        bad = honest[0].copy()
+        bad[off] ^= 1 << rng.randrange(8)
+        recs.append(bad)
+        expect.append(False)
+        if rng.random() < 0.5:
+            recs.append(honest[rng.randrange(4)])
+            expect.append(True)
+    d = torch.from_numpy(np.stack(recs)).cuda()
+    ver = cbp.RangeVerifier(dg, len(recs))
+    try:
+        cbp.check(lib.bpk_debug_set_option(13, 0), "set_option")  # BPK_OPT_VERIFY_GROUP: one by one
+        plain = ver(d).cpu().numpy().astype(bool).tolist()
+        cbp.check(lib.bpk_debug_set_option(13, group), "set_option")
+        grouped = ver(d).cpu().numpy().astype(bool).tolist()
+    finally:
+        lib.bpk_debug_set_option(13, -1)
+    assert plain == expect
+    assert grouped == expect
+
+
 def record_to_struct(rec, n):
     """flat record -> ctypes RangeProof (oracle layout) + V, keeping the backing arrays alive"""
     k = n.bit_length() - 1
