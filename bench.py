@@ -534,7 +534,7 @@ def run_cuda(args):
         ver = cbp.RangeVerifier(gens, m)
         masks = torch.zeros((world, m), dtype=torch.uint8, device=dev)
         # grouped verification (csrc/rangeproof.cu): K proofs share one combined identity; 0 / 1 = one by one
-        K = args.verify_group if args.verify_group >= 0 else (8 if m >= 256 else 0)
+        K = args.verify_group if args.verify_group >= 0 else (12 if m >= 256 else 0)
         lib.bpk_debug_set_option(13, K)  # BPK_OPT_VERIFY_GROUP
         groups_hit = len(set(int(b) // K for b in bad)) if K >= 2 else 0
         second_pass = min(m, groups_hit * K) if K >= 2 else 0  # proofs verified again one by one (upper bound)
@@ -587,9 +587,10 @@ def run_cuda(args):
         imad_single = (131 * nwin * 504 + 17 * 51 * 576 + 2 * (255 * 464 + 51 * 648)) * 1.0
         if K >= 2:
             # grouped: per proof its own points (A carries a 128-bit weight: 26 windows) + 1/K of one fixed-base sum over
-            # 130 bases and one Horner chain, + the second pass (members of failed groups, one by one)
+            # 130 bases and one Horner chain, + the second pass (members of failed groups, each as a group of one)
             var_proof = (16 * 51 + 26) * 576.0
-            imad_proof = var_proof + (130 * nwin * 504 + 255 * 464 + 51 * 648) / K + imad_single * second_pass / m
+            shared = 130 * nwin * 504 + 255 * 464 + 51 * 648.0
+            imad_proof = var_proof + shared / K + (var_proof + shared) * second_pass / m
             imad_kernel, kernel_name, ncu_kind = var_proof, "vg_winsum_kernel", f"vg_winsum_{m}"
         else:
             imad_proof = imad_single
@@ -625,7 +626,7 @@ def run_cuda(args):
                 "tampered": len(bad), "decisions_correct": ok, "gpu_launches": int(launches), "roofline": roofline,
                 "algorithm": ({"grouped": K, "second_pass_proofs": second_pass,
                                "note": f"groups of {K} proofs share one combined identity (128-bit weights from SHA-256 over "
-                                       "all records of the group); members of failed groups are verified again one by one; "
+                                       "all records of the group); members of failed groups are verified again on their own; "
                                        "accept bits per proof"} if K >= 2 else {"grouped": 0, "note": "two identities per proof"}),
                 "one_by_one": one_by_one,
                 "prover": {"proofs_per_s": distinct / (prove_ms * 1e-3), "ms": prove_ms, "proofs": distinct,

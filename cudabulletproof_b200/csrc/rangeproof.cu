@@ -147,9 +147,7 @@ static __device__ __noinline__ void sc_mul_nf(sc& r, const sc& a, const sc& b) {
 
 __global__ void __launch_bounds__(64) verify_transcript_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes,
                                                                const uint8_t* __restrict__ Vext, uint32_t n, int k,
-                                                               uint32_t num, VScal* __restrict__ out,
-                                                               const uint32_t* __restrict__ dyn_num = nullptr) {
-    if (dyn_num) num = *dyn_num;  // second pass of the grouped verification: the count is only known on the device
+                                                               uint32_t num, VScal* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= num) return;
     const uint8_t* rec = proofs + (size_t)p * rec_bytes;
@@ -349,11 +347,9 @@ __device__ __forceinline__ int var_point_offset(int q, int k) {  // record offse
 __global__ void __launch_bounds__(kCoeffThreads) verify_coeff_kernel(const uint8_t* __restrict__ gens,
                                                                      const VScal* __restrict__ vscal, uint32_t n, int k,
                                                                      int8_t* __restrict__ digits,
-                                                                     int8_t* __restrict__ vdigits,
-                                                                     const uint32_t* __restrict__ dyn_num = nullptr) {
+                                                                     int8_t* __restrict__ vdigits) {
     __shared__ sc s_sh[kMaxN], y_sh[kMaxN];
     const uint32_t p = blockIdx.x;
-    if (dyn_num && p >= *dyn_num) return;  // whole CTA
     const int t = threadIdx.x;
     const VScal& vs = vscal[p];
     if (!vs.valid) return;  // whole CTA
@@ -436,9 +432,7 @@ template <int WBITS>
 __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __restrict__ gens,
                                                               const VScal* __restrict__ vscal,
                                                               const int8_t* __restrict__ digits, uint32_t n,
-                                                              uint32_t num, uint8_t* __restrict__ fsum,
-                                                              const uint32_t* __restrict__ dyn_num = nullptr) {
-    if (dyn_num) num = *dyn_num;
+                                                              uint32_t num, uint8_t* __restrict__ fsum) {
     constexpr int LP = 256 / WBITS;  // lanes (= windows) per proof
     constexpr uint32_t E = 1u << (WBITS - 1);
     const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) / LP;
@@ -516,9 +510,7 @@ __global__ void __launch_bounds__(128, 4) verify_fixed_kernel(const uint8_t* __r
 // are also kept in extended form: the window sums START from that entry instead of adding it to the identity.
 __global__ void __launch_bounds__(128) verify_vtab_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, int k,
                                                           uint32_t num, uint8_t* __restrict__ vtab,
-                                                          uint8_t* __restrict__ vseed,
-                                                          const uint32_t* __restrict__ dyn_num = nullptr) {
-    if (dyn_num) num = *dyn_num;
+                                                          uint8_t* __restrict__ vseed) {
     const int nvar = 2 + 2 * k + 3;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * (uint32_t)nvar) return;
@@ -550,9 +542,7 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
                                                             const int8_t* __restrict__ vdigits,
                                                             const uint8_t* __restrict__ vtab,
                                                             const uint8_t* __restrict__ vseed, int k, uint32_t num,
-                                                            uint8_t* __restrict__ winsum,
-                                                            const uint32_t* __restrict__ dyn_num = nullptr) {
-    if (dyn_num) num = *dyn_num;
+                                                            uint8_t* __restrict__ winsum) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * 2 * kVarWin) return;
     int which = id >= num * kVarWin;  // 1: identity 1
@@ -594,9 +584,7 @@ __global__ void __launch_bounds__(128) verify_winsum_kernel(const VScal* __restr
 __global__ void __launch_bounds__(64) verify_finish_kernel(const VScal* __restrict__ vscal,
                                                            const uint8_t* __restrict__ fsum,
                                                            const uint8_t* __restrict__ winsum, uint32_t num,
-                                                           uint8_t* __restrict__ flags,
-                                                           const uint32_t* __restrict__ dyn_num = nullptr) {
-    if (dyn_num) num = *dyn_num;
+                                                           uint8_t* __restrict__ flags) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= num * 2) return;
     if (!vscal[id >> 1].valid) {
@@ -739,12 +727,9 @@ __global__ void __launch_bounds__(32 * kFinGroups) verify_finish_small_kernel(co
     fe_mul(d, V.Y, F.Z);
     if (threadIdx.x == 0) flags[id] = (fe_equal(a, b) && fe_equal(c, d)) ? 1 : 0;
 }
-__global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_t num, uint8_t* __restrict__ accept,
-                                      const uint32_t* __restrict__ dyn_num = nullptr,
-                                      const uint32_t* __restrict__ scatter = nullptr) {
-    if (dyn_num) num = *dyn_num;
+__global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_t num, uint8_t* __restrict__ accept) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < num) accept[scatter ? scatter[p] : p] = flags[2 * p] & flags[2 * p + 1];
+    if (p < num) accept[p] = flags[2 * p] & flags[2 * p + 1];
 }
 
 
@@ -756,9 +741,10 @@ __global__ void verify_combine_kernel(const uint8_t* __restrict__ flags, uint32_
 // The 2n+2 shared generators then cost one fixed-base sum per GROUP instead of one per proof (their coefficients add up
 // mod l), and the 255 doublings of the window combine run once per group; the 2 log n + 5 points of every proof still
 // cost their window sums.  Accept bits stay per proof: malformed records are excluded from the sums and rejected on
-// the spot, and the members of a group whose combined identity fails are verified again one by one, on gathered
-// copies of their records, by the two-identity pipeline above (the kernels take that second pass's count from device
-// memory).  With 1 % of the proofs tampered and groups of 8, ~8 % of the proofs take the second pass.
+// the spot, and every member of a group whose combined identity fails is verified again on its own — as a group of one,
+// its two identities combined with its own weights — by a second pass of the same kernels over what the first pass
+// left of it (transcript scalars, weights, point tables); that pass takes its count and indices from device memory.
+// With 1 % of the proofs tampered and groups of 8, ~8 % of the proofs take the second pass.
 struct VWeights {
     sc w1, w2;
 };
@@ -856,116 +842,116 @@ __global__ void __launch_bounds__(64) vg_weights_kernel(const uint32_t* __restri
     w.w2.v[0] |= 1u;
     wts[p] = w;
 }
-// coefficients: one CTA per group.  The members' coefficients of the shared generators are weighted and summed
-// (thread t < n: G_t and H_t, thread n: h, thread n + 1: g), the scalars of their own points weighted and recoded.
-__global__ void __launch_bounds__(kCoeffThreads) vg_coeff_kernel(const uint8_t* __restrict__ gens,
-                                                                 const VScal* __restrict__ vscal,
+// coefficients, in two steps.  vg_coeff: one CTA per proof (the ladder of verify_coeff_kernel): its weighted coefficients
+// of the shared generators go to memory as scalars (row t < n: G_t, n + t: H_t, 2n: g, 2n + 1: h), the weighted scalars
+// of its own points are recoded.  vg_rowsum: thread per (group, row) adds the members' scalars mod l and recodes the sum.
+// (A first version looped over the members inside one CTA per group: 0.72 ms per 2^14 proofs, the members' ladders
+// in sequence.)
+__global__ void __launch_bounds__(kCoeffThreads) vg_coeff_kernel(const VScal* __restrict__ vscal,
                                                                  const VWeights* __restrict__ wts, uint32_t n, int k,
-                                                                 uint32_t K, uint32_t num, int8_t* __restrict__ gdigits,
-                                                                 int8_t* __restrict__ vdigits) {
+                                                                 sc* __restrict__ cw, int8_t* __restrict__ vdigits) {
     __shared__ sc s_sh[kMaxN], y_sh[kMaxN];
-    __shared__ sc wsc[4];  // w2 a, w2 b, w2 z, w2 z^2 of the current member: the weight enters every G_i / H_i
-                           // coefficient through these four products instead of two more multiplications per i
-    const uint32_t g = blockIdx.x;
+    const uint32_t p = blockIdx.x;
     const int t = threadIdx.x;
-    const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
+    const VScal& vs = vscal[p];
+    if (!vs.valid) return;  // whole CTA
     const int nvar2 = 2 + 2 * k, nvar = nvar2 + 3;
-    sc sum0, sum1;
-    sc_set0(sum0);
-    sc_set0(sum1);
-#pragma unroll 1
-    for (uint32_t p = g * K; p < g * K + K && p < num; p++) {
-        const VScal& vs = vscal[p];
-        if (!vs.valid) continue;  // whole CTA
-        const sc w1 = wts[p].w1, w2 = wts[p].w2;
-        if (t == (int)n) {  // h: w1 taux + w2 (mu + ab - t)
-            sc a, b;
-            sc_mul_nf(a, w1, vs.h1);
-            sc_mul_nf(b, w2, vs.h2);
-            sc_add(a, a, b);
-            sc_add(sum0, sum0, a);
-        } else if (t == (int)n + 1) {  // g: w1 (t - delta)
-            sc a;
-            sc_mul_nf(a, w1, vs.g1);
-            sc_add(sum0, sum0, a);
-        } else if (t == (int)n + 2) {
-            sc a;
-            sc_mul_nf(a, w2, vs.a);
-            wsc[0] = a;
-            sc_mul_nf(a, w2, vs.b);
-            wsc[1] = a;
-            sc_mul_nf(a, w2, vs.z);
-            wsc[2] = a;
-            sc_mul_nf(a, w2, vs.z2);
-            wsc[3] = a;
-        } else if (t >= (int)n + 3 && t - (int)n - 3 < nvar) {
-            int q = t - (int)n - 3;
-            sc sv;
-            if (q == 0) sv = w2;
-            else {
-                if (q == 1) sv = vs.x;
-                else if (q < 2 + k) sv = vs.usq[q - 2];
-                else if (q < nvar2) sv = vs.uinvsq[q - 2 - k];
-                else if (q == nvar2) sv = vs.z2;
-                else if (q == nvar2 + 1) sv = vs.x;
-                else sv = vs.x2;
-                sc_mul_nf(sv, sv, q < nvar2 ? w2 : w1);
-            }
-            sc_recode_signed<kVarBits>(vdigits + ((size_t)p * kVarMax + q) * 64, sv, kVarWin);
+    const sc w1 = wts[p].w1, w2 = wts[p].w2;
+    sc* row = cw + (size_t)p * kRowsMax;
+    if (t == (int)n) {  // h: w1 taux + w2 (mu + ab - t)
+        sc a, b;
+        sc_mul_nf(a, w1, vs.h1);
+        sc_mul_nf(b, w2, vs.h2);
+        sc_add(a, a, b);
+        row[2 * n + 1] = a;
+    } else if (t == (int)n + 1) {  // g: w1 (t - delta)
+        sc a;
+        sc_mul_nf(a, w1, vs.g1);
+        row[2 * n] = a;
+    } else if (t >= (int)n + 3 && t - (int)n - 3 < nvar) {
+        int q = t - (int)n - 3;
+        sc sv;
+        if (q == 0) sv = w2;
+        else {
+            if (q == 1) sv = vs.x;
+            else if (q < 2 + k) sv = vs.usq[q - 2];
+            else if (q < nvar2) sv = vs.uinvsq[q - 2 - k];
+            else if (q == nvar2) sv = vs.z2;
+            else if (q == nvar2 + 1) sv = vs.x;
+            else sv = vs.x2;
+            sc_mul_nf(sv, sv, q < nvar2 ? w2 : w1);
         }
-        if (t == 0) {
-            s_sh[0] = vs.s0;
-            sc one;
-            sc_set1(one);
-            y_sh[0] = one;
+        sc_recode_signed<kVarBits>(vdigits + ((size_t)p * kVarMax + q) * 64, sv, kVarWin);
+    }
+    if (t == 0) {
+        s_sh[0] = vs.s0;
+        sc one;
+        sc_set1(one);
+        y_sh[0] = one;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int m = 0; m < k; m++) {
+        const int half = 1 << m;
+        if (half >= 32) __syncthreads();
+        if (t >= half && t < 2 * half) {
+            sc a = s_sh[t - half], b = y_sh[t - half];
+            sc_mul_nf(a, a, vs.usq[k - 1 - m]);
+            sc_mul_nf(b, b, vs.ypow[m]);
+            s_sh[t] = a;
+            y_sh[t] = b;
         }
         __syncwarp();
-#pragma unroll 1
-        for (int m = 0; m < k; m++) {
-            const int half = 1 << m;
-            if (half >= 32) __syncthreads();
-            if (t >= half && t < 2 * half) {
-                sc a = s_sh[t - half], b = y_sh[t - half];
-                sc_mul_nf(a, a, vs.usq[k - 1 - m]);
-                sc_mul_nf(b, b, vs.ypow[m]);
-                s_sh[t] = a;
-                y_sh[t] = b;
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        if (t < (int)n) {
-            sc cg, ch, tmp, two_i;
-            const sc wa = wsc[0], wb = wsc[1], wz = wsc[2], wz2 = wsc[3];  // written before the barriers above
-            sc_mul_nf(cg, wa, s_sh[t]);
-            sc_add(cg, cg, wz);
-            sc_set0(two_i);
-            two_i.v[t >> 5] = 1u << (t & 31);
-            sc_mul_nf(tmp, wz2, two_i);
-            sc_mul_nf(ch, wb, s_sh[n - 1 - t]);
-            sc_sub(ch, ch, tmp);
-            sc_mul_nf(ch, ch, y_sh[t]);
-            sc_sub(ch, ch, wz);
-            sc_add(sum0, sum0, cg);
-            sc_add(sum1, sum1, ch);
-        }
-        __syncthreads();  // the next member overwrites the ladders
     }
-    int8_t* grow = gdigits + (size_t)g * kRowsMax * kFixRowBytes;
+    __syncthreads();
     if (t < (int)n) {
-        fix_recode(grow + (size_t)t * kFixRowBytes, sum0, wbits);
-        fix_recode(grow + (size_t)(n + t) * kFixRowBytes, sum1, wbits);
-    } else if (t == (int)n) {
-        fix_recode(grow + (size_t)(2 * n + 1) * kFixRowBytes, sum0, wbits);  // base 2n + 1 = h
-    } else if (t == (int)n + 1) {
-        fix_recode(grow + (size_t)(2 * n) * kFixRowBytes, sum0, wbits);  // base 2n = g
+        // w2 enters through w2 a, w2 b, w2 z, w2 z^2 (every thread its own four products: cheaper than a barrier)
+        sc wa, wb, wz, wz2, cg, ch, tmp, two_i;
+        sc_mul_nf(wa, w2, vs.a);
+        sc_mul_nf(wb, w2, vs.b);
+        sc_mul_nf(wz, w2, vs.z);
+        sc_mul_nf(wz2, w2, vs.z2);
+        sc_mul_nf(cg, wa, s_sh[t]);
+        sc_add(cg, cg, wz);
+        sc_set0(two_i);
+        two_i.v[t >> 5] = 1u << (t & 31);
+        sc_mul_nf(tmp, wz2, two_i);
+        sc_mul_nf(ch, wb, s_sh[n - 1 - t]);
+        sc_sub(ch, ch, tmp);
+        sc_mul_nf(ch, ch, y_sh[t]);
+        sc_sub(ch, ch, wz);
+        row[t] = cg;
+        row[n + t] = ch;
     }
+}
+__global__ void __launch_bounds__(128) vg_rowsum_kernel(const uint8_t* __restrict__ gens, const VScal* __restrict__ vscal,
+                                                        const sc* __restrict__ cw, uint32_t n, uint32_t K, uint32_t num,
+                                                        uint32_t ngroups, int8_t* __restrict__ gdigits,
+                                                        const uint32_t* __restrict__ dyn_groups = nullptr,
+                                                        const uint32_t* __restrict__ index = nullptr) {
+    const uint32_t nrows = 2 * n + 2;
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dyn_groups) ngroups = *dyn_groups;
+    if (id >= ngroups * nrows) return;
+    const uint32_t g = id / nrows, r = id % nrows;
+    const int wbits = (int)reinterpret_cast<const GensHeader*>(gens)->wbits;
+    sc sum;
+    sc_set0(sum);
+#pragma unroll 1
+    for (uint32_t m = g * K; m < g * K + K && (index || m < num); m++) {
+        const uint32_t p = index ? index[m] : m;
+        if (!vscal[p].valid) continue;
+        sc_add(sum, sum, cw[(size_t)p * kRowsMax + r]);
+    }
+    fix_recode(gdigits + ((size_t)g * kRowsMax + r) * kFixRowBytes, sum, wbits);
 }
 // fixed-base sum of a group: one CTA of 128 threads, lane = window, the 2n+2 rows dealt round-robin to the 128 / LP
 // row slices (16-bit tables: 8 slices of 16 lanes); warp butterflies, then the four warp sums through shared memory
 template <int WBITS>
 __global__ void __launch_bounds__(128) vg_fixed_kernel(const uint8_t* __restrict__ gens, const int8_t* __restrict__ gdigits,
-                                                       uint32_t n, uint8_t* __restrict__ gfsum) {
+                                                       uint32_t n, uint8_t* __restrict__ gfsum,
+                                                       const uint32_t* __restrict__ dyn_groups = nullptr) {
+    if (dyn_groups && blockIdx.x >= *dyn_groups) return;  // whole CTA
     __shared__ __align__(16) uint8_t sh[4][128];
     constexpr int LP = 256 / WBITS;
     constexpr int S = 128 / LP;
@@ -1022,8 +1008,11 @@ __global__ void __launch_bounds__(128) vg_fixed_kernel(const uint8_t* __restrict
 // window sums of a group: thread per (group, window) over the points of all its valid members
 __global__ void __launch_bounds__(128) vg_winsum_kernel(const VScal* __restrict__ vscal, const int8_t* __restrict__ vdigits,
                                                         const uint8_t* __restrict__ vtab, int k, uint32_t K, uint32_t num,
-                                                        uint32_t ngroups, uint8_t* __restrict__ gwinsum) {
+                                                        uint32_t ngroups, uint8_t* __restrict__ gwinsum,
+                                                        const uint32_t* __restrict__ dyn_groups = nullptr,
+                                                        const uint32_t* __restrict__ index = nullptr) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dyn_groups) ngroups = *dyn_groups;
     if (id >= ngroups * kVarWin) return;
     const uint32_t g = id / kVarWin;
     const int w = (int)(id % kVarWin);
@@ -1031,7 +1020,8 @@ __global__ void __launch_bounds__(128) vg_winsum_kernel(const VScal* __restrict_
     ge_p3 ws;
     ge_p3_0(ws);
 #pragma unroll 1
-    for (uint32_t p = g * K; p < g * K + K && p < num; p++) {
+    for (uint32_t m = g * K; m < g * K + K && (index || m < num); m++) {
+        const uint32_t p = index ? index[m] : m;
         if (!vscal[p].valid) continue;
 #pragma unroll 1
         for (int q = 0; q < nvar; q++) {
@@ -1053,8 +1043,10 @@ __global__ void __launch_bounds__(128) vg_winsum_kernel(const VScal* __restrict_
 // Horner over the window sums of a group and the comparison with its fixed-base sum: one warp per group in octet
 // form (255 doublings + 51 additions deep at 0.63 / 0.82 us; all groups of a pass are resident at once)
 __global__ void __launch_bounds__(128) vg_finish_kernel(const uint8_t* __restrict__ gfsum, const uint8_t* __restrict__ gwinsum,
-                                                        uint32_t ngroups, uint8_t* __restrict__ gflags) {
+                                                        uint32_t ngroups, uint8_t* __restrict__ gflags,
+                                                        const uint32_t* __restrict__ dyn_groups = nullptr) {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (dyn_groups) ngroups = *dyn_groups;
     if (g >= ngroups) return;  // whole warp
     const Fe8Lane L = fe8_lane();
     const uint8_t* ws = gwinsum + (size_t)g * kVarWin * 128;
@@ -1094,23 +1086,11 @@ __global__ void vg_decide_kernel(const VScal* __restrict__ vscal, const uint8_t*
         fb_index[atomicAdd(fb_count, 1u)] = p;
     }
 }
-// copies of the queued records (and of their external commitments), 16 bytes per thread
-__global__ void vg_gather_kernel(const uint8_t* __restrict__ proofs, size_t rec_bytes, const uint8_t* __restrict__ Vext,
-                                 const uint32_t* __restrict__ fb_count, const uint32_t* __restrict__ fb_index,
-                                 uint8_t* __restrict__ fb_records, uint8_t* __restrict__ fb_V) {
-    const uint32_t per = (uint32_t)(rec_bytes / 16) + 8;  // + the 128 bytes of V
-    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t slot = (uint32_t)(id / per), part = (uint32_t)(id % per);
-    if (slot >= *fb_count) return;
-    const uint32_t p = fb_index[slot];
-    const uint32_t rparts = per - 8;
-    if (part < rparts) {
-        reinterpret_cast<uint4*>(fb_records + (size_t)slot * rec_bytes)[part] =
-            reinterpret_cast<const uint4*>(proofs + (size_t)p * rec_bytes)[part];
-    } else if (Vext) {
-        reinterpret_cast<uint4*>(fb_V + (size_t)slot * 128)[part - rparts] =
-            reinterpret_cast<const uint4*>(Vext + (size_t)p * 128)[part - rparts];
-    }
+// second pass: the verdict of queue slot s is the verdict of proof fb_index[s]
+__global__ void vg_decide_single_kernel(const uint8_t* __restrict__ gflags, const uint32_t* __restrict__ fb_count,
+                                        const uint32_t* __restrict__ fb_index, uint8_t* __restrict__ accept) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < *fb_count) accept[fb_index[s]] = gflags[s];
 }
 
 static constexpr uint32_t kVerifySmallBatch = 64;  // up to this many proofs per call take the latency kernels
@@ -1195,13 +1175,13 @@ int bpk_gens_init_device(void* d_gens_ws, size_t ws_bytes, const void* d_G, cons
 struct VerifyLayout {
     size_t vscal, fsum, winsum, flags, digits, vdigits, vtab, vseed;
     // grouped verification: record digests, weights, per-group digit rows / sums / flags, second-pass queue and copies
-    size_t leaves, digest, wts, gdigits, gfsum, gwinsum, gflags, fb_count, fb_index, fb_records, fb_V;
+    size_t leaves, digest, wts, cw, gdigits, gfsum, gwinsum, gflags, fb_count, fb_index;
     size_t total;
 };
 static constexpr uint32_t kVerifyGroupMin = 2;     // smallest group the grouped path is used with
-static constexpr uint32_t kVerifyGroupDefault = 8;
+static constexpr uint32_t kVerifyGroupDefault = 12;  // measured at 2^14 proofs, 1 % tampered: 4 / 8 / 12 / 16 -> 4.41 / 3.78 / 3.63 / 3.77 ms
 static constexpr uint32_t kVerifyGroupBatchMin = 256;  // below this many proofs per call: one by one
-static VerifyLayout verify_layout(size_t chunk, size_t rec_bytes) {
+static VerifyLayout verify_layout(size_t chunk, size_t rec_bytes) {  // rec_bytes sizes the leaf digests
     VerifyLayout L;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -1217,18 +1197,17 @@ static VerifyLayout verify_layout(size_t chunk, size_t rec_bytes) {
     L.vdigits = take(chunk * kVarMax * 64);
     L.vtab = take(chunk * kVarMax * kVarEntries * 128);
     L.vseed = take(chunk * 2 * kVarEntries * 128);
-    const size_t groups = (chunk + kVerifyGroupMin - 1) / kVerifyGroupMin;  // upper bound for any group size
+    const size_t groups = chunk;  // the second pass treats every queued proof as a group of one
     L.leaves = take(chunk * ((rec_bytes + 191) / 192) * 32);
     L.digest = take(chunk * 32);
     L.wts = take(chunk * sizeof(VWeights));
+    L.cw = take(chunk * kRowsMax * sizeof(sc));
     L.gdigits = take(groups * kRowsMax * kFixRowBytes);
     L.gfsum = take(groups * 128);
     L.gwinsum = take(groups * kVarWin * 128);
     L.gflags = take(groups);
     L.fb_count = take(4);
     L.fb_index = take(chunk * 4);
-    L.fb_records = take(chunk * rec_bytes);
-    L.fb_V = take(chunk * 128);
     L.total = off;
     return L;
 }
@@ -1310,9 +1289,10 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
             uint32_t *leaves = (uint32_t*)(ws + L.leaves), *digest = (uint32_t*)(ws + L.digest);
             VWeights* wts = (VWeights*)(ws + L.wts);
             int8_t* gdigits = (int8_t*)(ws + L.gdigits);
+            sc* cw = (sc*)(ws + L.cw);
+            const uint32_t nrows = (uint32_t)(2 * n + 2);
             uint8_t *gfsum = ws + L.gfsum, *gwinsum = ws + L.gwinsum, *gflags = ws + L.gflags;
             uint32_t *fb_count = (uint32_t*)(ws + L.fb_count), *fb_index = (uint32_t*)(ws + L.fb_index);
-            uint8_t *fb_records = ws + L.fb_records, *fb_V = ve ? ws + L.fb_V : nullptr;
             const uint32_t G = (cnt + K - 1) / K;
             // side stream, under the transcript: record digests and weights (the coefficients wait for them), then
             // the tables of the per-proof points (the window sums wait for those); all need only the records
@@ -1329,8 +1309,10 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
             CBP_CUDA(cudaEventRecord(side->ev_join, ss));
             CBP_CUDA(cudaMemsetAsync(fb_count, 0, 4, st));
             CBP_CUDA(cudaStreamWaitEvent(st, side->ev_weights, 0));
-            vg_coeff_kernel<<<G, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, wts, (uint32_t)n, k, K, cnt, gdigits,
-                                                         vdigits);
+            vg_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>(vscal, wts, (uint32_t)n, k, cw, vdigits);
+            CBP_CHECK_LAUNCH();
+            vg_rowsum_kernel<<<(G * nrows + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, cw, (uint32_t)n, K, cnt, G,
+                                                                      gdigits);
             CBP_CHECK_LAUNCH();
             CBP_CUDA(cudaStreamWaitEvent(st, side->ev_join, 0));
             // the groups' fixed-base sums (few, latency-bound CTAs) on the side stream, under the window sums
@@ -1349,31 +1331,22 @@ int bpk_range_verify_batch_device(const void* d_gens_ws, const void* d_proofs, c
             CBP_CHECK_LAUNCH();
             vg_decide_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(vscal, gflags, K, cnt, d_accept + done, fb_count, fb_index);
             CBP_CHECK_LAUNCH();
-            // second pass: the members of failed groups, one by one, count on the device (grids sized for all of them)
-            const size_t gthreads = (size_t)cnt * (rec / 16 + 8);
-            vg_gather_kernel<<<(unsigned)((gthreads + 255) / 256), 256, 0, st>>>(pr, rec, ve, fb_count, fb_index, fb_records,
-                                                                                fb_V);
+            // second pass: every member of a failed group as a group of ONE (its two identities combined with its own
+            // weights), on what the first pass left of it — transcript scalars, weights, point tables; count and indices
+            // on the device, grids sized for the whole batch, slots beyond the count exit at once
+            // (their coefficient scalars cw[] and weighted digit rows are those of the first pass)
+            vg_rowsum_kernel<<<(cnt * nrows + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, cw, (uint32_t)n, 1, cnt,
+                                                                        cnt, gdigits, fb_count, fb_index);
             CBP_CHECK_LAUNCH();
-            verify_transcript_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(fb_records, rec, fb_V, (uint32_t)n, k, cnt, vscal, fb_count);
+            if (wbits == 8) vg_fixed_kernel<8><<<cnt, 128, 0, st>>>((const uint8_t*)d_gens_ws, gdigits, (uint32_t)n, gfsum, fb_count);
+            else vg_fixed_kernel<16><<<cnt, 128, 0, st>>>((const uint8_t*)d_gens_ws, gdigits, (uint32_t)n, gfsum, fb_count);
             CBP_CHECK_LAUNCH();
-            verify_vtab_kernel<<<(cnt * nvar + 127) / 128, 128, 0, st>>>(fb_records, rec, k, cnt, vtab, vseed, fb_count);
+            vg_winsum_kernel<<<(cnt * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, k, 1, cnt, cnt, gwinsum, fb_count,
+                                                                          fb_index);
             CBP_CHECK_LAUNCH();
-            verify_coeff_kernel<<<cnt, kCoeffThreads, 0, st>>>((const uint8_t*)d_gens_ws, vscal, (uint32_t)n, k, digits, vdigits,
-                                                               fb_count);
+            vg_finish_kernel<<<(cnt * 32 + 127) / 128, 128, 0, st>>>(gfsum, gwinsum, cnt, gflags, fb_count);
             CBP_CHECK_LAUNCH();
-            if (wbits == 8)
-                verify_fixed_kernel<8><<<(cnt * 32 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
-                                                                               (uint32_t)n, cnt, fsum, fb_count);
-            else
-                verify_fixed_kernel<16><<<(cnt * 16 + 127) / 128, 128, 0, st>>>((const uint8_t*)d_gens_ws, vscal, digits,
-                                                                                (uint32_t)n, cnt, fsum, fb_count);
-            CBP_CHECK_LAUNCH();
-            verify_winsum_kernel<<<(cnt * 2 * kVarWin + 127) / 128, 128, 0, st>>>(vscal, vdigits, vtab, vseed, k, cnt, winsum,
-                                                                                   fb_count);
-            CBP_CHECK_LAUNCH();
-            verify_finish_kernel<<<(cnt * 2 + 63) / 64, 64, 0, st>>>(vscal, fsum, winsum, cnt, flags, fb_count);
-            CBP_CHECK_LAUNCH();
-            verify_combine_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(flags, cnt, d_accept + done, fb_count, fb_index);
+            vg_decide_single_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(gflags, fb_count, fb_index, d_accept + done);
             CBP_CHECK_LAUNCH();
             continue;
         }
