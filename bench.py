@@ -34,7 +34,8 @@ VERIFY_PROOFS_DEFAULT = 1 << 14
 INT_PEAK_PLANNING_TIMAD = 18.6  # SURVEY.md section 8d planning figure (148 SM x 4 x 16 lanes x 1.965 GHz, 32-bit IMAD)
 INT_PEAK_FALLBACK_TIMAD = 9.0   # round-1 measurement (profiles/r01_microbench_int_pipe.jsonl); used only if the in-run
                                 # microbenchmark fails, and then labelled "fallback"
-KERNEL_SOURCES = ("msm.cu", "ge25519.cuh", "fe25519.cuh", "rangeproof.cu", "rangeproof.cuh", "sc25519.cuh")
+KERNEL_SOURCES = {"msm": ("msm.cu", "ge25519.cuh", "fe25519.cuh", "fe8.cuh"),
+                  "verify": ("rangeproof.cu", "rangeproof.cuh", "ge25519.cuh", "fe25519.cuh", "fe8.cuh", "sc25519.cuh")}
 P25519 = 2**255 - 19
 L25519 = 2**252 + 27742317777372353535851937790883648493
 
@@ -73,12 +74,13 @@ def measure_int_peak(lib, target_ms=20.0):
     return rec
 
 
-def kernel_source_hash():
-    """sha256 over the CUDA sources that define the profiled kernels: ties a committed ncu summary to the code it
-    was taken from (the GPU box has no .git, so a commit hash cannot be checked there)."""
+def kernel_source_hash(kind):
+    """sha256 over the CUDA sources that define the profiled kernel (`kind`: an ncu summary name, msm_* or a verifier
+    kernel): ties a committed ncu summary to the code it was taken from (the GPU box has no .git, so a commit hash
+    cannot be checked there)."""
     import hashlib
     h = hashlib.sha256()
-    for name in KERNEL_SOURCES:
+    for name in KERNEL_SOURCES["msm" if kind.startswith("msm") else "verify"]:
         with open(os.path.join(ROOT, "cudabulletproof_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -94,9 +96,9 @@ def ncu_summary(kind):
             d = json.load(f)
     except (OSError, ValueError):
         return None, f"no profiles/ncu_{kind}.json"
-    if d.get("source_hash") != kernel_source_hash():
+    if d.get("source_hash") != kernel_source_hash(kind):
         return None, (f"profiles/ncu_{kind}.json was taken at source hash {d.get('source_hash')} (git {d.get('git')}), "
-                      f"this build is {kernel_source_hash()}: not reported")
+                      f"this build is {kernel_source_hash(kind)}: not reported")
     return d, None
 
 
@@ -446,13 +448,29 @@ def run_cuda(args):
                                    "result_matches_device_path": h_out.tobytes()[:64].hex() == result_hex}
             lib.bpk_debug_set_option(6, 0)
             lib.bpk_host_release()
+        # the documented extension for callers that can hand over affine points (x || y, 64 B): 96 B per pair on the wire
+        affine = None
+        if world == 1:
+            h_xy = torch.empty((n, 64), dtype=torch.uint8).pin_memory()
+            h_xy.copy_(pts[:, :64])  # the synthetic points are normalised (Z = 1)
+            h_out[:] = 0
+            for _ in range(2):
+                lib.bpk_msm_host_affine(h_out.ctypes.data_as(C.c_void_p), h_sc.data_ptr(), h_xy.data_ptr(), n)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                lib.bpk_msm_host_affine(h_out.ctypes.data_as(C.c_void_p), h_sc.data_ptr(), h_xy.data_ptr(), n)
+            torch.cuda.synchronize()
+            ams = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            affine = {"ms_per_step": ams, "value": n / (ams * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 96,
+                      "api": "bpk_msm_host_affine (extension: 64-byte affine points, pinned host buffers)",
+                      "result_matches_device_path": h_out.tobytes()[:64].hex() == result_hex}
         return {"ms": ms, "n": n, "clocks": clocks, "launches": int(launches), "roofline": roofline,
                 "roofline_hbm": roofline_hbm, "window_bits": msm.window_bits, "phases": phases,
                 "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "points/s",
                         "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": 128,
                         "api": "cuda_point_vector_multi_scalar_mul (host pointers, pinned)", "ms_per_step": e2e_ms / e2e_steps,
                         "result_matches_device_path": (e2e_hex == result_hex) if world == 1 else None,
-                        "pageable": pageable or None},
+                        "pageable": pageable or None, "affine_extension": affine},
                 "result_xy": result_hex}
 
     # ---------------- strong scaling: ONE global MSM cut into point-range shards ------

@@ -64,6 +64,8 @@ SIGNATURES = {
     "bpk_msm_workspace_bytes": (_i, [_sz, _i, C.POINTER(_sz)]),
     "bpk_msm_window_bits": (_i, [_sz]),
     "bpk_msm_device": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp]),
+    "bpk_msm_device_affine": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _i, _i, _vp]),
+    "bpk_msm_host_affine": (_i, [_vp, _vp, _vp, _sz]),
     "bpk_point_sum_device": (_i, [_vp, _sz, _vp, _i, _vp]),
     "bpk_fe_batch_device": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bpk_fe_batch_invert_workspace_bytes": (_i, [_sz, C.POINTER(_sz)]),

@@ -230,6 +230,20 @@ int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* 
     count_launches(launches);
     return fail_cuda(rc);
 }
+int bpk_msm_device_affine(const void* d_scalars, const void* d_xy, size_t n, void* d_result, void* d_workspace,
+                          size_t workspace_bytes, int window_bits, int normalize, void* stream) {
+    if (!d_result || (n && (!d_scalars || !d_xy || !d_workspace))) return fail(BPK_ERR_ARG);
+    if (window_bits < 0 || window_bits > 17 || (window_bits > 0 && window_bits < 4) || !msm_size_ok(n, window_bits))
+        return fail(BPK_ERR_ARG);
+    MsmPlan p;
+    msm_make_plan(&p, n, window_bits);
+    if (n && workspace_bytes < p.workspace_bytes) return fail(BPK_ERR_WORKSPACE);
+    int launches = 0;
+    int rc = msm_run(p, d_scalars, d_xy, d_result, d_workspace, normalize, (cudaStream_t)stream, &launches, nullptr, 0,
+                     kMsmAffineXY);
+    count_launches(launches);
+    return fail_cuda(rc);
+}
 int bpk_point_sum_device(const void* d_points, size_t count, void* d_result, int normalize, void* stream) {
     if (!d_result || (count && !d_points)) return fail(BPK_ERR_ARG);
     point_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const uint8_t*)d_points, count, normalize, (uint8_t*)d_result);
@@ -436,8 +450,9 @@ void trace_dump() {
 }
 }  // namespace
 
-static int msm_host(ge25519* result, const FieldVector* scalars, const PointVector* points) {
-    size_t n = scalars->length;
+// point_bytes = 128: the reference's extended ge25519; 64: affine x || y (bpk_msm_host_affine)
+static int msm_host(ge25519* result, const fe25519* scalars_h, const void* points_h, size_t n, size_t point_bytes) {
+    const int pflag = point_bytes == 64 ? kMsmAffineXY : 0;
     DeviceLock dlock;
     if (!dlock.ok()) return BPK_ERR_CUDA;
     HostPath& hp = g_hp[dlock.dev];
@@ -459,14 +474,14 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
         hp.ok = true;
     }
     if (n) {
-        if ((e = grow(&hp.d_s, &hp.cap_s, n * 32)) != cudaSuccess || (e = grow(&hp.d_p, &hp.cap_p, n * 128)) != cudaSuccess)
+        if ((e = grow(&hp.d_s, &hp.cap_s, n * 32)) != cudaSuccess || (e = grow(&hp.d_p, &hp.cap_p, n * point_bytes)) != cudaSuccess)
             return fail(BPK_ERR_CUDA, e);
     }
     int launches = 0;
-    const uint8_t* h_s = (const uint8_t*)scalars->elements;
-    const uint8_t* h_p = (const uint8_t*)points->elements;
+    const uint8_t* h_s = (const uint8_t*)scalars_h;
+    const uint8_t* h_p = (const uint8_t*)points_h;
     maybe_register(h_s, n * 32);
-    maybe_register(h_p, n * 128);
+    maybe_register(h_p, n * point_bytes);
     // pageable inputs take the chunked pipeline from 2^18 points: their upload is staged chunk by chunk anyway
     const bool staged = n >= ((size_t)1 << 18) && (is_pageable(h_s) || is_pageable(h_p));
     if (n < kHostChunkMin && !staged) {
@@ -476,15 +491,18 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
         if (n) {
             if ((e = grow(&hp.d_ws[0], &hp.cap_ws[0], p.workspace_bytes)) != cudaSuccess ||
                 (e = cudaMemcpyAsync(hp.d_s, h_s, n * 32, cudaMemcpyHostToDevice, hp.main)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(hp.d_p, h_p, n * 128, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(hp.d_p, h_p, n * point_bytes, cudaMemcpyHostToDevice, hp.copy)) != cudaSuccess ||
                 (e = cudaEventRecord(hp.ev_points, hp.copy)) != cudaSuccess)
                 return fail(BPK_ERR_CUDA, e);
         }
-        int rc = msm_run(p, hp.d_s, hp.d_p, hp.d_r, hp.d_ws[0], 1, hp.main, &launches, n ? hp.ev_points : nullptr);
+        int rc = msm_run(p, hp.d_s, hp.d_p, hp.d_r, hp.d_ws[0], 1, hp.main, &launches, n ? hp.ev_points : nullptr, 0, pflag);
         count_launches(launches);
         if (rc) return fail_cuda(rc);
     } else {
-        size_t chunk = kHostChunk;
+        // (affine points halve the bytes per chunk: the bucket sums then need twice the points per chunk to keep up with
+        // the wire — 2^20 pairs from pinned memory, chunks of 2^17 / 2^18 / 2^19: 3.08 / 2.63 / 2.80 ms; the reference layout
+        // is best at 2^17: 3.70 / 3.75 / 4.61 ms)
+        size_t chunk = pflag ? 2 * kHostChunk : kHostChunk;
         if (const int lg = options().host_chunk_log2; lg >= 15 && lg <= 26) chunk = (size_t)1 << lg;  // tuning knob
         size_t nchunks = (n + chunk - 1) / chunk;
         if (nchunks > (size_t)kMaxChunks) {  // keep the event pool bounded for enormous inputs
@@ -536,7 +554,7 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
             }
         // pageable inputs go through two pinned staging buffers, filled by the copy pool while the previous piece
         // is on the wire
-        const size_t stage_bytes = chunk * 128;
+        const size_t stage_bytes = chunk * 128;  // (affine points need half of it)
         if (staged && hp.cap_stage < stage_bytes) {
             for (int b = 0; b < 2; b++) {
                 if (hp.stage[b]) cudaFreeHost(hp.stage[b]);
@@ -578,7 +596,8 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
         };
         auto copy_points = [&](size_t c) -> cudaError_t {
             cudaError_t r;
-            if ((r = upload(hp.d_p + lo_of[c] * 128, h_p + lo_of[c] * 128, cnt_of[c] * 128)) != cudaSuccess) return r;
+            if ((r = upload(hp.d_p + lo_of[c] * point_bytes, h_p + lo_of[c] * point_bytes, cnt_of[c] * point_bytes)) != cudaSuccess)
+                return r;
             r = cudaEventRecord(hp.ev_chunk[c], hp.copy);
             trace_mark("points-in", c, hp.copy);
             return r;
@@ -604,8 +623,8 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
                 (r = cudaStreamWaitEvent(hp.main, hp.ev_front[c], 0)) != cudaSuccess)
                 return (int)r;
             int nl = 0;
-            int rc = msm_run(plan_of(c), hp.d_s + lo_of[c] * 32, hp.d_p + lo_of[c] * 128, hp.d_r, hp.d_ws[0], 1, hp.main, &nl,
-                             nullptr, 0, chunk_flags(c) | kMsmBackOnly, hp.d_front + c * front_bytes);
+            int rc = msm_run(plan_of(c), hp.d_s + lo_of[c] * 32, hp.d_p + lo_of[c] * point_bytes, hp.d_r, hp.d_ws[0], 1, hp.main,
+                             &nl, nullptr, 0, chunk_flags(c) | kMsmBackOnly | pflag, hp.d_front + c * front_bytes);
             launches += nl;
             trace_mark("summed", c, hp.main);
             return rc;
@@ -659,6 +678,10 @@ static int msm_host(ge25519* result, const FieldVector* scalars, const PointVect
     return BPK_OK;
 }
 
+int bpk_msm_host_affine(void* result, const void* scalars, const void* xy, size_t n) {
+    if (!result || (n && (!scalars || !xy))) return fail(BPK_ERR_ARG);
+    return msm_host((ge25519*)result, (const fe25519*)scalars, xy, n, 64);
+}
 int bpk_host_release(void) {
     std::lock_guard<std::mutex> lk(g_reg_mu);
     for (const Registered& r : g_registered) cudaHostUnregister((void*)r.base);
@@ -673,7 +696,7 @@ void cuda_point_vector_multi_scalar_mul(ge25519* result, const FieldVector* scal
         fail(BPK_ERR_ARG);
         return;
     }
-    msm_host(result, scalars, points);
+    msm_host(result, scalars->elements, points->elements, scalars->length, 128);
 }
 void cuda_point_vector_multi_scalar_mul_shared(ge25519* result, const FieldVector* scalars, const PointVector* points) {
     cuda_point_vector_multi_scalar_mul(result, scalars, points);

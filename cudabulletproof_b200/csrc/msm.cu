@@ -96,6 +96,19 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const uint8_t* __re
     }
 }
 
+// the same from affine input (x || y, 64 bytes per point): one point per thread, no inversion
+__global__ void __launch_bounds__(128) msm_precompute_affine_kernel(const uint8_t* __restrict__ xy, size_t n,
+                                                                    uint8_t* __restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y;
+    fe_load(x, xy + i * 64);
+    fe_load(y, xy + i * 64 + 32);
+    ge_niels q;
+    ge_to_niels_affine(q, x, y);
+    ge_niels_store(table + i * 96, q);
+}
+
 // ---- 2./4. digit recoding: histogram and scatter ------------------------------------------------
 // Measured and rejected: a two-level counting sort with shared-memory atomics only (keys first partitioned by
 // (window, high 5 bucket bits) with one global atomic per (CTA, partition), then one CTA sorts each partition by
@@ -1245,7 +1258,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (launches) *launches = 0;
         return (int)e;
     }
-    if (p.small && flags == 0) {
+    if (p.small && flags == 0) {  // (chunked and affine inputs always take the bucket path)
         cudaError_t e;
         if (points_ready && (e = cudaStreamWaitEvent(st, points_ready, 0)) != cudaSuccess) return (int)e;
         uint8_t* tables = ws + p.off_stables;
@@ -1320,7 +1333,10 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (points_ready && (e = cudaStreamWaitEvent(ps, points_ready, 0)) != cudaSuccess) return (int)e;
         size_t threads = (n + kPreChunk - 1) / kPreChunk;
         prof_begin(BPK_PROF_MSM_PRECOMPUTE, ps);
-        msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ps>>>((const uint8_t*)d_points, n, table);
+        if (flags & kMsmAffineXY)
+            msm_precompute_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ps>>>((const uint8_t*)d_points, n, table);
+        else
+            msm_precompute_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ps>>>((const uint8_t*)d_points, n, table);
         prof_end(BPK_PROF_MSM_PRECOMPUTE, ps);
         CBP_LAUNCH_CHECK(); nl++;
         if (kit && (e = cudaEventRecord(kit->ev_ready, ps)) != cudaSuccess) return (int)e;

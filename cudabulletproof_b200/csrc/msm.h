@@ -43,6 +43,9 @@ constexpr int kMsmCarryIn = 1, kMsmNoTail = 2;
 // part instead of the head of d_workspace, so that the sorted scalars of several chunks can wait for their points
 // while the chunks share one set of buckets (the chunked host path sorts every chunk while the points upload).
 constexpr int kMsmFrontOnly = 4, kMsmBackOnly = 8;
+// kMsmAffineXY — d_points holds affine points, 64 bytes each (x || y as fe25519 containers, Z = 1 implied) instead of
+// the reference's 128-byte extended ge25519: 96 instead of 160 bytes per pair on the wire (bpk_msm_*_affine)
+constexpr int kMsmAffineXY = 16;
 inline size_t msm_front_bytes(const MsmPlan& p) { return p.off_buckets; }
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
             int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready, int kit_index = 0,

@@ -161,6 +161,15 @@ class Msm:
                                      1 if normalize else 0, _stream_ptr(stream)), "bpk_msm_device")
         return out
 
+    def affine(self, scalars, xy, normalize=True, out=None, stream=None):
+        """the same over affine points: xy cuda uint8 tensor (n, 64), x || y (bpk_msm_device_affine)"""
+        out = self.result if out is None else out
+        assert scalars.is_cuda and xy.is_cuda and scalars.numel() == self.n * 32 and xy.numel() == self.n * 64
+        _check(_lib().bpk_msm_device_affine(scalars.data_ptr(), xy.data_ptr(), self.n, out.data_ptr(),
+                                            self.workspace.data_ptr(), self.workspace.numel(), self._window_arg,
+                                            1 if normalize else 0, _stream_ptr(stream)), "bpk_msm_device_affine")
+        return out
+
 
 def point_sum(points, normalize=True, stream=None):
     """Sum of extended points (count, 128) uint8 on device -> (128,) uint8."""

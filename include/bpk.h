@@ -91,6 +91,13 @@ int bpk_msm_window_bits(size_t n);
 /* d_result: one ge25519 (128 B); normalize != 0 returns (x, y, 1, xy) canonical like the CPU MSM */
 int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* d_result, void* d_workspace,
                    size_t workspace_bytes, int window_bits, int normalize, void* stream);
+/* Extension (no counterpart in the reference): the same sum over AFFINE points, 64 bytes each (x || y as fe25519
+   containers, Z = 1 implied, not checked to be on the curve — like every point input of the reference): 96 instead of
+   160 bytes per pair, which is what bounds the host-pointer call (PCIe).  Workspace as for bpk_msm_device.
+   bpk_msm_host_affine takes host pointers (pinned or pageable) like cuda_point_vector_multi_scalar_mul. */
+int bpk_msm_device_affine(const void* d_scalars, const void* d_xy, size_t n, void* d_result, void* d_workspace,
+                          size_t workspace_bytes, int window_bits, int normalize, void* stream);
+int bpk_msm_host_affine(void* result /* ge25519 */, const void* scalars /* n fe25519 */, const void* xy, size_t n);
 /* sum of `count` extended points (multi-GPU partial results), normalised: d_result = sum d_points[i] */
 int bpk_point_sum_device(const void* d_points, size_t count, void* d_result, int normalize, void* stream);
 

@@ -193,6 +193,65 @@ def test_msm_host_pointer_chunked_upload(oracle):
     assert np.array_equal(got, dev)
 
 
+@pytest.mark.parametrize("chunk_log2,taper_log2", [(0, 0), (16, 0), (17, 13), (18, 15)])
+def test_msm_host_pointer_chunk_layouts_pinned(chunk_log2, taper_log2):
+    """The chunked host path sorts every chunk's scalars ahead of its points (msm_run front / back split, one front
+    workspace per chunk, shared buckets).  Pinned inputs (every copy queued before the first kernel), several chunk
+    sizes, a tapered and ragged last chunk: the result is the device-resident MSM's, byte for byte, call after call."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    n = (1 << 20) + 4097
+    pts, _ = cbp.synth_points(n, seed=0xE30)
+    sc = cbp.synth_scalars(n, seed=0x5EEE, bits=253)
+    want = cbp.Msm(n)(sc, pts).cpu().numpy().view(np.uint64)
+    h_sc = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    h_sc.copy_(sc)
+    h_pts = torch.empty((n, 128), dtype=torch.uint8).pin_memory()
+    h_pts.copy_(pts)
+    fv, pv = cbp.FieldVector(h_sc.data_ptr(), n), cbp.PointVector(h_pts.data_ptr(), n)
+    out = np.zeros(16, dtype=np.uint64)
+    try:
+        cbp.check(lib.bpk_debug_set_option(2, chunk_log2), "set_option")   # BPK_OPT_HOST_CHUNK_LOG2
+        cbp.check(lib.bpk_debug_set_option(10, taper_log2), "set_option")  # BPK_OPT_HOST_TAPER_LOG2
+        for _ in range(2):  # the second call reuses the front workspaces of the first
+            out[:] = 0
+            lib.cuda_point_vector_multi_scalar_mul(out.ctypes.data_as(C.c_void_p), C.byref(fv), C.byref(pv))
+            assert np.array_equal(out, want)
+    finally:
+        lib.bpk_debug_set_option(2, 0)
+        lib.bpk_debug_set_option(10, 0)
+
+
+@pytest.mark.parametrize("n", [1, 300, (1 << 16) + 5, (1 << 20) + 4097])
+def test_msm_affine_input_extension(n):
+    """bpk_msm_device_affine / bpk_msm_host_affine (64-byte x || y points, an extension without a counterpart in the
+    reference): the same bytes as the reference-layout MSM over the same points, on the device and through the
+    host-pointer path (one piece below 2^20 pairs, chunked above), also when some coordinates are given as x + p."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    pts, _ = cbp.synth_points(n, seed=0xAFF + n)
+    sc = cbp.synth_scalars(n, seed=0xAFE + n, bits=253)
+    msm = cbp.Msm(n)
+    want = msm(sc, pts).cpu().numpy().view(np.uint64).copy()
+    xy = pts[:, :64].contiguous()
+    h_xy = xy.cpu().numpy().copy()
+    P = 2**255 - 19
+    for i in range(0, n, max(1, n // 7)):  # weakly reduced containers: x + p, y + p
+        for off in (0, 32):
+            v = int.from_bytes(h_xy[i, off:off + 32].tobytes(), "little") + P
+            h_xy[i, off:off + 32] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+    xy = torch.from_numpy(h_xy).cuda()
+    got = msm.affine(sc, xy).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, want)
+    h_sc = sc.cpu().numpy().copy()
+    out = np.zeros(16, dtype=np.uint64)
+    cbp.check(lib.bpk_msm_host_affine(out.ctypes.data_as(C.c_void_p), h_sc.ctypes.data_as(C.c_void_p),
+                                      h_xy.ctypes.data_as(C.c_void_p), n), "bpk_msm_host_affine")
+    assert np.array_equal(out, want)
+
+
 def test_msm_host_pointer_chunked_equal_scalars(oracle):
     """chunks add into shared buckets (carry-in): with all scalars equal every chunk hits the same, split
     ("heavy") buckets, so the carry path of the split-bucket kernels is exercised"""

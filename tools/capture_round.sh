@@ -17,11 +17,11 @@ python tools/probe_phases.py --once 20 > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_msm20.csv \
     python tools/probe_phases.py --once 20 > /dev/null 2>&1
 python tools/probe_verify.py 1 > $out/${tag}_verify_plain.txt 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:verify_ -c 100 --csv --log-file $out/${tag}_launches_verify.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"verify_|vg_" -c 100 --csv --log-file $out/${tag}_launches_verify.csv \
     python tools/probe_verify.py 1 > /dev/null 2>&1
 # full captures
 ncu --set full --clock-control none --import-source on -k regex:msm_accumulate -c 8 -f -o $out/${tag}_acc \
     python tools/probe_phases.py --once 20 > $out/${tag}_ncu_acc.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:verify_fixed -c 2 -f -o $out/${tag}_verify_fixed \
+ncu --set full --clock-control none --import-source on -k regex:"vg_winsum|vg_fixed|vg_finish|vg_coeff" -c 8 -f -o $out/${tag}_verify \
     python tools/probe_verify.py 1 > $out/${tag}_ncu_verify.log 2>&1
 ls -la $out | tail -20

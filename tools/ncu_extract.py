@@ -41,7 +41,7 @@ def main():
         git = None
     rd = [val(r, "dram__bytes_read.sum") for r in launches]
     wr = [val(r, "dram__bytes_write.sum") for r in launches]
-    out = {"kernel": pattern, "file": os.path.relpath(path, ROOT), "git": git, "source_hash": kernel_source_hash(),
+    out = {"kernel": pattern, "file": os.path.relpath(path, ROOT), "git": git, "source_hash": kernel_source_hash(kind),
            "launches": len(launches), "dram_bytes": sum(rd) + sum(wr), "dram_read_bytes_per_launch": rd,
            "dram_write_bytes_per_launch": wr,
            "duration_us_per_launch": [val(r, "gpu__time_duration.sum") for r in launches],
