@@ -851,6 +851,7 @@ __global__ void __launch_bounds__(kCoeffThreads) vg_coeff_kernel(const VScal* __
                                                                  const VWeights* __restrict__ wts, uint32_t n, int k,
                                                                  sc* __restrict__ cw, int8_t* __restrict__ vdigits) {
     __shared__ sc s_sh[kMaxN], y_sh[kMaxN];
+    __shared__ sc wsc[4];  // w2 a, w2 b, w2 z, w2 z^2: the weight enters every G_t / H_t coefficient through these
     const uint32_t p = blockIdx.x;
     const int t = threadIdx.x;
     const VScal& vs = vscal[p];
@@ -868,6 +869,16 @@ __global__ void __launch_bounds__(kCoeffThreads) vg_coeff_kernel(const VScal* __
         sc a;
         sc_mul_nf(a, w1, vs.g1);
         row[2 * n] = a;
+    } else if (t == (int)n + 2) {  // under the ladder below; visible after its closing barrier
+        sc a;
+        sc_mul_nf(a, w2, vs.a);
+        wsc[0] = a;
+        sc_mul_nf(a, w2, vs.b);
+        wsc[1] = a;
+        sc_mul_nf(a, w2, vs.z);
+        wsc[2] = a;
+        sc_mul_nf(a, w2, vs.z2);
+        wsc[3] = a;
     } else if (t >= (int)n + 3 && t - (int)n - 3 < nvar) {
         int q = t - (int)n - 3;
         sc sv;
@@ -905,12 +916,8 @@ __global__ void __launch_bounds__(kCoeffThreads) vg_coeff_kernel(const VScal* __
     }
     __syncthreads();
     if (t < (int)n) {
-        // w2 enters through w2 a, w2 b, w2 z, w2 z^2 (every thread its own four products: cheaper than a barrier)
-        sc wa, wb, wz, wz2, cg, ch, tmp, two_i;
-        sc_mul_nf(wa, w2, vs.a);
-        sc_mul_nf(wb, w2, vs.b);
-        sc_mul_nf(wz, w2, vs.z);
-        sc_mul_nf(wz2, w2, vs.z2);
+        const sc wa = wsc[0], wb = wsc[1], wz = wsc[2], wz2 = wsc[3];
+        sc cg, ch, tmp, two_i;
         sc_mul_nf(cg, wa, s_sh[t]);
         sc_add(cg, cg, wz);
         sc_set0(two_i);
