@@ -47,6 +47,7 @@ Options& options() {
         opt.msm_small_max = num("CBP_MSM_SMALL_MAX", -1);
         opt.host_register = num("CBP_HOST_REGISTER", 0);
         opt.verify_group = num("CBP_VERIFY_GROUP", -1);
+        opt.msm_fused_front = num("CBP_MSM_FUSED_FRONT", 1);
         opt.host_taper_log2 = num("CBP_HOST_TAPER_LOG2", 0);
         opt.msm_acc_streams = num("CBP_MSM_ACC_STREAMS", -1);
         if (const char* g = getenv("CBP_GROUPS")) {
@@ -186,6 +187,7 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_MSM_ACC_STREAMS: o.msm_acc_streams = (int)value; break;
         case BPK_OPT_HOST_TRACE: o.host_trace = value != 0; break;
         case BPK_OPT_VERIFY_GROUP: o.verify_group = (int)value; break;
+        case BPK_OPT_MSM_FUSED_FRONT: o.msm_fused_front = value != 0; break;
         case BPK_OPT_DEBUG_VARIANT: o.debug_variant = (int)value; break;
         case BPK_OPT_HOST_TAPER_LOG2: o.host_taper_log2 = (value >= 10 && value <= 30) ? (int)value : 0; break;
         case BPK_OPT_MSM_GROUPS:  // hex digits, top group first: 0x844 = 8, 4, 4; 0 = automatic

@@ -55,6 +55,7 @@ struct Options {
     int host_trace = 0;       // chunked host path: print the timeline of every call to stderr (measurements)
     int debug_variant = 0;    // A/B switch for kernels under measurement (tools/probe_ops.py)
     int verify_group = -1;    // batch verification: proofs per combined identity (-1 auto: 12 from 256 proofs; 0 / 1: one by one)
+    int msm_fused_front = 1;  // 1: scans and segment build of the MSM front end in one cooperative launch; 0: eleven launches
     int host_register = 0;    // CBP_HOST_REGISTER: 1 = page-lock large pageable caller buffers once and remember them
 };
 Options& options();

@@ -26,6 +26,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "fe8.cuh"
 #include "msm.h"
 #include "common.h"
@@ -409,6 +410,191 @@ __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint2* __restric
     if (lane == leader) base = atomicAdd(&cursors[bin], __popc(peers));
     base = __shfl_sync(peers, base, leader);
     order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
+// ---- 4c. everything between the first digit pass and the accumulation in ONE cooperative launch ----------------
+// scan_tile_sums / scan_tiles / scan_apply (twice: entry offsets, segment offsets), seg_build, seg_hist, seg_bin_scan and
+// seg_scatter are eleven launches of 3-20 us each, and a 2^20-point MSM spent 0.18 ms of its 0.39 ms front end in them
+// and in the gaps between them (a 2^16-point one 0.08 of 0.10 ms).  Here they are the phases of one kernel whose CTAs
+// are all resident (cooperative launch) and meet at four grid barriers:
+//   A  per tile of 4096 buckets: sum of the compactly placed entry counts and of the segment counts
+//   B  (CTA 0) exclusive scan of both rows of tile sums
+//   C  per tile: offsets, cursors and run ends of every bucket, its segment offset, its segment descriptors, the list
+//      of split buckets, and the histogram of (window group, length class) of its segments
+//   D  (CTA 0) exclusive scan of the histogram
+//   E  segments scattered into their bins (warp-aggregated atomics)
+// The run ends — what the placing pass would leave in the cursors — are offsets + counts, so the placing pass
+// (msm_digits_kernel<1>) runs AFTER this kernel and nothing here waits for it.  The separate kernels above remain as
+// the fallback for devices without cooperative launch and as a cross-check (BPK_OPT_MSM_FUSED_FRONT = 0).
+struct FrontTail {
+    const uint32_t* counts;
+    const uint32_t* overflow;
+    uint32_t* tilesA;
+    uint32_t* tilesS;
+    uint32_t* offsets;
+    uint32_t* cursors;
+    uint32_t* ends;
+    uint32_t* segoff;
+    uint2* desc;
+    uint32_t* heavy;
+    uint32_t* heavy_cnt;
+    uint32_t* hist;
+    uint32_t* binstart;
+    uint32_t* order;
+    uint32_t total, B, slotted_ids, cap, ranked_from;
+};
+__device__ __forceinline__ uint32_t seg_bin_of(uint32_t len, uint32_t w, const GroupMap& gm) {
+    const int seg_shift = gm.seg_shift_of_window[w];
+    uint32_t cls = (len * 64u + (1u << seg_shift) - 1u) >> seg_shift;  // 0..64
+    return (uint32_t)gm.group_of_window[w] * kSegBinsPerGroup + (64u - cls);
+}
+// exclusive scan of a[0..n) in place by one CTA (n <= 4 * blockDim.x * ... : looped), total returned
+__device__ __forceinline__ uint32_t cta_scan_inplace(uint32_t* a, uint32_t n, uint32_t* smem) {
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += blockDim.x * 4) {
+        const uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = i0 + j < n ? a[i0 + j] : 0;
+            sum += v[j];
+        }
+        uint32_t bt;
+        uint32_t ex = block_exclusive_scan(sum, smem, bt) + carry;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < n) a[i0 + j] = ex;
+            ex += v[j];
+        }
+        carry += bt;
+        __syncthreads();
+    }
+    return carry;
+}
+static constexpr int kFtPer = 4, kFtTile = kScanThreads * kFtPer;  // buckets per thread / per tile of the fused kernel (16: 61 us at 2^20)
+__global__ void __launch_bounds__(kScanThreads) msm_front_tail_kernel(FrontTail f, GroupMap gm) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t smemA[64], smemS[64];
+    __shared__ uint32_t sh_hist[kSegBins];
+    const uint32_t total = f.total;
+    const uint32_t slotted = (f.slotted_ids && !*f.overflow) ? f.slotted_ids : 0u;
+    const uint32_t ntiles = (total + 1 + kFtTile - 1) / kFtTile;
+    // ---- A
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t base = tile * kFtTile + threadIdx.x * kFtPer;
+        uint32_t sA = 0, sS = 0;
+#pragma unroll
+        for (int j = 0; j < kFtPer; j++) {
+            const uint32_t id = base + j;
+            if (id < total) {
+                const uint32_t c = f.counts[id];
+                sA += id >= slotted ? c : 0u;
+                sS += seg_count(c, gm.seg_shift_of_window[id >> gm.log2B]);
+            }
+        }
+        uint32_t btA, btS;
+        block_exclusive_scan(sA, smemA, btA);
+        block_exclusive_scan(sS, smemS, btS);
+        if (threadIdx.x == 0) {
+            f.tilesA[tile] = btA;
+            f.tilesS[tile] = btS;
+        }
+        __syncthreads();
+    }
+    grid.sync();
+    // ---- B
+    if (blockIdx.x == 0) {
+        cta_scan_inplace(f.tilesA, ntiles, smemA);
+        cta_scan_inplace(f.tilesS, ntiles, smemS);
+    }
+    grid.sync();
+    // ---- C
+    for (int i = threadIdx.x; i < kSegBins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t base = tile * kFtTile + threadIdx.x * kFtPer;
+        uint32_t cnt[kFtPer], sA = 0, sS = 0;
+#pragma unroll
+        for (int j = 0; j < kFtPer; j++) {
+            const uint32_t id = base + j;
+            cnt[j] = id < total ? f.counts[id] : 0u;
+            if (id < total) {
+                sA += id >= slotted ? cnt[j] : 0u;
+                sS += seg_count(cnt[j], gm.seg_shift_of_window[id >> gm.log2B]);
+            }
+        }
+        uint32_t btA, btS;
+        uint32_t exA = block_exclusive_scan(sA, smemA, btA) + f.tilesA[tile] + slotted * f.cap;  // compact runs start behind the slots
+        uint32_t exS = block_exclusive_scan(sS, smemS, btS) + f.tilesS[tile];
+#pragma unroll
+        for (int j = 0; j < kFtPer; j++) {
+            const uint32_t id = base + j;
+            if (id == total) {  // sentinels: end of the compact area, number of segments
+                f.offsets[id] = exA;
+                f.segoff[id] = exS;
+            }
+            if (id >= total) continue;
+            const uint32_t c = cnt[j];
+            uint32_t start;
+            if (id < slotted) {  // placed by the first digit pass: run = [id * cap, id * cap + count)
+                start = id * f.cap;
+                f.cursors[id] = start + c;
+            } else {
+                start = exA;
+                // the placing pass advances the cursors of the buckets it places through atomics (from the start of the run);
+                // buckets from ranked_from on are placed by rank: their cursor is the end already
+                f.cursors[id] = exA + (id >= f.ranked_from ? c : 0u);
+                exA += c;
+            }
+            f.offsets[id] = start;
+            f.ends[id] = start + c;
+            // segments of this bucket
+            const uint32_t w = id >> gm.log2B;
+            const int seg_shift = gm.seg_shift_of_window[w];
+            const uint32_t ns = seg_count(c, seg_shift), seglen = 1u << seg_shift;
+            f.segoff[id] = exS;
+            for (uint32_t q = 0; q < ns; q++) {
+                f.desc[exS + q] = make_uint2(start + (q << seg_shift), id);
+                const uint32_t rest = c - (q << seg_shift);
+                atomicAdd(&sh_hist[seg_bin_of(rest < seglen ? rest : seglen, w, gm)], 1u);
+            }
+            if (ns > 1) {
+                const int g = gm.group_of_window[w];
+                const uint32_t idx = atomicAdd(&f.heavy_cnt[g], 1u);
+                f.heavy[(uint32_t)gm.w_lo[g] * f.B + idx] = id;
+            }
+            exS += ns;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSegBins; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&f.hist[i], sh_hist[i]);
+    grid.sync();
+    // ---- D
+    if (blockIdx.x == 0) {
+        const uint32_t nsegs = cta_scan_inplace(f.hist, kSegBins, smemA);
+        for (int i = threadIdx.x; i < kSegBins; i += blockDim.x) f.binstart[i] = f.hist[i];
+        if (threadIdx.x == 0) f.binstart[kSegBins] = nsegs;
+    }
+    grid.sync();
+    // ---- E
+    const uint32_t nsegs = f.segoff[total];
+    const uint32_t rounded = (nsegs + 31u) & ~31u;  // whole warps take part in the ballots
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        const bool live = i < nsegs;
+        const uint32_t bin = live ? seg_bin(f.desc[i], f.ends, gm) : 0xffffffffu;
+        const uint32_t active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const uint32_t peers = __match_any_sync(active, bin);
+            const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+            uint32_t b0 = 0;
+            if (lane == leader) b0 = atomicAdd(&f.hist[bin], __popc(peers));
+            b0 = __shfl_sync(peers, b0, leader);
+            f.order[b0 + __popc(peers & ((1u << lane) - 1u))] = i;
+        }
+    }
 }
 
 // ---- 5. bucket accumulation ---------------------------------------------------------------------
@@ -1062,7 +1248,8 @@ void msm_make_plan(MsmPlan* p, size_t n, int c) {
     p->off_counts = take((size_t)p->nbuckets * 4);
     p->off_offsets = take(((size_t)p->nbuckets + 1) * 4);
     p->off_cursors = take((size_t)p->nbuckets * 4);
-    p->off_tiles = take(1024 * 4);
+    p->off_tiles = take(2 * 2048 * 4);  // tile sums of the entry scan | of the segment scan
+    p->off_ends = take((size_t)p->nbuckets * 4);
     p->off_segoff = take(((size_t)p->nbuckets + 1) * 4);
     p->off_desc = take(p->max_segs * 8);
     p->off_order = take(p->max_segs * 4);
@@ -1225,6 +1412,23 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
     }
 }
 
+// CTAs of msm_front_tail_kernel that are resident at once on this device (0: no cooperative launch), cached
+static int front_tail_grid(int dev) {
+    static int cached[kMaxDevices];
+    static bool known[kMaxDevices];
+    if (dev < 0 || dev >= kMaxDevices) return 0;
+    if (!known[dev]) {
+        int coop = 0, sms = 0, per_sm = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_front_tail_kernel, kScanThreads, 0) == cudaSuccess)
+            cached[dev] = sms * (per_sm > 2 ? 2 : per_sm);  // two CTAs per SM: barriers get dearer with more
+        (void)cudaGetLastError();
+        known[dev] = true;
+    }
+    return cached[dev];
+}
+
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
             int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index, int flags,
@@ -1236,6 +1440,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     uint32_t* offsets = (uint32_t*)(fw + p.off_offsets);
     uint32_t* cursors = (uint32_t*)(fw + p.off_cursors);
     uint32_t* tiles = (uint32_t*)(fw + p.off_tiles);
+    uint32_t* ends_buf = (uint32_t*)(fw + p.off_ends);
     uint32_t* segoff = (uint32_t*)(fw + p.off_segoff);
     uint2* desc = (uint2*)(fw + p.off_desc);
     uint32_t* order = (uint32_t*)(fw + p.off_order);
@@ -1321,9 +1526,12 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if ((e = cudaMemsetAsync(counts, 0, (size_t)p.nbuckets * 4, st)) != cudaSuccess) return (int)e;
         if ((e = cudaMemsetAsync(bins, 0, (2 * kSegBins + 2 + kMaxGroups) * 4, st)) != cudaSuccess) return (int)e;
     }
-    if (do_back) {
+    auto build_table = [&]() -> int {
         // the affine table depends only on the points: build it on a side stream while the scalar-only
-        // front end (recoding, histogram, sort) runs on the main stream
+        // front end (recoding, histogram, sort) runs on the main stream.  Measured at 2^20 / 2^22 (tools/probe_table_order.py,
+        // ms per MSM): forked before the first digit pass 1.818 / 6.123, in line before it 1.822 / 6.128 (the two kernels
+        // gain nothing from running together: one is bound by load/store issue, the other streams 224 B per point),
+        // forked behind the first digit pass, under the scans and the placing pass, 1.807 / 6.084 — the default.
         cudaStream_t ps = st;
         if (kit) {
             ps = kit->aux;
@@ -1340,8 +1548,15 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         prof_end(BPK_PROF_MSM_PRECOMPUTE, ps);
         CBP_LAUNCH_CHECK(); nl++;
         if (kit && (e = cudaEventRecord(kit->ev_ready, ps)) != cudaSuccess) return (int)e;
-    }
-    const uint32_t* ends = cursors;  // after the placing pass: end of every bucket's run
+        return 0;
+    };
+    const bool table_late = do_front && do_back;
+    if (do_back && !table_late)
+        if (int rc = build_table()) return rc;
+    // fused front end (one cooperative launch, section 4c): run ends in their own array; otherwise the cursors after
+    // the placing pass are the run ends
+    const bool fused = front_tail_grid(dlock.dev) > 0 && options().msm_fused_front != 0;
+    const uint32_t* ends = fused ? ends_buf : cursors;
     if (do_front) {
     prof_begin(BPK_PROF_MSM_FRONT, st);
     unsigned dgrid = (unsigned)((n + 255) / 256);
@@ -1350,7 +1565,30 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     msm_digits_kernel<0><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, counts,
                                                 entries, overflow, offsets, toprank);
     CBP_LAUNCH_CHECK(); nl++;
+    if (table_late)
+        if (int rc = build_table()) return rc;
     uint32_t ntiles = (p.nbuckets + 1 + kScanTile - 1) / kScanTile;  // +1: the sentinel slot
+    if (fused) {
+        const uint32_t ftiles = (p.nbuckets + 1 + kFtTile - 1) / kFtTile;
+        FrontTail ft;
+        ft.counts = counts; ft.overflow = overflow; ft.tilesA = tiles; ft.tilesS = tiles + 2048; ft.offsets = offsets;
+        ft.cursors = cursors; ft.ends = ends_buf; ft.segoff = segoff; ft.desc = desc; ft.heavy = heavy; ft.heavy_cnt = heavy_cnt;
+        ft.hist = bins; ft.binstart = binstart; ft.order = order;
+        ft.total = p.nbuckets; ft.B = p.B; ft.slotted_ids = slotted_ids; ft.cap = p.cap;
+        ft.ranked_from = p.cap ? slotted_ids : 0xffffffffu;
+        // enough CTAs for the tiles and for ~4 segments per thread in the last phase, all of them resident
+        unsigned want = ftiles > (unsigned)((p.max_segs + 1023) / 1024) ? ftiles : (unsigned)((p.max_segs + 1023) / 1024);
+        unsigned grid = (unsigned)front_tail_grid(dlock.dev);
+        if (want < grid) grid = want ? want : 1;
+        void* args[] = {&ft, &gm};
+        if ((e = cudaLaunchCooperativeKernel((const void*)msm_front_tail_kernel, dim3(grid), dim3(kScanThreads), args, 0, st)) !=
+            cudaSuccess)
+            return (int)e;
+        nl++;
+        msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
+                                                    entries, overflow, offsets, toprank);
+        CBP_LAUNCH_CHECK(); nl++;
+    } else {
     scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, overflow, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
@@ -1380,6 +1618,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     CBP_LAUNCH_CHECK(); nl++;
     seg_scatter_kernel<<<sgrid, 256, 0, st>>>(desc, ends, nsegs_p, gm, bins, order);
     CBP_LAUNCH_CHECK(); nl++;
+    }
 
     prof_end(BPK_PROF_MSM_FRONT, st);
     }  // do_front

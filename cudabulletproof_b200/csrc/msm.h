@@ -16,6 +16,7 @@ struct MsmPlan {
     int w_exact;        // windows below this one are slotted, the others placed exactly by the second pass
     int seg_shift;      // log2 of the accumulation segment length
     size_t max_segs;    // upper bound on accumulation segments (buckets + entries / segment length)
+    size_t off_ends;    // run ends of the buckets (fused front end)
     size_t off_table, off_counts, off_offsets, off_cursors, off_tiles, off_segoff, off_desc, off_order, off_bins, off_heavy,
         off_entries, off_toprank, off_buckets, off_segsums;
     size_t off_redX[2], off_redY[2], off_winX, off_winY, off_state;
