@@ -401,8 +401,12 @@ def run_cuda(args):
                                                        "duration_us_per_launch") if k in ncu_acc} if ncu_acc else None),
                     "algorithmic_gather_bytes": n * W * 100.0,
                     "launch_ms": acc_ms, "launches_timed": acc_n,
-                    "launch_note": "span of the window-group accumulation launches per MSM (CUDA events on the launching stream)",
+                    "launch_note": "span of the window-group accumulation launches per MSM: every group accumulates on its own "
+                                   "stream, so the span runs from the first launch to the end of the last one (CUDA events on the "
+                                   "launching stream, which waits for every group); the groups' bucket reductions share the span",
                     "algorithmic_imad_per_launch": imad_acc,
+                    # the W * 2^c additions (9M = 648) of the bucket reductions that run inside the same span
+                    "frac_with_reductions": (imad_acc + W * (1 << msm.window_bits) * 648.0) / (acc_ms * 1e-3) / 1e12 / INT_PEAK_TIMAD,
                     "whole_call_frac": imad_acc / (ms / args.steps * 1e-3) / 1e12 / INT_PEAK_TIMAD}
         roofline_hbm = {"bound": "hbm", "kernel": "msm_precompute_kernel", "achieved": n * 224.0 / (pre_ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "frac": n * 224.0 / (pre_ms * 1e-3) / 1e9 / hbm_peak,

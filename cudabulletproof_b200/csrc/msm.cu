@@ -1412,6 +1412,15 @@ static void make_groups(GroupMap* gm, int W, int c, int seg_shift, bool pipeline
     }
 }
 
+// Cooperative kernels whose CTAs wait for each other at grid barriers must never hold SM slots that another such grid
+// is waiting for: every launch of msm_front_tail_kernel on a device is ordered behind the previous one by an event
+// (the enqueue is serialised by the device lock), so at most one of them runs at a time, whatever the streams are.
+static cudaEvent_t front_tail_fence(int dev) {
+    static cudaEvent_t ev[kMaxDevices];
+    if (dev < 0 || dev >= kMaxDevices) return nullptr;
+    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) ev[dev] = nullptr;
+    return ev[dev];
+}
 // CTAs of msm_front_tail_kernel that are resident at once on this device (0: no cooperative launch), cached
 static int front_tail_grid(int dev) {
     static int cached[kMaxDevices];
@@ -1581,9 +1590,13 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         unsigned grid = (unsigned)front_tail_grid(dlock.dev);
         if (want < grid) grid = want ? want : 1;
         void* args[] = {&ft, &gm};
+        cudaEvent_t fence = front_tail_fence(dlock.dev);
+        if (!fence) return (int)cudaErrorInitializationError;
+        if ((e = cudaStreamWaitEvent(st, fence, 0)) != cudaSuccess) return (int)e;  // no-op before the first record
         if ((e = cudaLaunchCooperativeKernel((const void*)msm_front_tail_kernel, dim3(grid), dim3(kScanThreads), args, 0, st)) !=
             cudaSuccess)
             return (int)e;
+        if ((e = cudaEventRecord(fence, st)) != cudaSuccess) return (int)e;
         nl++;
         msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
                                                     entries, overflow, offsets, toprank);

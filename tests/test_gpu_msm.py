@@ -298,6 +298,37 @@ def test_msm_slotted_front_end_small(oracle, slot_option, slots, window_bits):
         assert np.array_equal(got, oracle_msm(oracle, sc, pts)), name
 
 
+@pytest.mark.parametrize("slots", [0, 1])
+def test_msm_fused_front_end_matches_separate_kernels(slot_option, slots):
+    """The scans / segment build / histogram / scatter of the front end run as one cooperative launch
+    (msm_front_tail_kernel) or as the eleven separate kernels it replaced (BPK_OPT_MSM_FUSED_FRONT = 0): same bytes, for
+    random scalars, for repeated scalars (split buckets; with slots forced on, the overflow fallback) and for a size
+    whose bucket count is not a multiple of the tile."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    slot_option(slots)
+    n = (1 << 16) + 123
+    pts, _ = cbp.synth_points(n, seed=0xF05ED)
+    sc = cbp.synth_scalars(n, seed=0xF05EE, bits=253)
+    adv = sc.clone()
+    adv[: n // 3] = adv[1]
+    out = {}
+    try:
+        for fused in (1, 0):
+            cbp.check(lib.bpk_debug_set_option(14, fused), "set_option")  # BPK_OPT_MSM_FUSED_FRONT
+            for wb in (0, 11):
+                msm = cbp.Msm(n, window_bits=wb)
+                out[(fused, wb)] = (msm(sc, pts).cpu().numpy().copy(), msm(adv, pts).cpu().numpy().copy())
+                torch.cuda.synchronize()
+    finally:
+        lib.bpk_debug_set_option(14, 1)
+    for wb in (0, 11):
+        assert np.array_equal(out[(1, wb)][0], out[(0, wb)][0])
+        assert np.array_equal(out[(1, wb)][1], out[(0, wb)][1])
+    assert np.array_equal(out[(1, 0)][0], out[(1, 11)][0])
+
+
 def test_msm_slotted_equals_two_pass_at_size(oracle, slot_option):
     """2^18 points, both forced: the slotted and the two-pass front end give identical bytes, for
     252-bit random scalars and for an adversarial input that overflows the slots."""
