@@ -18,6 +18,7 @@ CUDA-event timed inside the timed region), cpu_baseline (the unmodified referenc
 box's host cores), clocks, gpu_launches.
 """
 import argparse
+import glob
 import ctypes as C
 import json
 import os
@@ -308,6 +309,42 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs next to its GPU (NVML's affinity mask) BEFORE any pinned host buffer is allocated:
+    with the default first-touch policy the buffers then live in that GPU's NUMA node, so N ranks uploading at once draw
+    on every node's memory bandwidth instead of the one the launcher happened to start them on.  Returns what was done."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        nodes = {}
+        for path in glob.glob("/sys/devices/system/node/node*/cpulist"):
+            node = int(path.split("node")[-1].split("/")[0])
+            got = set()
+            for part in open(path).read().strip().split(","):
+                if part:
+                    lo, _, hi = part.partition("-")
+                    got |= set(range(int(lo), int(hi or lo) + 1))
+            nodes[node] = got
+        info.update({"gpu_pci": bus, "gpu_cpus": len(cpus), "numa_nodes": len(nodes),
+                     "gpu_nodes": sorted(n for n, c in nodes.items() if c & cpus)})
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as exc:  # noqa: BLE001 - best effort: no NVML, no permission, one node
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 def run_cuda(args):
     import numpy as np
     import torch
@@ -321,6 +358,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa_bind) else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -786,7 +824,8 @@ def run_cuda(args):
                                "window_bits": msm_res["window_bits"], "points_per_gpu": n,
                                "l2": "inputs (160 B/pair = 168 MB at 2^20) larger than the 126 MB L2; no explicit flush",
                                "parallelism": f"point-range x{world}" if world > 1 else "single GPU",
-                               "combine": "NCCL all_gather of 128 B partial points + point-sum kernel" if world > 1 else None},
+                               "combine": "NCCL all_gather of 128 B partial points + point-sum kernel" if world > 1 else None,
+                               "host_numa": numa if world > 1 else None},
                     "e2e": msm_res["e2e"], "gpu_launches": msm_res["launches"], "clocks": msm_res["clocks"],
                     "roofline": msm_res["roofline"], "roofline_hbm": msm_res["roofline_hbm"], "phases": msm_res["phases"],
                     "cpu_baseline": cpu,
@@ -830,6 +869,7 @@ def main():
     ap.add_argument("--verify-group", type=int, default=-1,
                     help="proofs per combined identity in batch verification (-1: library default, 0: one by one)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: leave the ranks where the launcher put them")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling rows (secondary_scaling)")
     ap.add_argument("--strong-log-n", type=int, nargs="*", default=[20, 22],
                     help="global sizes of the strong-scaling MSMs (one MSM cut into N point-range shards)")
