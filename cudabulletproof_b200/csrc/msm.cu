@@ -1537,8 +1537,8 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     }
     auto build_table = [&]() -> int {
         // the affine table depends only on the points: build it on a side stream while the scalar-only
-        // front end (recoding, histogram, sort) runs on the main stream.  Measured at 2^20 / 2^22 (tools/probe_table_order.py,
-        // ms per MSM): forked before the first digit pass 1.818 / 6.123, in line before it 1.822 / 6.128 (the two kernels
+        // front end (recoding, histogram, sort) runs on the main stream.  Measured at 2^20 / 2^22 with a temporary switch (ms per MSM,
+        // profiles/r02_summary.md): forked before the first digit pass 1.818 / 6.123, in line before it 1.822 / 6.128 (the two kernels
         // gain nothing from running together: one is bound by load/store issue, the other streams 224 B per point),
         // forked behind the first digit pass, under the scans and the placing pass, 1.807 / 6.084 — the default.
         cudaStream_t ps = st;
