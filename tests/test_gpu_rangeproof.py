@@ -117,8 +117,8 @@ def test_batch_verify_matches_oracle_honest_and_tampered(oracle, gens16, gens64,
         assert oracle_verify(oracle, g, proof, V) == got[idx]
 
 
-@pytest.mark.parametrize("group", [2, 3, 8, 64])
-def test_grouped_verification_same_decisions_as_one_by_one(oracle, gens16, group):
+@pytest.mark.parametrize("group,window_bits", [(2, 16), (3, 8), (8, 16), (12, 8), (64, 16)])
+def test_grouped_verification_same_decisions_as_one_by_one(oracle, gens16, group, window_bits):
     """Grouped verification (one combined identity per `group` proofs, hash-derived weights, members of failed groups
     verified again one by one; BPK_OPT_VERIFY_GROUP) on a batch that mixes honest proofs, one bit flipped in every field
     of the record, and runs of consecutive honest proofs long enough to fill whole groups: decisions equal the oracle's
@@ -127,7 +127,7 @@ def test_grouped_verification_same_decisions_as_one_by_one(oracle, gens16, group
     import cudabulletproof_b200 as cbp
     lib = cbp.load()
     n, g = 16, gens16
-    dg = dev_gens(g, 16)
+    dg = dev_gens(g, window_bits)
     k = n.bit_length() - 1
     rng = random.Random(1000 + group)
     honest = []
