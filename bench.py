@@ -54,10 +54,10 @@ def measure_int_peak(lib, target_ms=20.0):
     """The integer roofline denominator, measured in THIS run on this GPU (csrc/intpeak.cu): lane operations per
     second of IMAD.WIDE.U32 carry chains (fe_mul's inner pattern), next to the other multiply flavours so that
     the record shows why IMAD.WIDE is the right denominator here."""
-    rates = (C.c_double * 5)()
-    names = ["imad_wide_carry", "imad_wide_indep", "imad_lo", "imad_hi", "dfma_fp64"]
+    names = ["imad_wide_carry", "imad_wide_indep", "imad_lo", "imad_hi", "dfma_fp64", "imad_wide_carry_beside_equal_dfma"]
+    rates = (C.c_double * len(names))()
     try:
-        rc = lib.bpk_measure_int_peak(target_ms, rates, 5)
+        rc = lib.bpk_measure_int_peak(target_ms, rates, len(names))
     except Exception:  # noqa: BLE001
         rc = -1
     if rc != 0 or not rates[0] > 0:

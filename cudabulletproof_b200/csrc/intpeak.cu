@@ -9,6 +9,8 @@
 //   [2] IMAD (32-bit low product), independent accumulators
 //   [3] IMAD.HI.U32, independent accumulators
 //   [4] DFMA (FP64), independent accumulators — a 5x51-bit floating-point limb product would issue here
+//   [5] the carry rows of [0] with as many DFMA beside them in the same thread: the IMAD.WIDE rate that is left when
+//       the FP64 pipe is kept busy too — equal to [0] if the two pipes issue side by side, half of it if they do not
 // Rates are lane operations per second (one warp instruction = 32).
 #include "common.h"
 #include "fe25519.cuh"
@@ -100,6 +102,37 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(uint32_t* out, uint32_t 
     out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)__double2ll_rn(s);
 }
 
+__global__ void __launch_bounds__(256) peak_imad_wide_beside_dfma_kernel(uint32_t* out, uint32_t a, uint32_t b, int outer) {
+    uint32_t c[9], d[9];
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        c[i] = threadIdx.x + i;
+        d[i] = threadIdx.x * 3 + i;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = (double)(threadIdx.x + i);
+    uint32_t x0 = a + threadIdx.x, x1 = a ^ 0x55, x2 = a + 7, x3 = a * 3, y = b;
+    const double fx = 1.0 + 1e-9 * (double)(a + threadIdx.x), fy = 1e-7 * (double)b;
+    for (int o = 0; o < outer; o++)
+        for (int it = 0; it < kPeakInner; it++) {
+            mad_row4(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], x0, x1, x2, x3, y);
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[i] = fma(acc[i], fx, fy);
+            mad_row4(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], x1, x2, x3, x0, y);
+#pragma unroll
+            for (int i = 4; i < 8; i++) acc[i] = fma(acc[i], fx, fy);
+            y = c[0] ^ d[1];
+        }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) s ^= c[i] ^ d[i];
+    double fs = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) fs += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s ^ (uint32_t)__double2ll_rn(fs);
+}
+
 }  // namespace cbp
 
 using namespace cbp;
@@ -118,9 +151,9 @@ extern "C" int bpk_measure_int_peak(double target_ms, double* rates, int count) 
     if (e == cudaSuccess) e = cudaEventCreate(&e0);
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
     using Kern = void (*)(uint32_t*, uint32_t, uint32_t, int);
-    const Kern kern[5] = {peak_imad_wide_carry_kernel, peak_imad_wide_kernel, peak_imad_lo_kernel, peak_imad_hi_kernel,
-                          peak_dfma_kernel};
-    for (int k = 0; k < 5 && k < count && e == cudaSuccess; k++) {
+    const Kern kern[BPK_PEAK_KINDS] = {peak_imad_wide_carry_kernel, peak_imad_wide_kernel, peak_imad_lo_kernel,
+                                       peak_imad_hi_kernel, peak_dfma_kernel, peak_imad_wide_beside_dfma_kernel};
+    for (int k = 0; k < BPK_PEAK_KINDS && k < count && e == cudaSuccess; k++) {
         int outer = 1;
         float ms = 0;
         for (int attempt = 0; attempt < 12 && e == cudaSuccess; attempt++) {  // grow the launch until it lasts target_ms

@@ -82,7 +82,8 @@ int bpk_profile_read(int kind, float* mean_ms, int* samples); /* synchronises th
 #define BPK_PEAK_IMAD_LO 2
 #define BPK_PEAK_IMAD_HI 3
 #define BPK_PEAK_DFMA 4
-#define BPK_PEAK_KINDS 5
+#define BPK_PEAK_IMAD_WIDE_BESIDE_DFMA 5 /* rate [0] while the same number of DFMA issue from the same threads */
+#define BPK_PEAK_KINDS 6
 int bpk_measure_int_peak(double target_ms, double* rates, int count);
 
 /* ---- multi-scalar multiplication: replaces cuda_point_vector_multi_scalar_mul (cuda_bulletproof.h:13) ---- */
