@@ -27,7 +27,7 @@ def check_common(d):
 
 
 def test_own_arm_artefact_has_every_contract_key():
-    d = last_json_line(os.path.join(ROOT, "profiles", "r01_bench_1gpu.json"))
+    d = last_json_line(os.path.join(ROOT, "profiles", "r02_bench_1gpu.json"))
     check_common(d)
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["value"] > 0
     assert d["gpu_launches"] > 0
@@ -44,13 +44,24 @@ def test_own_arm_artefact_has_every_contract_key():
     for key in ("value", "unit", "cores", "kind", "sample"):
         assert key in c, key
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1
+    assert "measured" in r["peak_source"] or "bpk_measure_int_peak" in r["peak_source"]  # the peak comes from the same run
+    assert r["traffic"] and r["ncu"]["source_hash"]  # parsed from a committed ncu summary of the same kernel sources
+    assert 0.95 * r["peak"] < r["peak_all_T_per_s"]["imad_wide_carry"] < 1.05 * r["peak"]
     s = d["secondary"]
     assert s["metric"] == "range_proof_verifies_per_sec" and s["decisions_correct"] is True
     assert 0 < s["roofline"]["frac"] < 1
+    assert s["one_by_one"]["same_decisions"] is True and s["algorithm"]["grouped"] >= 2
+    # pageable and affine rows of the end-to-end call, every result equal to the device-resident one
+    assert d["e2e"]["result_matches_device_path"] is True
+    for row in list(d["e2e"]["pageable"].values()) + [d["e2e"]["affine_extension"]]:
+        assert row["result_matches_device_path"] is True and row["value"] > 0
+    # strong scaling: ONE global MSM per row, checked against the scalar identity
+    for row in d["secondary_scaling"]["rows"]:
+        assert row["result_check"] is True and len(row["result_xy"]) == 128
 
 
 def test_reference_arm_artefact():
-    d = last_json_line(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json"))
+    d = last_json_line(os.path.join(ROOT, "profiles", "r02_bench_reference_arm.json"))
     check_common(d)
     assert d["impl"] == "reference"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
@@ -59,12 +70,17 @@ def test_reference_arm_artefact():
 
 
 def test_scaling_artefacts_are_weak_scaling_lines():
-    one = last_json_line(os.path.join(ROOT, "profiles", "r01_bench_1gpu.json"))["value"]
+    single = last_json_line(os.path.join(ROOT, "profiles", "r02_bench_1gpu.json"))
+    one = single["value"]
+    xy = {r["log2_n"]: r["result_xy"] for r in single["secondary_scaling"]["rows"]}
     for n in (2, 4, 8):
-        d = last_json_line(os.path.join(ROOT, "profiles", f"r01_bench_{n}gpu_stdout.txt"))
+        d = last_json_line(os.path.join(ROOT, "profiles", f"r02_bench_{n}gpu.json"))
         check_common(d)
         assert d["n_gpus"] == n
         assert 0.85 * n * one < d["value"] < 1.1 * n * one  # whole-job aggregate, near-linear
+        for r in d["secondary_scaling"]["rows"]:  # the same global MSM on every N: identical bytes, checked result
+            assert r["result_check"] is True and r["result_xy"] == xy[r["log2_n"]]
+            assert r["n_gpus"] == n
 
 
 def test_bench_py_accepts_the_driver_flags():
