@@ -1422,10 +1422,15 @@ static cudaEvent_t front_tail_fence(int dev) {
     return ev[dev];
 }
 // CTAs of msm_front_tail_kernel that are resident at once on this device (0: no cooperative launch), cached
-static int front_tail_grid(int dev) {
+static int front_tail_grid(int dev, bool disable = false) {
     static int cached[kMaxDevices];
     static bool known[kMaxDevices];
     if (dev < 0 || dev >= kMaxDevices) return 0;
+    if (disable) {  // a cooperative launch was refused at run time: separate kernels from now on
+        cached[dev] = 0;
+        known[dev] = true;
+        return 0;
+    }
     if (!known[dev]) {
         int coop = 0, sms = 0, per_sm = 0;
         if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
@@ -1562,10 +1567,10 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     const bool table_late = do_front && do_back;
     if (do_back && !table_late)
         if (int rc = build_table()) return rc;
-    // fused front end (one cooperative launch, section 4c): run ends in their own array; otherwise the cursors after
-    // the placing pass are the run ends
-    const bool fused = front_tail_grid(dlock.dev) > 0 && options().msm_fused_front != 0;
-    const uint32_t* ends = fused ? ends_buf : cursors;
+    // the cursors after the placing pass are the run ends — with either front end; the fused one (one cooperative launch,
+    // section 4c) runs BEFORE the placing pass and keeps its own copy of the ends for its last phase
+    bool fused = front_tail_grid(dlock.dev) > 0 && options().msm_fused_front != 0;
+    const uint32_t* ends = cursors;
     if (do_front) {
     prof_begin(BPK_PROF_MSM_FRONT, st);
     unsigned dgrid = (unsigned)((n + 255) / 256);
@@ -1594,14 +1599,21 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (!fence) return (int)cudaErrorInitializationError;
         if ((e = cudaStreamWaitEvent(st, fence, 0)) != cudaSuccess) return (int)e;  // no-op before the first record
         if ((e = cudaLaunchCooperativeKernel((const void*)msm_front_tail_kernel, dim3(grid), dim3(kScanThreads), args, 0, st)) !=
-            cudaSuccess)
-            return (int)e;
-        if ((e = cudaEventRecord(fence, st)) != cudaSuccess) return (int)e;
-        nl++;
-        msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
-                                                    entries, overflow, offsets, toprank);
-        CBP_LAUNCH_CHECK(); nl++;
-    } else {
+            cudaSuccess) {
+            // refused (a partitioned or shared device may not grant the residency the occupancy query promised): nothing has
+            // been enqueued, so the separate kernels take over — for this call and every later one on this device
+            (void)cudaGetLastError();
+            front_tail_grid(dlock.dev, true);
+            fused = false;
+        } else {
+            if ((e = cudaEventRecord(fence, st)) != cudaSuccess) return (int)e;
+            nl++;
+            msm_digits_kernel<1><<<dgrid, 256, 0, st>>>((const uint8_t*)d_scalars, n, p.c, p.W, p.B, p.cap, p.w_exact, cursors,
+                                                        entries, overflow, offsets, toprank);
+            CBP_LAUNCH_CHECK(); nl++;
+        }
+    }
+    if (!fused) {
     scan_tile_sums_kernel<false><<<ntiles, kScanThreads, 0, st>>>(counts, p.nbuckets, gm, slotted_ids, overflow, tiles);
     CBP_LAUNCH_CHECK(); nl++;
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, ntiles);
