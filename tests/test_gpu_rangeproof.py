@@ -161,6 +161,35 @@ def test_grouped_verification_same_decisions_as_one_by_one(oracle, gens16, group
     assert grouped == expect
 
 
+def test_grouped_verification_across_the_pass_boundary(gens16):
+    """More proofs than one pass of the batch verifier takes (2^14): the second pass starts a fresh set of groups; a ragged
+    last group, tampered proofs on both sides of the boundary and in the last group.  Decisions equal the one-by-one path."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    dg = dev_gens(gens16, 8)
+    m = (1 << 14) + 101
+    rng = random.Random(77)
+    vals = [rng.getrandbits(16) for _ in range(m)]
+    seeds = list(range(5000, 5000 + m))
+    gam = ob.ints_to_fe([gamma_for(s) for s in seeds])
+    proofs = cbp.range_prove_batch(dg, vals, gam, seeds)
+    bad = sorted({3, 16383, 16384, 16390, m - 1, *rng.sample(range(m), 40)})
+    h = proofs.cpu().numpy()
+    for i in bad:
+        h[i, rng.randrange(h.shape[1])] ^= 1 << rng.randrange(8)
+    d = torch.from_numpy(h).cuda()
+    ver = cbp.RangeVerifier(dg, m)
+    try:
+        grouped = ver(d).cpu().numpy().astype(bool)
+        cbp.check(lib.bpk_debug_set_option(13, 0), "set_option")  # BPK_OPT_VERIFY_GROUP: one by one
+        plain = ver(d).cpu().numpy().astype(bool)
+    finally:
+        lib.bpk_debug_set_option(13, -1)
+    assert [i for i in range(m) if not plain[i]] == bad
+    assert np.array_equal(grouped, plain)
+
+
 def record_to_struct(rec, n):
     """flat record -> ctypes RangeProof (oracle layout) + V, keeping the backing arrays alive"""
     k = n.bit_length() - 1
