@@ -16,6 +16,7 @@
 
 namespace cbp {
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_options_epoch{0};
 std::atomic<int> g_last_error{0};
 std::atomic<int> g_last_cuda_error{0};
 
@@ -47,6 +48,7 @@ Options& options() {
         opt.msm_small_max = num("CBP_MSM_SMALL_MAX", -1);
         opt.host_register = num("CBP_HOST_REGISTER", 0);
         opt.verify_group = num("CBP_VERIFY_GROUP", -1);
+        opt.msm_graph = num("CBP_MSM_GRAPH", 1);
         opt.msm_fused_front = num("CBP_MSM_FUSED_FRONT", 1);
         opt.host_taper_log2 = num("CBP_HOST_TAPER_LOG2", 0);
         opt.msm_acc_streams = num("CBP_MSM_ACC_STREAMS", -1);
@@ -175,6 +177,7 @@ int bpk_clear_last_error(void) {
 uint64_t bpk_kernel_launches(void) { return g_launches.load(); }
 int bpk_debug_set_option(int option, long long value) {
     Options& o = options();
+    g_options_epoch.fetch_add(1);
     switch (option) {
         case BPK_OPT_MSM_SLOTS: o.msm_slots = (int)value; break;
         case BPK_OPT_MSM_NO2D: o.msm_no2d = value != 0; break;
@@ -187,6 +190,7 @@ int bpk_debug_set_option(int option, long long value) {
         case BPK_OPT_MSM_ACC_STREAMS: o.msm_acc_streams = (int)value; break;
         case BPK_OPT_HOST_TRACE: o.host_trace = value != 0; break;
         case BPK_OPT_VERIFY_GROUP: o.verify_group = (int)value; break;
+        case BPK_OPT_MSM_GRAPH: o.msm_graph = value != 0; break;
         case BPK_OPT_MSM_FUSED_FRONT: o.msm_fused_front = value != 0; break;
         case BPK_OPT_DEBUG_VARIANT: o.debug_variant = (int)value; break;
         case BPK_OPT_HOST_TAPER_LOG2: o.host_taper_log2 = (value >= 10 && value <= 30) ? (int)value : 0; break;
@@ -228,7 +232,7 @@ int bpk_msm_device(const void* d_scalars, const void* d_points, size_t n, void* 
     msm_make_plan(&p, n, window_bits);
     if (n && workspace_bytes < p.workspace_bytes) return fail(BPK_ERR_WORKSPACE);
     int launches = 0;
-    int rc = msm_run(p, d_scalars, d_points, d_result, d_workspace, normalize, (cudaStream_t)stream, &launches, nullptr);
+    int rc = msm_run_cached(p, d_scalars, d_points, d_result, d_workspace, normalize, (cudaStream_t)stream, &launches);
     count_launches(launches);
     return fail_cuda(rc);
 }

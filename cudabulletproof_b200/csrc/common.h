@@ -56,11 +56,14 @@ struct Options {
     int debug_variant = 0;    // A/B switch for kernels under measurement (tools/probe_ops.py)
     int verify_group = -1;    // batch verification: proofs per combined identity (-1 auto: 12 from 256 proofs; 0 / 1: one by one)
     int msm_fused_front = 1;  // 1: scans and segment build of the MSM front end in one cooperative launch; 0: eleven launches
+    int msm_graph = 1;        // 1: mid-size device MSMs replay a cached CUDA graph of their launch DAG (see msm_run_cached)
     int host_register = 0;    // CBP_HOST_REGISTER: 1 = page-lock large pageable caller buffers once and remember them
 };
 Options& options();
 
 // optional per-kernel timing: no-ops unless bpk_profile_enable(1)
+bool prof_enabled();
+extern std::atomic<uint64_t> g_options_epoch;  // bumped by every bpk_debug_set_option: cached launch graphs are stale then
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);
 }  // namespace cbp

@@ -26,6 +26,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 #include <cooperative_groups.h>
 #include "fe8.cuh"
 #include "msm.h"
@@ -1443,6 +1444,10 @@ static int front_tail_grid(int dev, bool disable = false) {
     return cached[dev];
 }
 
+// set while msm_run_cached records a launch graph on this thread: the cooperative front kernel (whose per-device fence
+// is an event recorded outside the capture) gives way to the separate kernels — inside a graph their launch gaps are gone anyway
+static thread_local bool tl_capturing = false;
+
 // d_scalars: n x 32 B, d_points: n x 128 B (reference AoS ge25519), d_result: 128 B
 int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws,
             int normalize, cudaStream_t st, int* launches, cudaEvent_t points_ready, int kit_index, int flags,
@@ -1569,7 +1574,7 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
         if (int rc = build_table()) return rc;
     // the cursors after the placing pass are the run ends — with either front end; the fused one (one cooperative launch,
     // section 4c) runs BEFORE the placing pass and keeps its own copy of the ends for its last phase
-    bool fused = front_tail_grid(dlock.dev) > 0 && options().msm_fused_front != 0;
+    bool fused = front_tail_grid(dlock.dev) > 0 && options().msm_fused_front != 0 && !tl_capturing;
     const uint32_t* ends = cursors;
     if (do_front) {
     prof_begin(BPK_PROF_MSM_FRONT, st);
@@ -1791,6 +1796,80 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
     prof_end(BPK_PROF_MSM_TOTAL, st);
     if (launches) *launches = nl;
     return 0;
+}
+
+// ---- cached launch graphs for the latency-bound sizes ----------------------------------------------------------------
+namespace {
+struct GraphEntry {
+    const void *s, *p, *r, *ws;
+    size_t n;
+    int c, normalize, launches;
+    uint64_t epoch, last_use;
+    cudaGraphExec_t exec;
+};
+struct GraphCache {
+    std::vector<GraphEntry> entries;
+    cudaStream_t cap = nullptr;
+    uint64_t tick = 0;
+    bool broken = false;  // a capture failed on this device: plain launches from then on
+};
+GraphCache g_graph_cache[kMaxDevices];
+constexpr size_t kGraphCacheMax = 8;
+}  // namespace
+
+int msm_run_cached(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_ws, int normalize,
+                   cudaStream_t st, int* launches) {
+    const bool eligible = options().msm_graph != 0 && !prof_enabled() && !p.small && p.n > ((size_t)1 << 13) &&
+                          p.n < ((size_t)1 << 19);
+    if (!eligible) return msm_run(p, d_scalars, d_points, d_result, d_ws, normalize, st, launches, nullptr);
+    DeviceLock dlock;  // the cache, and (below) the side streams a capture records on, belong to the device
+    if (!dlock.ok()) return (int)cudaErrorInvalidDevice;
+    GraphCache& gc = g_graph_cache[dlock.dev];
+    if (gc.broken) return msm_run(p, d_scalars, d_points, d_result, d_ws, normalize, st, launches, nullptr);
+    const uint64_t epoch = g_options_epoch.load();
+    GraphEntry* hit = nullptr;
+    for (GraphEntry& e : gc.entries)
+        if (e.s == d_scalars && e.p == d_points && e.r == d_result && e.ws == d_ws && e.n == p.n && e.c == p.c &&
+            e.normalize == normalize && e.epoch == epoch)
+            hit = &e;
+    if (!hit) {
+        // everything a capture must not do itself: streams, events, occupancy queries
+        if (!gc.cap && cudaStreamCreateWithFlags(&gc.cap, cudaStreamNonBlocking) != cudaSuccess) gc.broken = true;
+        if (!stream_kit(dlock.dev, 0)) gc.broken = true;
+        (void)front_tail_grid(dlock.dev);
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        int nl = 0, rc = 0;
+        if (!gc.broken && cudaStreamBeginCapture(gc.cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            tl_capturing = true;
+            rc = msm_run(p, d_scalars, d_points, d_result, d_ws, normalize, gc.cap, &nl, nullptr);
+            tl_capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(gc.cap, &graph);
+            if (rc == 0 && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (rc != 0 || ce != cudaSuccess || !exec) gc.broken = true;
+            if (graph) cudaGraphDestroy(graph);
+        } else {
+            gc.broken = true;
+        }
+        if (gc.broken) {
+            (void)cudaGetLastError();
+            if (exec) cudaGraphExecDestroy(exec);
+            return msm_run(p, d_scalars, d_points, d_result, d_ws, normalize, st, launches, nullptr);
+        }
+        if (gc.entries.size() >= kGraphCacheMax) {  // evict the least recently used (and any entry of an older options epoch)
+            size_t victim = 0;
+            for (size_t i = 1; i < gc.entries.size(); i++)
+                if (gc.entries[i].epoch != epoch || gc.entries[i].last_use < gc.entries[victim].last_use) victim = i;
+            cudaGraphExecDestroy(gc.entries[victim].exec);
+            gc.entries.erase(gc.entries.begin() + (long)victim);
+        }
+        gc.entries.push_back({d_scalars, d_points, d_result, d_ws, p.n, p.c, normalize, nl, epoch, 0, exec});
+        hit = &gc.entries.back();
+    }
+    hit->last_use = ++gc.tick;
+    cudaError_t e = cudaGraphLaunch(hit->exec, st);
+    if (launches) *launches = hit->launches;
+    return (int)e;
 }
 
 }  // namespace cbp

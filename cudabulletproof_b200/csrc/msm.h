@@ -52,4 +52,10 @@ int msm_run(const MsmPlan& p, const void* d_scalars, const void* d_points, void*
             int normalize, cudaStream_t stream, int* launches, cudaEvent_t points_ready, int kit_index = 0,
             int flags = 0, void* d_front_workspace = nullptr);
 
+// bpk_msm_device's way in: mid-size calls (2^13 < n < 2^19, latency-bound: 36-70 dependent launches on up to ten streams)
+// replay a CUDA graph of msm_run's launch DAG, captured on first use and cached per device by (buffers, n, window width,
+// normalize); everything else — and every call while the profiler timers are on — goes straight to msm_run.
+int msm_run_cached(const MsmPlan& p, const void* d_scalars, const void* d_points, void* d_result, void* d_workspace,
+                   int normalize, cudaStream_t stream, int* launches);
+
 }  // namespace cbp

@@ -16,6 +16,7 @@ size_t g_used[BPK_PROF_KINDS] = {0};
 constexpr size_t kMaxPairs = 4096;
 }  // namespace
 
+bool prof_enabled() { return g_enabled; }
 void prof_begin(int kind, cudaStream_t st) {
     if (!g_enabled) return;
     std::lock_guard<std::mutex> lk(g_mu);

@@ -51,6 +51,7 @@ uint64_t bpk_kernel_launches(void);
 #define BPK_OPT_DEBUG_VARIANT 12    /* A/B switch for kernels under measurement; 0 = the shipped code */
 #define BPK_OPT_VERIFY_GROUP 13     /* batch verification: proofs per combined identity; -1 auto, 0 or 1 = one by one */
 #define BPK_OPT_MSM_FUSED_FRONT 14   /* 1 (default): scans + segment build of the MSM front end in one cooperative launch; 0: separately */
+#define BPK_OPT_MSM_GRAPH 15        /* 1 (default): device MSMs of 2^13 < n < 2^19 pairs replay a cached CUDA graph; 0: plain launches */
 #define BPK_OPT_MSM_ACC_STREAMS 9   /* 1 / 0: every window group accumulates on its own stream (groups overlap) / in turn; -1 auto */
 int bpk_debug_set_option(int option, long long value);
 /* With BPK_OPT_HOST_REGISTER on, the host-pointer MSM page-locks large pageable input buffers in place the first time

@@ -329,6 +329,37 @@ def test_msm_fused_front_end_matches_separate_kernels(slot_option, slots):
     assert np.array_equal(out[(1, 0)][0], out[(1, 11)][0])
 
 
+def test_msm_cached_launch_graph_replays(oracle):
+    """Device MSMs of 2^13 < n < 2^19 pairs replay a CUDA graph of their launch DAG, cached by (buffers, n, window width)
+    (msm_run_cached; BPK_OPT_MSM_GRAPH = 0: plain launches).  Same bytes as plain launches: on first use (capture), on
+    replays after the buffers' CONTENTS changed, with more live (workspace, buffer) combinations than the cache holds
+    (eviction), and after an option change that alters the DAG (stale graphs are not replayed)."""
+    import torch
+    import cudabulletproof_b200 as cbp
+    lib = cbp.load()
+    n = (1 << 14) + 77
+    pts, _ = cbp.synth_points(n, seed=0x6A)
+    scs = [cbp.synth_scalars(n, seed=0x6B + i, bits=253) for i in range(3)]
+    try:
+        cbp.check(lib.bpk_debug_set_option(15, 0), "set_option")
+        plain_msm = cbp.Msm(n)
+        want = [plain_msm(s, pts).cpu().numpy().copy() for s in scs]
+        cbp.check(lib.bpk_debug_set_option(15, 1), "set_option")
+        msms = [cbp.Msm(n) for _ in range(10)]  # ten workspaces: more entries than the cache keeps
+        buf = scs[0].clone()
+        for rnd in range(3):
+            buf.copy_(scs[rnd])  # same buffer, new contents: the replayed graph must read them
+            for m in msms:
+                got = m(buf, pts).cpu().numpy()
+                assert np.array_equal(got, want[rnd])
+        cbp.check(lib.bpk_debug_set_option(4, 0x666), "set_option")  # other window groups: a different DAG
+        assert np.array_equal(msms[0](buf, pts).cpu().numpy(), want[2])
+    finally:
+        lib.bpk_debug_set_option(4, 0)
+        lib.bpk_debug_set_option(15, 1)
+    torch.cuda.synchronize()
+
+
 def test_msm_slotted_equals_two_pass_at_size(oracle, slot_option):
     """2^18 points, both forced: the slotted and the two-pass front end give identical bytes, for
     252-bit random scalars and for an adversarial input that overflows the slots."""
