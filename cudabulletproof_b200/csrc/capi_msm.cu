@@ -637,7 +637,16 @@ static int msm_host(ge25519* result, const fe25519* scalars_h, const void* point
         };
         int rc = 0;
         if (!staged) {
-            for (size_t c = 0; c < nchunks && rc == 0; c++) rc = (int)copy_scalars(c);
+            {  // all scalars in two copies: fewer, larger transfers (one per chunk: 3.655 ms, two in all: 3.63 ms at 2^20 pairs);
+               // the sorts have slack, the first points do not
+                trace_mark("start", 0, hp.copy);
+                const size_t half_c = nchunks / 2, split = lo_of[half_c];
+                cudaError_t r = cudaMemcpyAsync(hp.d_s, h_s, split * 32, cudaMemcpyHostToDevice, hp.copy);
+                for (size_t c = 0; c < half_c && r == cudaSuccess; c++) r = cudaEventRecord(hp.ev_scalars[c], hp.copy);
+                if (r == cudaSuccess) r = cudaMemcpyAsync(hp.d_s + split * 32, h_s + split * 32, (n - split) * 32, cudaMemcpyHostToDevice, hp.copy);
+                for (size_t c = half_c; c < nchunks && r == cudaSuccess; c++) r = cudaEventRecord(hp.ev_scalars[c], hp.copy);
+                rc = (int)r;
+            }
             for (size_t c = 0; c < nchunks && rc == 0; c++) rc = (int)copy_points(c);
             for (size_t c = 0; c < nchunks && rc == 0; c++) rc = sort_chunk(c);
             for (size_t c = 0; c < nchunks && rc == 0; c++) rc = sum_chunk(c);

@@ -12,6 +12,8 @@ for a in sys.argv[1:]:
         lib.bpk_debug_set_option(10, int(a.split("=")[1]))  # BPK_OPT_HOST_TAPER_LOG2
     if a == "--trace":
         trace = True
+    if a.startswith("--variant="):
+        lib.bpk_debug_set_option(12, int(a.split("=")[1]))  # BPK_OPT_DEBUG_VARIANT
     if a.startswith("--chunk="):
         lib.bpk_debug_set_option(2, int(a.split("=")[1]))  # BPK_OPT_HOST_CHUNK_LOG2
 for lg in [int(a) for a in args] or [16, 18, 19, 20, 22]:
